@@ -1,0 +1,154 @@
+"""ctypes binding of the C-ABI library ``csrc/libcfen_b200.so`` (declared in include/cfen_b200.h).
+
+No torch types cross this boundary: only raw device pointers, sizes and the CUDA stream handle.
+The library is built in-tree by ``__graft_entry__.build()`` / ``csrc/build.py``.  There is no
+fallback: if the library is missing every entry point raises ``RuntimeError``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcfen_b200.so")
+
+_lib = None
+
+# every symbol include/cfen_b200.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "cfen_abi_version", "cfen_last_error",
+    "cfen_plan_create", "cfen_plan_destroy", "cfen_plan_set_weight", "cfen_plan_pack_weights",
+    "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option",
+    "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
+    "cfen_plan_stage_ptr",
+    "cfen_gemm_tf32", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
+    "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_cfsm", "cfen_merge_lg",
+    "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward",
+)
+
+
+class cfen_config(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "struct_size", "device", "max_batch", "height", "width", "n_feats", "hidden_dim_ratio",
+        "num_heads", "patch_dim", "patch_size", "load_size", "flags")]
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "cfen_b200 native library not built: %s is missing. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or python "
+                "cfen_vit_dehazing_b200/csrc/build.py). There is no CPU/eager fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, cp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_char_p
+        L.cfen_abi_version.restype = i32
+        L.cfen_last_error.restype = cp
+        L.cfen_plan_create.argtypes = [ctypes.POINTER(cfen_config), ctypes.POINTER(vp)]
+        L.cfen_plan_destroy.argtypes = [vp]
+        L.cfen_plan_set_weight.argtypes = [vp, cp, vp, i64]
+        L.cfen_plan_pack_weights.argtypes = [vp, vp]
+        L.cfen_plan_workspace_bytes.argtypes = [vp]
+        L.cfen_plan_workspace_bytes.restype = i64
+        L.cfen_plan_launches_per_forward.argtypes = [vp]
+        L.cfen_plan_launches_per_forward.restype = i64
+        L.cfen_plan_set_option.argtypes = [vp, cp, i64]
+        L.cfen_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.cfen_forward_calibrate.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.cfen_forward_u8.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.cfen_plan_stage_ptr.argtypes = [vp, cp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        L.cfen_gemm_tf32.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]
+        L.cfen_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
+        L.cfen_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+        L.cfen_tokenize_local.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+        L.cfen_tokenize_global.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+        L.cfen_conv2d_nhwc.argtypes = [cp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+        L.cfen_cfsm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        L.cfen_merge_lg.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        L.cfen_deform_conv2d_forward.argtypes = [vp, vp, vp, vp] + [i32] * 16 + [vp]
+        L.cfen_modulated_deform_conv2d_forward.argtypes = [vp, vp, vp, vp, vp, vp] + [i32] * 16 + [vp]
+        for name in EXPORTED_SYMBOLS:
+            fn = getattr(L, name)
+            if fn.restype is ctypes.c_int and name not in ("cfen_abi_version",):
+                fn.restype = i32
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().cfen_last_error()
+        raise RuntimeError("cfen_b200 native error %d: %s" % (status, (msg or b"?").decode()))
+
+
+def chunk_images(height, batch):
+    """Images processed per internal pass: bounds the workspace (~70 MB/image at 512x512)."""
+    per = 16 if height <= 512 else 4
+    return max(1, min(per, batch))
+
+
+class Plan:
+    """Opaque per-(device, H, W) execution plan: packed weights + static workspace."""
+
+    def __init__(self, device, height, width, n_feats, hidden_dim_ratio, num_heads, patch_dim,
+                 patch_size, load_size, max_batch):
+        L = lib()
+        cfg = cfen_config(struct_size=ctypes.sizeof(cfen_config), device=device, max_batch=max_batch,
+                          height=height, width=width, n_feats=n_feats,
+                          hidden_dim_ratio=hidden_dim_ratio, num_heads=num_heads, patch_dim=patch_dim,
+                          patch_size=patch_size, load_size=load_size, flags=0)
+        handle = ctypes.c_void_p()
+        check(L.cfen_plan_create(ctypes.byref(cfg), ctypes.byref(handle)))
+        self._h = handle
+        self.weights_version = -1
+        self.needs_calibration = False
+        self.max_batch = max_batch
+
+    def pack(self, tensors, stream):
+        """Register the reference-layout tensors by state_dict name and run the pack kernels."""
+        L = lib()
+        need_cal = False
+        for name, t in tensors.items():
+            if name.endswith(".initialized"):
+                need_cal = need_cal or int(t.item()) == 0
+                continue
+            if not t.is_floating_point():
+                continue
+            if not t.is_contiguous():
+                raise RuntimeError("parameter %s must be contiguous" % name)
+            check(L.cfen_plan_set_weight(self._h, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()))
+        check(L.cfen_plan_pack_weights(self._h, ctypes.c_void_p(stream)))
+        self.needs_calibration = need_cal
+
+    def forward(self, batch, x, xr, xs, xd, stream):
+        check(lib().cfen_forward(self._h, batch, x, xr, xs, xd, ctypes.c_void_p(stream)))
+
+    def calibrate(self, batch, x, xr, xs, xd, stream):
+        check(lib().cfen_forward_calibrate(self._h, batch, x, xr, xs, xd, ctypes.c_void_p(stream)))
+
+    def forward_u8(self, batch, x_u8, xr_u8, xs_u8, xd_u8, stream):
+        check(lib().cfen_forward_u8(self._h, batch, x_u8, xr_u8, xs_u8, xd_u8, ctypes.c_void_p(stream)))
+
+    def set_option(self, name, value):
+        check(lib().cfen_plan_set_option(self._h, name.encode(), int(value)))
+
+    def stage_ptr(self, name):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        check(lib().cfen_plan_stage_ptr(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    @property
+    def workspace_bytes(self):
+        return lib().cfen_plan_workspace_bytes(self._h)
+
+    @property
+    def launches_per_forward(self):
+        return lib().cfen_plan_launches_per_forward(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().cfen_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -1,0 +1,170 @@
+/*
+ * cfen_b200.h - C ABI of libcfen_b200.so: the sm_100a implementation of the CFEN-ViT v3
+ * dehazing generator forward pass.
+ *
+ * The reference (phoenixtreesky7/CFEN-ViT-Dehazing) has no C ABI for this path: the path is the
+ * Python method dec_ipt.forward (models/networks_iid_hlgvit_crs_gd4_cfs_v3.py:392-1020) reached
+ * through define_G (:93-100) from DECHLGVIT.forward (models/model_iid_dehazing.py:140-143).  Its
+ * only native-op precedent is the pybind11 module `deform_conv_cuda`
+ * (dcn/src/deform_conv_cuda.cpp:681-695: free functions returning int, tensors + ints in).
+ * This header is the boundary a host in any language binds instead (ctypes stub:
+ * cfen_vit_dehazing_b200/_native.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; cfen_last_error() gives the text
+ *     (thread-local).  No exceptions, no torch types, plain pointers and sizes only.
+ *   - all pointers named *dev* / in / out are DEVICE pointers on the plan's device; the caller
+ *     owns them.  The library owns only the plan (packed weights + static workspace).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised, and
+ *     nothing is allocated inside cfen_forward*, so a forward is CUDA-graph capturable.
+ *   - activations cross the boundary in the reference's layout: fp32 NCHW, values in [-1, 1].
+ */
+#ifndef CFEN_B200_H
+#define CFEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFEN_ABI_VERSION 1
+
+typedef struct cfen_plan cfen_plan;
+
+/* Mirrors the option flags dec_ipt.__init__ consumes (v3.py:111-246; defaults in
+ * options/base_options.py:16,96-110,191-201).  Supported: n_feats=24, hidden_dim_ratio in {2,4},
+ * num_heads=4, patch_dim=2, load_size = height/2, patch_size = height/16, height == width,
+ * height % 128 == 0.  Anything else -> error (the Python shim raises NotImplementedError). */
+typedef struct cfen_config {
+  int32_t struct_size;       /* sizeof(cfen_config), for forward compatibility            */
+  int32_t device;            /* CUDA device ordinal                                        */
+  int32_t max_batch;         /* images per internal pass; workspace is sized for this      */
+  int32_t height, width;     /* input size baked into pos-embeddings (v3.py:136-246)       */
+  int32_t n_feats;           /* --n_feats                                                   */
+  int32_t hidden_dim_ratio;  /* --hidden_dim_ratio                                          */
+  int32_t num_heads;         /* --num_heads                                                 */
+  int32_t patch_dim;         /* --patch_dim                                                 */
+  int32_t patch_size;        /* --patch_size  (window edge in pixels of every level)       */
+  int32_t load_size;         /* --loadSize                                                  */
+  int32_t flags;             /* reserved, 0                                                 */
+} cfen_config;
+
+int32_t     cfen_abi_version(void);
+const char* cfen_last_error(void);
+
+/* ---- plan lifetime (replaces dec_ipt.__init__ + init_net's .to(device), v3.py:77-83,103) ---- */
+int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out);
+int32_t cfen_plan_destroy(cfen_plan* plan);
+
+/* Register one tensor of the reference state_dict by its key, e.g.
+ * "localvit_encoder_01.encoder.layers.0.self_attn.in_proj_weight".  fp32, contiguous, reference
+ * layout.  Keys the forward never reads (dead decoder weights, query_embed, sub_mean...) are
+ * accepted and ignored.  Replaces load_state_dict (models/base_model.py:114-131). */
+int32_t cfen_plan_set_weight(cfen_plan* plan, const char* key, const void* dev_ptr, int64_t numel);
+
+/* Permute / TF32-round / fold the registered tensors into the kernels' layouts.  Must be called
+ * after all set_weight calls and again whenever the registered tensors change. */
+int32_t cfen_plan_pack_weights(cfen_plan* plan, void* stream);
+
+int64_t cfen_plan_workspace_bytes(const cfen_plan* plan);
+int64_t cfen_plan_launches_per_forward(const cfen_plan* plan); /* kernels per max_batch pass */
+int32_t cfen_plan_set_option(cfen_plan* plan, const char* name, int64_t value);
+
+/* ---- the hot path: dec_ipt.forward (v3.py:392-1020) ----
+ * in  [batch,3,H,W];  xr [batch,3,H,W], xs [batch,1,H,W], xd [batch,3,H,W]  (v3.py:1020). */
+int32_t cfen_forward(cfen_plan* plan, int32_t batch, const float* in,
+                     float* xr, float* xs, float* xd, void* stream);
+
+/* Same, but first initialises every ActNorm2d from the batch statistics of its input and writes
+ * weight/bias back into the registered tensors: the reference's first-forward behaviour
+ * (models/actnorm.py:25-37).  batch must be <= max_batch (statistics span the whole batch). */
+int32_t cfen_forward_calibrate(cfen_plan* plan, int32_t batch, const float* in,
+                               float* xr, float* xs, float* xd, void* stream);
+
+/* Fused pre/post-processing variant: uint8 HWC in ([batch,H,W,3]),
+ * (x/255-0.5)/0.5 as data/base_dataset.py:44-46; uint8 HWC out, (y+1)/2*255 as
+ * util/util.py:22-24 (xs is replicated to 3 channels like tensor2im does). */
+int32_t cfen_forward_u8(cfen_plan* plan, int32_t batch, const uint8_t* in_hwc,
+                        uint8_t* xr_hwc, uint8_t* xs_hwc, uint8_t* xd_hwc, void* stream);
+
+/* Debug/testing: device pointer + element count of a named internal NHWC stage buffer of the
+ * last pass ("xf", "e1", "e2", "e3", "u3r", ...). */
+int32_t cfen_plan_stage_ptr(cfen_plan* plan, const char* name, void** dev_ptr, int64_t* numel);
+
+/* ---- per-kernel entry points (unit parity tests; same kernels the plan launches) ---- */
+
+/* C[M,N] = epi(A[M,K] * W[N,K]^T): nn.Linear (v3.py:1143,1173,1387) on TF32 tensor cores.
+ * epi: + bias[N]; relu; + residual[M,N]; + pos[(m % pos_period), N].  Null pointers skip. */
+int32_t cfen_gemm_tf32(const float* A, const float* W, float* C, int32_t M, int32_t N, int32_t K,
+                       const float* bias, const float* residual, const float* pos,
+                       int32_t pos_period, int32_t relu, void* stream);
+
+/* y[rows,E] = LayerNorm(x) * gamma + beta, biased variance (nn.LayerNorm, v3.py:1370-1371). */
+int32_t cfen_layernorm(const float* x, float* y, const float* gamma, const float* beta,
+                       int32_t rows, int32_t E, float eps, void* stream);
+
+/* softmax(q k^T / sqrt(hd)) v per (sequence, head) on packed qkv[nseq*L, 3E] -> out[nseq*L, E]
+ * (nn.MultiheadAttention(bias=False) core, v3.py:1364,1385). */
+int32_t cfen_attention(const float* qkv, float* out, int32_t nseq, int32_t L, int32_t E,
+                       int32_t heads, void* stream);
+
+/* Window partition + unfold(p=2) of an NHWC map into tokens [B*nW*L, 4C] (v3.py:1025-1040,1140);
+ * feature order (ky,kx,c). */
+int32_t cfen_tokenize_local(const float* map_nhwc, float* tokens, int32_t B, int32_t H, int32_t W,
+                            int32_t C, int32_t window, void* stream);
+
+/* AvgPool2 twice + unfold(p=4) of an NHWC map into tokens [B*(H/16)*(W/16), 16C] (v3.py:1274-1275). */
+int32_t cfen_tokenize_global(const float* map_nhwc, float* tokens, int32_t B, int32_t H, int32_t W,
+                             int32_t C, void* stream);
+
+/* One convolution-family layer on NHWC fp32 maps, selected by `kind`:
+ *   "conv3x3_12_12", "ds_12_24", "ds_24_48", "ds_48_96", "up_96_48", "up_48_24", "up_24_12",
+ *   "head5x5", "tail7x7_3", "tail7x7_1", "skip_96_48", "skip_48_24"
+ * weight/bias in the reference layout (Conv2d [Cout,Cin,kh,kw]; ConvTranspose2d [Cin,Cout,4,4]);
+ * scale/shift: optional per-channel affine applied to conv+bias (ActNorm), flags: bit0 relu,
+ * bit1 tanh, bit2 add `extra` after activation (residual), bit3 output NCHW, bit4 input NCHW,
+ * bit5 `extra` is a second input summed (SUM2) / concatenated (skip) before the conv. */
+int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const float* extra, const float* weight,
+                         const float* bias, const float* an_weight, const float* an_bias,
+                         float* out, int32_t B, int32_t H, int32_t W, int32_t flags, void* stream);
+/* (argument order in the .so: kind,in,extra,weight,bias,an_weight,an_bias,out,B,H,W,flags,stream) */
+
+/* CFSM2G (v3.py:1502-1517): out = x0 + x1*sig1 + x2*sig2 on NHWC maps; w = the 8 bias-free 1x1
+ * weights concatenated in state_dict order (avg_cf1.0, avg_cf1.2, avg_cf2.0, avg_cf2.2,
+ * max_cf1.0, max_cf1.2, max_cf2.0, max_cf2.2). */
+int32_t cfen_cfsm(const float* x0, const float* x1, const float* x2, const float* w, float* out,
+                  float* scratch, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* lgcat merge (v3.py:488): out = relu(actnorm(conv1x1(cat(local, up4(global))))) + x, with
+ * local/global given as final token matrices of the two ViTs. */
+int32_t cfen_merge_lg(const float* local_tokens, const float* global_tokens, const float* x,
+                      const float* weight, const float* bias, const float* an_weight,
+                      const float* an_bias, float* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                      int32_t window, void* stream);
+
+/* ---- dcn -------------------------------------------------------
+ * Forward entry points mirroring deform_conv_forward_cuda (dcn/src/deform_conv_cuda.cpp:151-156)
+ * and modulated_deform_conv_cuda_forward (:486-492).  NCHW fp32; offset
+ * [B, dg*2*kh*kw, Ho, Wo] (channel 2t = dy, 2t+1 = dx of tap t); mask [B, dg*kh*kw, Ho, Wo].
+ * The sampled columns are never materialised: gather and contraction are one kernel. */
+int32_t cfen_deform_conv2d_forward(const float* input, const float* weight, const float* offset,
+                                   float* output, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                                   int32_t Cout, int32_t kH, int32_t kW, int32_t strideH,
+                                   int32_t strideW, int32_t padH, int32_t padW, int32_t dilH,
+                                   int32_t dilW, int32_t group, int32_t deformable_group,
+                                   int32_t im2col_step, void* stream);
+int32_t cfen_modulated_deform_conv2d_forward(const float* input, const float* weight,
+                                             const float* bias, const float* offset,
+                                             const float* mask, float* output, int32_t B,
+                                             int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                             int32_t kH, int32_t kW, int32_t strideH,
+                                             int32_t strideW, int32_t padH, int32_t padW,
+                                             int32_t dilH, int32_t dilW, int32_t group,
+                                             int32_t deformable_group, int32_t with_bias,
+                                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFEN_B200_H */
