@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: CFEN-ViT v3 generator forward, 512x512 images/s (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward pass of the generator over one per-GPU batch of synthetic hazy images
+(BASELINE.json configs[3]: v3, hidden_dim_ratio=4, 512x512, image-sharded with replicated weights
+and no collective on the data path => weak scaling, per-GPU batch fixed).  `value` is whole-job
+images/s with inputs resident in HBM; `e2e` is the same metric through the public module API with
+pinned HOST inputs and outputs (H2D + D2H inside the timed region).  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference algorithm's CPU implementation (the oracle port of
+models/networks_iid_hlgvit_crs_gd4_cfs_v3.py; the reference checkout itself does not travel to the
+GPU box) on the host cores, one image per step.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SIZE = 512
+HR = 4
+FLOPS_PER_IMAGE = {(512, 4): 120.853e9, (512, 2): 85.067e9, (1024, 4): 624.213e9}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CFEN_BENCH_BATCH", 128)),
+                    help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=SIZE)
+    ap.add_argument("--hr", type=int, default=HR)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+def make_opt(hr, size):
+    """The reference's option namespace for this workload (options/base_options.py names)."""
+    return argparse.Namespace(n_feats=24, hidden_dim_ratio=hr, patch_size=size // 16, patch_dim=2, num_heads=4,
+                              num_layers=1, num_queries=1, dropout_rate=0, no_mlp=False, pos_every=False,
+                              no_pos=False, no_norm=False, loadSize=size // 2, rgb_range=255, n_colors=3,
+                              init_type="kaiming", gpu_ids=[])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"],
+                "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_forward(size, hr, seconds_budget=20.0, min_iters=3, max_iters=30):
+    """Times the oracle port of the reference forward on the host cores (B=1)."""
+    import torch
+    import cfen_vit_dehazing_b200 as prod
+    from oracle import cfen_oracle as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    opt = orc.default_opt(hr, size)
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = prod.define_G(opt, prod.common.default_conv)   # parameter containers only
+    x0, x1 = orc.make_inputs(size, [1, 1])
+    sd = orc.prime(net.state_dict(), x0)                       # also the warm-up forward
+    times = []
+    t_end = time.time() + seconds_budget
+    while len(times) < min_iters or (time.time() < t_end and len(times) < max_iters):
+        t = time.perf_counter()
+        orc.forward(sd, x1)
+        times.append(time.perf_counter() - t)
+    return times, threads
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    from oracle import cfen_oracle as orc
+    import cfen_vit_dehazing_b200 as prod
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    opt = orc.default_opt(args.hr, args.size)
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = prod.define_G(opt, prod.common.default_conv)
+    x0, x1 = orc.make_inputs(args.size, [1, 1])
+    sd = orc.prime(net.state_dict(), x0)
+    for _ in range(max(0, args.warmup)):
+        orc.forward(sd, x1)
+    times = []
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        orc.forward(sd, x1)
+        times.append(time.perf_counter() - t)
+    total = sum(times)
+    val = args.steps / total
+    sample = "1 image (1x3x%dx%d) per step, %d steps, fp32, torch CPU %d threads" % (args.size, args.size,
+                                                                                    args.steps, threads)
+    line = {
+        "impl": "reference", "metric": "images_per_s_%dx%d" % (args.size, args.size), "value": val,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "cpu_model": cpu_model_name(),
+                   "note": "oracle port of the reference forward (reference checkout does not travel to the GPU box)"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+                         "p50_s": statistics.median(times), "min_s": min(times)},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return ("v3 generator (iid_hlgvit_crs_gd4_cfs_v3) n_feats=24 hidden_dim_ratio=%d, %dx%d, per-GPU batch %d "
+            "(BASELINE configs[3]: image-sharded, replicated weights)" % (args.hr, args.size, args.size, args.batch))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import cfen_vit_dehazing_b200 as prod
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    size, hr, B = args.size, args.hr, args.batch
+    opt = make_opt(hr, size)
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = prod.define_G(opt, prod.common.default_conv).to(dev)
+    g = torch.Generator().manual_seed(123)
+    x0 = (2 * torch.rand(1, 3, size, size, generator=g) - 1)
+    g2 = torch.Generator().manual_seed(1000 + rank)
+    host_in = (2 * torch.rand(B, 3, size, size, generator=g2) - 1).pin_memory()
+    with torch.no_grad():
+        net(x0.to(dev))                      # first forward: ActNorm data-dependent init on the GPU
+        x_dev = host_in.to(dev)
+        plan = net._plan_for(dev, size, size, B)
+        stream = torch.cuda.current_stream(dev)
+
+        # ---------------- device-resident throughput
+        plan.set_option("timing", 1)
+        for _ in range(max(3, args.warmup)):
+            out = net(x_dev)
+        plan.set_option("timing_reset", 1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            e0.record(stream)
+            for _ in range(args.steps):
+                out = net(x_dev)
+            e1.record(stream)
+            barrier()
+        ms_total = e0.elapsed_time(e1)
+        prof = plan.profile()
+        plan.set_option("timing", 0)
+        chunks = (B + plan.max_batch - 1) // plan.max_batch
+        launches_per_step = plan.launches_per_forward * chunks
+        finite = all(bool(torch.isfinite(o).all()) for o in out)
+
+        # ---------------- end to end through the module API with host buffers
+        host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in out]
+        h2d = host_in.numel() * 4
+        d2h = sum(o.numel() * 4 for o in host_out)
+
+        def e2e_step():
+            xd = host_in.to(dev, non_blocking=True)
+            ys = net(xd)
+            for h, y in zip(host_out, ys):
+                h.copy_(y, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record(stream)
+        barrier()
+        e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
+
+        # ---------------- batch-1 latency, CUDA-graph replay (BASELINE configs[1])
+        lat = None
+        if rank == 0 and not args.no_latency:
+            x1 = x_dev[:1].contiguous()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    net(x1)
+            stream.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                y1 = net(x1)
+            for _ in range(20):
+                graph.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(200):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); graph.replay(); b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            lat = {"p50_ms": statistics.median(ts), "min_ms": min(ts), "p90_ms": sorted(ts)[179],
+                   "replays": 200, "mode": "cuda_graph"}
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = t.tolist()
+        fin = torch.tensor([1 if finite else 0], device=dev)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        finite = bool(fin.item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        images = B * world * args.steps
+        value = images / (ms_total / 1e3)
+        # dominant kernel class -> roofline
+        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        name, d = dom
+        nl = max(1, d["launches"])
+        t_s = d["ms"] / 1e3
+        tf = d["flops"] / t_s / 1e12 if t_s > 0 else 0.0
+        gbs = d["bytes"] / t_s / 1e9 if t_s > 0 else 0.0
+        tensor_bound = d["flops"] / (peaks["tf_sustained"] * 1e12) >= d["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        roof = ({"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                 "frac": tf / peaks["tf_sustained"]} if tensor_bound else
+                {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": gbs / peaks["hbm_gbs"]})
+        roof.update({"kernel": name, "traffic": None, "launches": d["launches"],
+                     "avg_launch_us": 1e3 * d["ms"] / nl, "peak_source": peaks["source"],
+                     "note": "algorithmic flops/bytes per launch over CUDA-event launch time in the timed region; "
+                             "peak = measured dense bf16 (sustained); TF32 operands run at half the bf16 rate"})
+        tprof = sum(v["ms"] for v in prof.values())
+        breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / tprof if tprof else 0,
+                         "launches_per_step": v["launches"] / args.steps,
+                         "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else 0,
+                         "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else 0}
+                     for k, v in prof.items() if v["launches"]}
+        line = {
+            "metric": "images_per_s_%dx%d" % (size, size), "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "inputs_larger_than_l2 (%.0f MB per step per GPU)" % (h2d / 1e6),
+                       "weights": "seeded random init (seed 1), ActNorm initialised by the first GPU forward",
+                       "algorithmic_gflop_per_image": FLOPS_PER_IMAGE.get((size, hr), 0) / 1e9},
+            "clocks": clocks.summary(),
+            "e2e": {"value": images / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roof,
+            "kernel_breakdown": breakdown,
+            "whole_net_tflops": value / world * FLOPS_PER_IMAGE.get((size, hr), 0) / 1e12,
+            "outputs_finite": finite,
+        }
+        if lat:
+            line["latency_batch1"] = lat
+        if world == 1 and not args.no_cpu_baseline:
+            times, threads = cpu_reference_forward(size, hr)
+            line["cpu_baseline"] = {
+                "value": 1.0 / statistics.median(times), "unit": "images/s", "cores": threads, "kind": "port",
+                "sample": "%d forwards of 1x3x%dx%d (BASELINE configs[0]) on %s, torch CPU fp32" % (
+                    len(times), size, size, cpu_model_name()),
+                "p50_s": statistics.median(times), "min_s": min(times)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

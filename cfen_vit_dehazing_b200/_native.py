@@ -17,6 +17,7 @@ EXPORTED_SYMBOLS = (
     "cfen_abi_version", "cfen_last_error",
     "cfen_plan_create", "cfen_plan_destroy", "cfen_plan_set_weight", "cfen_plan_pack_weights",
     "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option",
+    "cfen_plan_profile_json",
     "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
     "cfen_plan_stage_ptr",
     "cfen_gemm_tf32", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
@@ -53,6 +54,7 @@ def lib():
         L.cfen_plan_launches_per_forward.argtypes = [vp]
         L.cfen_plan_launches_per_forward.restype = i64
         L.cfen_plan_set_option.argtypes = [vp, cp, i64]
+        L.cfen_plan_profile_json.argtypes = [vp, cp, i64]
         L.cfen_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_forward_calibrate.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_forward_u8.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -62,15 +64,13 @@ def lib():
         L.cfen_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.cfen_tokenize_local.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
         L.cfen_tokenize_global.argtypes = [vp, vp, i32, i32, i32, i32, vp]
-        L.cfen_conv2d_nhwc.argtypes = [cp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+        L.cfen_conv2d_nhwc.argtypes = [cp] + [vp] * 7 + [i32] * 4 + [vp]
         L.cfen_cfsm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
-        L.cfen_merge_lg.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        L.cfen_merge_lg.argtypes = [vp] * 8 + [i32] * 5 + [vp]
         L.cfen_deform_conv2d_forward.argtypes = [vp, vp, vp, vp] + [i32] * 16 + [vp]
         L.cfen_modulated_deform_conv2d_forward.argtypes = [vp, vp, vp, vp, vp, vp] + [i32] * 16 + [vp]
         for name in EXPORTED_SYMBOLS:
-            fn = getattr(L, name)
-            if fn.restype is ctypes.c_int and name not in ("cfen_abi_version",):
-                fn.restype = i32
+            getattr(L, name)  # AttributeError here means the .so is stale: rebuild
         _lib = L
     return _lib
 
@@ -131,6 +131,13 @@ class Plan:
 
     def set_option(self, name, value):
         check(lib().cfen_plan_set_option(self._h, name.encode(), int(value)))
+
+    def profile(self):
+        """Per-kernel-class timing of the last forward (needs set_option("timing", 1))."""
+        import json
+        buf = ctypes.create_string_buffer(4096)
+        check(lib().cfen_plan_profile_json(self._h, buf, 4096))
+        return json.loads(buf.value.decode())
 
     def stage_ptr(self, name):
         p, n = ctypes.c_void_p(), ctypes.c_int64()

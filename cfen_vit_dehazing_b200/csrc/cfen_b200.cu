@@ -1,0 +1,963 @@
+// libcfen_b200.so - plan, weight packing, forward orchestration and the C ABI (include/cfen_b200.h).
+//
+// Forward graph = reference dec_ipt.forward (models/networks_iid_hlgvit_crs_gd4_cfs_v3.py:392-1020)
+// re-expressed over NHWC fp32 maps and token matrices:
+//   head -> ds_e01 -> [block e1] -> ds_e02 -> [block e2] -> ds_e03 -> [block e3]
+//   R,S: [block d3] -> up(IN) -> skip1x1 -> [block d2] -> up(AN) -> skip1x1 -> [block d1] -> up(AN, +xf) -> tail
+//   D  : [block d3] -> up(IN) -> CFSM     -> [block d2] -> up(AN) -> CFSM     -> [block d1] -> up(AN, +xf) -> tail
+//   block(x) = relu(actnorm(conv1x1(cat(LViT_windows(x), up4(GViT(pool4(x))))))) + x
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cfen_b200.h"
+#include "common.cuh"
+#include "conv_igemm.cuh"
+#include "dcn.cuh"
+#include "gemm_tf32.cuh"
+#include "map_kernels.cuh"
+#include "vit_kernels.cuh"
+
+using namespace cfen;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define RET(expr)              \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+static int ew_blocks(long long n, int threads = 256) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static cudaError_t set_kernel_attributes() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<128, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmTile<128, 96>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<64, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmTile<64, 96>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                AttnCfg<24>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                AttnCfg<96>::SMEM_BYTES)) != cudaSuccess) return e;
+#define SETC(S) if ((e = conv_set_attr<S>()) != cudaSuccess) return e;
+  SETC(ConvHead5x5) SETC(Conv3x3_12) SETC(ConvDs12_24) SETC(ConvDs24_48) SETC(ConvDs48_96)
+  SETC(ConvUp96_48) SETC(ConvUp48_24) SETC(ConvUp24_12) SETC(ConvLg1) SETC(ConvLg2) SETC(ConvLg3)
+  SETC(ConvSk96_48) SETC(ConvSk48_24) SETC(ConvTail7_3) SETC(ConvTail7_1)
+#undef SETC
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+enum ConvKind { K_HEAD5, K_C3, K_DS1, K_DS2, K_DS3, K_UP3, K_UP2, K_UP1, K_LG1, K_LG2, K_LG3,
+                K_SK3, K_SK2, K_T3, K_T1, K_COUNT };
+
+static int conv_wpack_floats(int kind) {
+  switch (kind) {
+    case K_HEAD5: return ConvHead5x5::WPACK_FLOATS; case K_C3: return Conv3x3_12::WPACK_FLOATS;
+    case K_DS1: return ConvDs12_24::WPACK_FLOATS;   case K_DS2: return ConvDs24_48::WPACK_FLOATS;
+    case K_DS3: return ConvDs48_96::WPACK_FLOATS;   case K_UP3: return ConvUp96_48::WPACK_FLOATS;
+    case K_UP2: return ConvUp48_24::WPACK_FLOATS;   case K_UP1: return ConvUp24_12::WPACK_FLOATS;
+    case K_LG1: return ConvLg1::WPACK_FLOATS;       case K_LG2: return ConvLg2::WPACK_FLOATS;
+    case K_LG3: return ConvLg3::WPACK_FLOATS;       case K_SK3: return ConvSk96_48::WPACK_FLOATS;
+    case K_SK2: return ConvSk48_24::WPACK_FLOATS;   case K_T3: return ConvTail7_3::WPACK_FLOATS;
+    case K_T1: return ConvTail7_1::WPACK_FLOATS;
+  }
+  return 0;
+}
+static int conv_cout(int kind) {
+  switch (kind) {
+    case K_HEAD5: case K_C3: case K_UP1: return 12;
+    case K_DS1: case K_UP2: case K_LG1: case K_SK2: return 24;
+    case K_DS2: case K_UP3: case K_LG2: case K_SK3: return 48;
+    case K_DS3: case K_LG3: return 96;
+    case K_T3: return 3; case K_T1: return 1;
+  }
+  return 0;
+}
+
+static cudaError_t conv_pack_dispatch(int kind, const float* src, float* dst, cudaStream_t st) {
+#define PK(S, CS) conv_pack_kernel<S><<<ew_blocks(S::WPACK_FLOATS), 256, 0, st>>>(src, dst, CS); break;
+  switch (kind) {
+    case K_HEAD5: PK(ConvHead5x5, 3) case K_C3: PK(Conv3x3_12, 12) case K_DS1: PK(ConvDs12_24, 12)
+    case K_DS2: PK(ConvDs24_48, 24) case K_DS3: PK(ConvDs48_96, 48) case K_UP3: PK(ConvUp96_48, 96)
+    case K_UP2: PK(ConvUp48_24, 48) case K_UP1: PK(ConvUp24_12, 24) case K_LG1: PK(ConvLg1, 48)
+    case K_LG2: PK(ConvLg2, 96) case K_LG3: PK(ConvLg3, 192) case K_SK3: PK(ConvSk96_48, 96)
+    case K_SK2: PK(ConvSk48_24, 48) case K_T3: PK(ConvTail7_3, 12) case K_T1: PK(ConvTail7_1, 12)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PK
+  return cudaGetLastError();
+}
+
+static cudaError_t conv_launch_dispatch(int kind, const ConvArgs& a, cudaStream_t st) {
+  switch (kind) {
+    case K_HEAD5: return launch_conv<ConvHead5x5>(a, st); case K_C3: return launch_conv<Conv3x3_12>(a, st);
+    case K_DS1: return launch_conv<ConvDs12_24>(a, st);   case K_DS2: return launch_conv<ConvDs24_48>(a, st);
+    case K_DS3: return launch_conv<ConvDs48_96>(a, st);   case K_UP3: return launch_conv<ConvUp96_48>(a, st);
+    case K_UP2: return launch_conv<ConvUp48_24>(a, st);   case K_UP1: return launch_conv<ConvUp24_12>(a, st);
+    case K_LG1: return launch_conv<ConvLg1>(a, st);       case K_LG2: return launch_conv<ConvLg2>(a, st);
+    case K_LG3: return launch_conv<ConvLg3>(a, st);       case K_SK3: return launch_conv<ConvSk96_48>(a, st);
+    case K_SK2: return launch_conv<ConvSk48_24>(a, st);   case K_T3: return launch_conv<ConvTail7_3>(a, st);
+    case K_T1: return launch_conv<ConvTail7_1>(a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+static int conv_wpack_k(int kind) {  // contraction length (taps * input channels) per output pixel
+  switch (kind) {
+    case K_HEAD5: return 75; case K_C3: return 108; case K_DS1: return 108; case K_DS2: return 216;
+    case K_DS3: return 432; case K_UP3: return 384; case K_UP2: return 192; case K_UP1: return 96;
+    case K_LG1: return 48; case K_LG2: return 96; case K_LG3: return 192; case K_SK3: return 96;
+    case K_SK2: return 48; case K_T3: case K_T1: return 588;
+  }
+  return 0;
+}
+static double conv_cin_bytes(int kind) {  // input floats read per tile-domain pixel (compulsory)
+  switch (kind) {
+    case K_HEAD5: return 3; case K_C3: return 12; case K_DS1: return 12 * 4; case K_DS2: return 24 * 4;
+    case K_DS3: return 48 * 4; case K_UP3: return 96; case K_UP2: return 48; case K_UP1: return 48;
+    case K_LG1: return 24 + 24 / 16.0; case K_LG2: return 48 + 48 / 16.0; case K_LG3: return 96 + 96 / 16.0;
+    case K_SK3: return 96; case K_SK2: return 48; case K_T3: case K_T1: return 12;
+  }
+  return 0;
+}
+static int conv_parts(int kind, int H, int W) {  // H, W = tile domain
+  const int tiles = (H / 8) * (W / 16);
+  return (kind == K_UP3 || kind == K_UP2 || kind == K_UP1) ? tiles * 4 : tiles;
+}
+
+enum ProfClass { PC_GEMM, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"gemm_tf32", "attention", "layernorm", "tokenize", "conv_igemm",
+                                           "merge_lg", "instnorm", "cfsm", "misc"};
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+
+struct ConvLayer {
+  int kind = 0;
+  std::string wkey, bkey, ankey;  // ankey: ActNorm module prefix ("" = none)
+  float *wpack = nullptr, *scale = nullptr, *shift = nullptr;
+  const float* bias_src = nullptr;  // registered tensors (reference layout)
+  float *an_w = nullptr, *an_b = nullptr;
+};
+
+struct VitW {
+  std::string prefix;
+  int E = 0, hid = 0, L = 0, heads = 0, C = 0, P2 = 0;
+  float *w_le, *b_le, *pos, *ln1g, *ln1b, *w_in, *w_out, *w1, *b1, *w2, *b2, *ln2g, *ln2b, *wm0, *bm0,
+      *wm3, *bm3;
+};
+
+struct TokWs { float *t0, *t1, *h, *qkv, *o, *f; };
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  float* take(size_t floats) {
+    size_t bytes = (floats * sizeof(float) + 255) & ~(size_t)255;
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct cfen_plan {
+  cfen_config cfg;
+  int H, W, nbmax, hr, win;
+  int Hl[4], Cl[4];  // level 1..3 map size / channels
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> reg;
+  Arena wa, ws;  // packed weights, workspace
+  bool allocated = false, packed = false;
+  VitW lvit[12], gvit[12];
+  std::map<std::string, ConvLayer> conv;
+  float* cfsm_w[2] = {nullptr, nullptr};  // d03d (C=48), d02d (C=24): 8 weights concatenated
+  float* ones = nullptr;
+  // workspace
+  TokWs lws, gws;
+  std::map<std::string, std::pair<float*, int64_t>> stage;  // named maps (per-image floats)
+  float *partials = nullptr, *mean_rstd = nullptr, *gates = nullptr, *cfsm_part = nullptr;
+  float *u8_in = nullptr, *u8_xr = nullptr, *u8_xs = nullptr, *u8_xd = nullptr;
+  long long launches = 0, launches_last = 0;
+  bool calibrating = false;
+  // optional per-launch CUDA-event timing (cfen_plan_set_option("timing", 1))
+  bool timing = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+};
+
+static const char* kStages[12] = {"encoder_01", "encoder_02", "encoder_03", "decoder_03r", "decoder_02r",
+                                  "decoder_01r", "decoder_03s", "decoder_02s", "decoder_01s",
+                                  "decoder_03d", "decoder_02d", "decoder_01d"};
+static int stage_level(const char* s) {
+  const size_t n = strlen(s);
+  const char c = s[n - 1];
+  return (c >= '0' && c <= '9') ? c - '0' : s[n - 2] - '0';
+}
+static std::string stage_tag(const char* s) {  // encoder_01 -> e01, decoder_03r -> d03r
+  std::string t(s);
+  if (t.compare(0, 7, "encoder") == 0) return "e" + t.substr(8);
+  return "d" + t.substr(8);
+}
+
+static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
+  const int H = p->H, hr = p->hr, nb = p->nbmax;
+  if (weights) {
+    Arena& a = p->wa;
+    a.off = 0;
+    for (int i = 0; i < 12; ++i) {
+      for (int g = 0; g < 2; ++g) {
+        VitW& v = g ? p->gvit[i] : p->lvit[i];
+        const int lvl = stage_level(kStages[i]);
+        v.prefix = std::string(g ? "globalvit_" : "localvit_") + kStages[i];
+        v.C = p->Cl[lvl];
+        v.P2 = g ? 16 : 4;
+        v.E = v.C * v.P2;
+        v.heads = p->cfg.num_heads << (lvl - 1);
+        v.hid = v.E * hr;
+        if (g && i == 1) v.hid = v.C * 4 * hr;  // globalvit_encoder_02 quirk (v3.py:200)
+        v.L = g ? (p->Hl[lvl] / 16) * (p->Hl[lvl] / 16) : (p->win / 2) * (p->win / 2);
+        const size_t E = v.E, hd = v.hid;
+        v.w_le = a.take(E * E); v.b_le = a.take(E); v.pos = a.take((size_t)v.L * E);
+        v.ln1g = a.take(E); v.ln1b = a.take(E); v.w_in = a.take(3 * E * E); v.w_out = a.take(E * E);
+        v.w1 = a.take(hd * E); v.b1 = a.take(hd); v.w2 = a.take(E * hd); v.b2 = a.take(E);
+        v.ln2g = a.take(E); v.ln2b = a.take(E); v.wm0 = a.take(hd * E); v.bm0 = a.take(hd);
+        v.wm3 = a.take(E * hd); v.bm3 = a.take(E);
+      }
+    }
+    for (auto& kv : p->conv) {
+      ConvLayer& c = kv.second;
+      c.wpack = a.take(conv_wpack_floats(c.kind));
+      c.scale = a.take(96);
+      c.shift = a.take(96);
+    }
+    p->cfsm_w[0] = a.take(8 * 12 * 48);
+    p->cfsm_w[1] = a.take(8 * 6 * 24);
+    p->ones = a.take(96);
+  }
+  if (workspace) {
+    Arena& a = p->ws;
+    a.off = 0;
+    const size_t HH = (size_t)H * H;
+    // local token workspace (M*E is largest on level 1: 6*H*H floats per image)
+    const size_t lt = 6 * HH * nb;
+    p->lws.t0 = a.take(lt); p->lws.t1 = a.take(lt); p->lws.h = a.take(lt); p->lws.o = a.take(lt);
+    p->lws.qkv = a.take(3 * lt); p->lws.f = a.take(lt * hr);
+    const size_t gt = (size_t)(H / 32) * (H / 32) * 384 * nb;  // global: Lg*E largest on level 1
+    p->gws.t0 = a.take(gt); p->gws.t1 = a.take(gt); p->gws.h = a.take(gt); p->gws.o = a.take(gt);
+    p->gws.qkv = a.take(3 * gt); p->gws.f = a.take(gt * hr);
+    auto add = [&](const char* name, size_t per_image) {
+      p->stage[name] = std::make_pair(a.take(per_image * nb), (int64_t)per_image);
+    };
+    const size_t F = HH * 12, M1 = (size_t)p->Hl[1] * p->Hl[1] * 24, M2 = (size_t)p->Hl[2] * p->Hl[2] * 48,
+                 M3 = (size_t)p->Hl[3] * p->Hl[3] * 96;
+    add("f0", F); add("f1", F); add("f2", F);
+    add("xf", M1); add("e1", M1); add("e1d", M2); add("e2", M2); add("e2d", M3); add("e3", M3);
+    for (const char* br : {"r", "s", "d"}) {
+      std::string b(br);
+      add(("d3" + b).c_str(), M3); add(("u3" + b).c_str(), M2); add(("d2in" + b).c_str(), M2);
+      add(("d2" + b).c_str(), M2); add(("u2" + b).c_str(), M1); add(("d1in" + b).c_str(), M1);
+      add(("d1" + b).c_str(), M1);
+    }
+    const size_t parts_max = (size_t)(H / 8) * (H / 16) * 2 * 12;  // tail conv / up_24_12 (4 phases on H/2)
+    p->partials = a.take(parts_max * nb * 2);
+    p->mean_rstd = a.take((size_t)nb * 2 * 96);
+    p->gates = a.take((size_t)nb * 2 * 48);
+    p->cfsm_part = a.take((size_t)nb * 64 * 2 * 48);
+    p->u8_in = a.take(HH * 3 * nb); p->u8_xr = a.take(HH * 3 * nb);
+    p->u8_xs = a.take(HH * nb); p->u8_xd = a.take(HH * 3 * nb);
+  }
+}
+
+static void plan_declare_convs(cfen_plan* p) {
+  auto add = [&](const std::string& name, int kind, const std::string& w, bool bias, const std::string& an) {
+    ConvLayer c;
+    c.kind = kind;
+    c.wkey = w + ".weight";
+    c.bkey = bias ? w + ".bias" : "";
+    c.ankey = an;
+    p->conv[name] = c;
+  };
+  add("head.0.0", K_HEAD5, "head.0.0", true, "");
+  add("head.0.1.body.0", K_C3, "head.0.1.body.0", true, "");
+  add("head.0.1.body.2", K_C3, "head.0.1.body.2", true, "");
+  add("ds_conv_e01", K_DS1, "ds_conv_e01.0", true, "");
+  add("ds_conv_e02", K_DS2, "ds_conv_e02.0", true, "");
+  add("ds_conv_e03", K_DS3, "ds_conv_e03.0", true, "");
+  for (int i = 0; i < 12; ++i) {
+    const int lvl = stage_level(kStages[i]);
+    const std::string n = "lgcat_conv_" + stage_tag(kStages[i]);
+    add(n, lvl == 1 ? K_LG1 : (lvl == 2 ? K_LG2 : K_LG3), n + ".0", true, n + ".1");
+  }
+  for (const char* br : {"r", "s", "d"}) {
+    std::string b(br);
+    add("us_conv_d03" + b, K_UP3, "us_conv_d03" + b + ".0", true, "");
+    add("us_conv_d02" + b, K_UP2, "us_conv_d02" + b + ".0", true, "us_conv_d02" + b + ".1");
+    add("us_conv_d01" + b, K_UP1, "us_conv_d01" + b + ".0", true, "us_conv_d01" + b + ".1");
+  }
+  for (const char* br : {"r", "s"}) {
+    std::string b(br);
+    add("sk_conv_d03" + b, K_SK3, "sk_conv_d03" + b + ".0", true, "sk_conv_d03" + b + ".1");
+    add("sk_conv_d02" + b, K_SK2, "sk_conv_d02" + b + ".0", true, "sk_conv_d02" + b + ".1");
+  }
+  add("tail_R.c1", K_C3, "tail_R.0.1", true, "tail_R.0.2");
+  add("tail_R.c2", K_T3, "tail_R.0.5", true, "");
+  add("tail_D.c1", K_C3, "tail_D.0.1", true, "tail_D.0.2");
+  add("tail_D.c2", K_T3, "tail_D.0.5", true, "");
+  add("tail_S.c1", K_C3, "tail_S.0.1", true, "");
+  add("tail_S.c2", K_T1, "tail_S.0.4", true, "");
+}
+
+extern "C" int32_t cfen_abi_version(void) { return CFEN_ABI_VERSION; }
+extern "C" const char* cfen_last_error(void) { return g_err; }
+
+extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
+  if (!cfg || !out) return fail(1, "cfen_plan_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(cfen_config)) return fail(1, "cfen_config size mismatch");
+  if (cfg->n_feats != 24) return fail(3, "unsupported n_feats=%d (24 only)", cfg->n_feats);
+  if (cfg->hidden_dim_ratio != 2 && cfg->hidden_dim_ratio != 4)
+    return fail(3, "unsupported hidden_dim_ratio=%d (2 or 4)", cfg->hidden_dim_ratio);
+  if (cfg->num_heads != 4 || cfg->patch_dim != 2) return fail(3, "num_heads/patch_dim must be 4/2");
+  if (cfg->height != cfg->width || cfg->height % 128 != 0 || cfg->height < 128)
+    return fail(3, "input must be square with edge a multiple of 128 (got %dx%d)", cfg->height, cfg->width);
+  if (cfg->load_size * 2 != cfg->height || cfg->patch_size * 16 != cfg->height)
+    return fail(3, "loadSize must be H/2 and patch_size H/16 (got %d, %d for H=%d)", cfg->load_size,
+                cfg->patch_size, cfg->height);
+  if (cfg->max_batch < 1) return fail(1, "max_batch must be >= 1");
+  CU(cudaSetDevice(cfg->device));
+  int major = 0;
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+  if (major != 10) return fail(4, "libcfen_b200 needs an sm_100 device (found sm_%d*)", major);
+  CU(set_kernel_attributes());
+
+  cfen_plan* p = new cfen_plan();
+  p->cfg = *cfg;
+  p->H = cfg->height; p->W = cfg->width; p->nbmax = cfg->max_batch; p->hr = cfg->hidden_dim_ratio;
+  p->win = cfg->patch_size;
+  for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
+  plan_declare_convs(p);
+  plan_layout(p, true, true);  // dry run: sizes
+  const size_t wbytes = p->wa.off, sbytes = p->ws.off;
+  cudaError_t e = cudaMalloc(&p->wa.base, wbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&p->ws.base, sbytes);
+  if (e != cudaSuccess) {
+    if (p->wa.base) cudaFree(p->wa.base);
+    delete p;
+    return fail(2, "cudaMalloc of %zu + %zu bytes failed: %s", wbytes, sbytes, cudaGetErrorString(e));
+  }
+  p->wa.cap = wbytes; p->ws.cap = sbytes;
+  plan_layout(p, true, true);
+  p->allocated = true;
+  *out = p;
+  return 0;
+}
+
+extern "C" int32_t cfen_plan_destroy(cfen_plan* p) {
+  if (!p) return 0;
+  cudaSetDevice(p->cfg.device);
+  if (p->wa.base) cudaFree(p->wa.base);
+  if (p->ws.base) cudaFree(p->ws.base);
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  delete p;
+  return 0;
+}
+
+extern "C" int32_t cfen_plan_set_weight(cfen_plan* p, const char* key, const void* dev_ptr, int64_t numel) {
+  if (!p || !key || !dev_ptr) return fail(1, "cfen_plan_set_weight: null argument");
+  p->reg[key] = std::make_pair(static_cast<const float*>(dev_ptr), numel);
+  p->packed = false;
+  return 0;
+}
+
+extern "C" int64_t cfen_plan_workspace_bytes(const cfen_plan* p) { return p ? (int64_t)(p->wa.cap + p->ws.cap) : 0; }
+extern "C" int64_t cfen_plan_launches_per_forward(const cfen_plan* p) { return p ? p->launches_last : 0; }
+extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t value) {
+  if (!p || !name) return fail(1, "cfen_plan_set_option: null argument");
+  // "timing": records accumulate over forwards until "timing_reset" (or re-enabling) clears them
+  if (strcmp(name, "timing") == 0) {
+    if (value != 0 && !p->timing) { p->prof.clear(); p->ev_used = 0; }
+    p->timing = value != 0;
+    return 0;
+  }
+  if (strcmp(name, "timing_reset") == 0) {
+    CU(cudaSetDevice(p->cfg.device));
+    CU(cudaDeviceSynchronize());
+    p->prof.clear(); p->ev_used = 0;
+    return 0;
+  }
+  return fail(5, "unknown option '%s'", name);
+}
+
+// Per-kernel-class totals of all cfen_forward* calls since timing was enabled / reset, as JSON:
+// {"gemm_tf32": {"launches": n, "ms": t, "flops": f, "bytes": b}, ...}.  Synchronises the device.
+extern "C" int32_t cfen_plan_profile_json(cfen_plan* p, char* buf, int64_t cap) {
+  if (!p || !buf || cap < 64) return fail(1, "cfen_plan_profile_json: bad argument");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaDeviceSynchronize());
+  double ms[PC_COUNT] = {0}, fl[PC_COUNT] = {0}, by[PC_COUNT] = {0};
+  long long n[PC_COUNT] = {0};
+  for (const ProfRec& r : p->prof) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t; fl[r.cls] += r.flops; by[r.cls] += r.bytes; n[r.cls]++;
+  }
+  std::string s = "{";
+  for (int c = 0; c < PC_COUNT; ++c) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             c ? ", " : "", kProfNames[c], n[c], ms[c], fl[c], by[c]);
+    s += tmp;
+  }
+  s += "}";
+  if ((int64_t)s.size() + 1 > cap) return fail(1, "cfen_plan_profile_json: buffer too small");
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+
+static int lookup(cfen_plan* p, const std::string& key, int64_t numel, const float** out) {
+  auto it = p->reg.find(key);
+  if (it == p->reg.end()) return fail(6, "weight '%s' was not registered", key.c_str());
+  if (it->second.second != numel)
+    return fail(6, "weight '%s' has %lld elements, expected %lld", key.c_str(), (long long)it->second.second,
+                (long long)numel);
+  *out = it->second.first;
+  return 0;
+}
+
+static int pack_linear(cfen_plan* p, const std::string& key, float* dst, int rows, int cols, bool prow,
+                       bool pcol, int C, int P2, bool round, cudaStream_t st) {
+  const float* src;
+  RET(lookup(p, key, (int64_t)rows * cols, &src));
+  pack_linear_kernel<<<ew_blocks((long long)rows * cols), 256, 0, st>>>(src, dst, rows, cols, prow, pcol, C,
+                                                                       P2, round);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
+  if (!p) return fail(1, "cfen_plan_pack_weights: null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(p->cfg.device));
+  for (int i = 0; i < 12; ++i)
+    for (int g = 0; g < 2; ++g) {
+      VitW& v = g ? p->gvit[i] : p->lvit[i];
+      const std::string& pre = v.prefix;
+      const std::string enc = pre + ".encoder.layers.0";
+      const int E = v.E, hid = v.hid, C = v.C, P2 = v.P2;
+      RET(pack_linear(p, pre + ".linear_encoding.weight", v.w_le, E, E, true, true, C, P2, true, st));
+      RET(pack_linear(p, pre + ".linear_encoding.bias", v.b_le, E, 1, true, false, C, P2, false, st));
+      RET(pack_linear(p, pre + ".position_encoding.pe.weight", v.pos, v.L, E, false, true, C, P2, false, st));
+      RET(pack_linear(p, enc + ".norm1.weight", v.ln1g, E, 1, true, false, C, P2, false, st));
+      RET(pack_linear(p, enc + ".norm1.bias", v.ln1b, E, 1, true, false, C, P2, false, st));
+      RET(pack_linear(p, enc + ".self_attn.in_proj_weight", v.w_in, 3 * E, E, false, true, C, P2, true, st));
+      RET(pack_linear(p, enc + ".self_attn.out_proj.weight", v.w_out, E, E, true, false, C, P2, true, st));
+      RET(pack_linear(p, enc + ".linear1.weight", v.w1, hid, E, false, true, C, P2, true, st));
+      RET(pack_linear(p, enc + ".linear1.bias", v.b1, hid, 1, false, false, C, P2, false, st));
+      RET(pack_linear(p, enc + ".linear2.weight", v.w2, E, hid, true, false, C, P2, true, st));
+      RET(pack_linear(p, enc + ".linear2.bias", v.b2, E, 1, true, false, C, P2, false, st));
+      RET(pack_linear(p, enc + ".norm2.weight", v.ln2g, E, 1, true, false, C, P2, false, st));
+      RET(pack_linear(p, enc + ".norm2.bias", v.ln2b, E, 1, true, false, C, P2, false, st));
+      RET(pack_linear(p, pre + ".mlp_head.0.weight", v.wm0, hid, E, false, true, C, P2, true, st));
+      RET(pack_linear(p, pre + ".mlp_head.0.bias", v.bm0, hid, 1, false, false, C, P2, false, st));
+      RET(pack_linear(p, pre + ".mlp_head.3.weight", v.wm3, E, hid, true, false, C, P2, true, st));
+      RET(pack_linear(p, pre + ".mlp_head.3.bias", v.bm3, E, 1, true, false, C, P2, false, st));
+    }
+  for (auto& kv : p->conv) {
+    ConvLayer& c = kv.second;
+    const int cout = conv_cout(c.kind);
+    auto it = p->reg.find(c.wkey);
+    if (it == p->reg.end()) return fail(6, "weight '%s' was not registered", c.wkey.c_str());
+    CU(conv_pack_dispatch(c.kind, it->second.first, c.wpack, st));
+    c.bias_src = nullptr; c.an_w = nullptr; c.an_b = nullptr;
+    if (!c.bkey.empty()) RET(lookup(p, c.bkey, cout, &c.bias_src));
+    if (!c.ankey.empty()) {
+      const float *w, *b;
+      RET(lookup(p, c.ankey + ".weight", cout, &w));
+      RET(lookup(p, c.ankey + ".bias", cout, &b));
+      c.an_w = const_cast<float*>(w);
+      c.an_b = const_cast<float*>(b);
+    }
+    conv_affine_kernel<<<1, 128, 0, st>>>(c.bias_src, c.an_w, c.an_b, c.scale, c.shift, cout);
+    CU(cudaGetLastError());
+  }
+  conv_affine_kernel<<<1, 128, 0, st>>>(nullptr, nullptr, nullptr, p->ones, p->mean_rstd /*scratch*/, 96);
+  CU(cudaGetLastError());
+  static const char* kMlp[8] = {"fc_avg_cf1.0", "fc_avg_cf1.2", "fc_avg_cf2.0", "fc_avg_cf2.2",
+                                "fc_max_cf1.0", "fc_max_cf1.2", "fc_max_cf2.0", "fc_max_cf2.2"};
+  for (int k = 0; k < 2; ++k) {
+    const int C = k == 0 ? 48 : 24, R = C / 4;
+    const std::string pre = k == 0 ? "cfsm2g_d03d.0." : "cfsm2g_d02d.0.";
+    for (int j = 0; j < 8; ++j) {
+      const float* src;
+      RET(lookup(p, pre + kMlp[j] + ".weight", (int64_t)R * C, &src));
+      CU(cudaMemcpyAsync(p->cfsm_w[k] + (size_t)j * R * C, src, sizeof(float) * R * C,
+                         cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  p->packed = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+struct Run {
+  cfen_plan* p;
+  cudaStream_t st;
+  int nb;
+};
+
+// Counts the launch and, when timing is on, brackets it with CUDA events on the launching stream.
+struct Launch {
+  cfen_plan* p; cudaStream_t st; bool on; ProfRec rec;
+  Launch(Run& r, int cls, double flops, double bytes) : p(r.p), st(r.st), on(r.p->timing) {
+    p->launches++;
+    if (!on) return;
+    while (p->ev_pool.size() < p->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->ev_pool.push_back(e); }
+    rec.cls = cls; rec.flops = flops; rec.bytes = bytes;
+    rec.a = p->ev_pool[p->ev_used++]; rec.b = p->ev_pool[p->ev_used++];
+    cudaEventRecord(rec.a, st);
+  }
+  ~Launch() {
+    if (!on) return;
+    cudaEventRecord(rec.b, st);
+    p->prof.push_back(rec);
+  }
+};
+
+static int run_gemm(Run& r, const float* A, const float* W, float* C, int M, int N, int K, const float* bias,
+                    const float* res, const float* pos, int period, int relu) {
+  GemmEpilogue ep{bias, res, pos, period > 0 ? period : 1, relu};
+  Launch l(r, PC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)));
+  CU(launch_gemm_tf32(A, W, C, M, N, K, ep, r.st));
+  return 0;
+}
+
+// Token algebra of one LViT/GViT call (reference v3.py:1143-1173 + encoder layer :1382-1390).
+static int run_ln(Run& r, const float* x, float* y, const float* g, const float* b, int M, int E) {
+  Launch l(r, PC_LN, 0.0, 8.0 * M * E);
+  CU(launch_layernorm(x, y, g, b, M, E, 1e-5f, r.st));
+  return 0;
+}
+static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, int heads) {
+  Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 16.0 * nseq * L * E);
+  CU(launch_attention(qkv, o, nseq, L, E, heads, r.st));
+  return 0;
+}
+static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq) {
+  const int M = nseq * v.L, E = v.E, hid = v.hid;
+  RET(run_gemm(r, w.t0, v.w_le, w.t1, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
+  RET(run_ln(r, w.t1, w.h, v.ln1g, v.ln1b, M, E));
+  RET(run_gemm(r, w.h, v.w_in, w.qkv, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
+  RET(run_attn(r, w.qkv, w.o, nseq, v.L, E, v.heads));
+  RET(run_gemm(r, w.o, v.w_out, w.t1, M, E, E, nullptr, w.t1, nullptr, 0, 0));
+  RET(run_ln(r, w.t1, w.h, v.ln2g, v.ln2b, M, E));
+  RET(run_gemm(r, w.h, v.w1, w.f, M, hid, E, v.b1, nullptr, nullptr, 0, 1));
+  RET(run_gemm(r, w.f, v.w2, w.t1, M, E, hid, v.b2, w.t1, nullptr, 0, 0));
+  RET(run_gemm(r, w.t1, v.wm0, w.f, M, hid, E, v.bm0, nullptr, nullptr, 0, 1));
+  RET(run_gemm(r, w.f, v.wm3, w.t1, M, E, hid, v.bm3, w.t1, nullptr, 0, 0));
+  return 0;
+}
+
+// One conv-family layer; handles ActNorm calibration (two-pass) when the plan is calibrating.
+static int run_conv(Run& r, const std::string& name, const float* in0, const float* in1, const float* res,
+                    float* out, int H, int W, int flags, float* stats = nullptr) {
+  cfen_plan* p = r.p;
+  auto it = p->conv.find(name);
+  if (it == p->conv.end()) return fail(7, "internal: unknown conv layer %s", name.c_str());
+  ConvLayer& c = it->second;
+  ConvArgs a;
+  a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = c.wpack; a.out = out;
+  a.B = r.nb; a.H = H; a.W = W; a.win = p->win;
+  const bool is_lg = c.kind == K_LG1 || c.kind == K_LG2 || c.kind == K_LG3;
+  const bool is_up = c.kind == K_UP3 || c.kind == K_UP2 || c.kind == K_UP1;
+  const int cout_ = conv_cout(c.kind);
+  const double kelems = (double)conv_wpack_k(c.kind);           // contraction length per output pixel
+  const double opix = (double)r.nb * H * W * (is_up ? 4 : 1);
+  const double cflops = 2.0 * opix * kelems * cout_;
+  const double cbytes = 4.0 * (opix * cout_ * ((flags & CF_RES) ? 2 : 1) + (double)r.nb * H * W * conv_cin_bytes(c.kind));
+  const int pcls = is_lg ? PC_MERGE : PC_CONV;
+  if (p->calibrating && !c.ankey.empty()) {
+    // pass 1: conv + bias only, per-CTA statistics (models/actnorm.py:25-37)
+    const int cout = conv_cout(c.kind);
+    const int parts = conv_parts(c.kind, H, W);
+    a.scale = p->ones; a.shift = c.bias_src; a.flags = 0; a.stats = p->partials;
+    { Launch l(r, pcls, cflops, cbytes); CU(conv_launch_dispatch(c.kind, a, r.st)); }
+    const long long count = (long long)r.nb * H * W * (is_up ? 4 : 1);
+    Launch l(r, PC_NORM, 0.0, 0.0);
+    actnorm_calibrate_kernel<<<1, 128, 0, r.st>>>(p->partials, r.nb * parts, cout, count, c.bias_src, c.an_w,
+                                                  c.an_b, c.scale, c.shift);
+    CU(cudaGetLastError());
+  }
+  a.scale = c.scale; a.shift = c.shift; a.flags = flags; a.stats = stats;
+  Launch l(r, pcls, cflops, cbytes);
+  CU(conv_launch_dispatch(c.kind, a, r.st));
+  return 0;
+}
+
+// conv + InstanceNorm2d + ReLU (v3.py:292-298, 301): conv emits partial stats, then normalise in place
+static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, float* out, int H, int W,
+                            int Hout, int Wout, int C) {
+  cfen_plan* p = r.p;
+  RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, 0, p->partials));
+  const int parts = conv_parts(p->conv[name].kind, H, W);
+  {
+    Launch l(r, PC_NORM, 0.0, 8.0 * r.nb * parts * C);
+    instnorm_finalize_kernel<<<r.nb, 128, 0, r.st>>>(p->partials, p->mean_rstd, parts, C, Hout * Wout, 1e-5f);
+    CU(cudaGetLastError());
+  }
+  const long long total4 = (long long)r.nb * Hout * Wout * C / 4;
+  Launch l(r, PC_NORM, 0.0, 32.0 * total4);
+  instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, p->mean_rstd, Hout * Wout, C, total4);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const float* x2, float* out, int H,
+                    int W) {
+  cfen_plan* p = r.p;
+  const int C = which == 0 ? 48 : 24, HW = H * W, parts = 64;
+  const long long total4 = (long long)r.nb * HW * C / 4;
+  {
+    Launch l(r, PC_CFSM, 0.0, 48.0 * total4);
+    if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, p->cfsm_part, HW);
+    else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, p->cfsm_part, HW);
+    CU(cudaGetLastError());
+  }
+  {
+    Launch l(r, PC_CFSM, 0.0, 0.0);
+    if (C == 48) cfsm_gate_kernel<48><<<r.nb, 128, 0, r.st>>>(p->cfsm_part, p->cfsm_w[0], p->gates, parts, HW);
+    else cfsm_gate_kernel<24><<<r.nb, 128, 0, r.st>>>(p->cfsm_part, p->cfsm_w[1], p->gates, parts, HW);
+    CU(cudaGetLastError());
+  }
+  Launch l(r, PC_CFSM, 0.0, 64.0 * total4);
+  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, p->gates, out, HW, C, total4);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// block(x) for stage index si (reference e.g. v3.py:403-488)
+static int run_block(Run& r, int si, const float* x, float* out) {
+  cfen_plan* p = r.p;
+  const int lvl = stage_level(kStages[si]);
+  const int Hl = p->Hl[lvl], C = p->Cl[lvl];
+  const int nwin = (Hl / p->win) * (Hl / p->win);
+  {
+    const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
+    {
+      Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4);
+      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->lws.t0, r.nb, Hl, Hl, C, p->win);
+      CU(cudaGetLastError());
+    }
+    RET(run_vit(r, p->lvit[si], p->lws, r.nb * nwin));
+  }
+  {
+    const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
+    {
+      Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17);
+      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->gws.t0, r.nb, Hl, Hl, C);
+      CU(cudaGetLastError());
+    }
+    RET(run_vit(r, p->gvit[si], p->gws, r.nb));
+  }
+  const std::string name = "lgcat_conv_" + stage_tag(kStages[si]);
+  return run_conv(r, name, p->lws.t1, p->gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES);
+}
+
+static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float* xs, float* xd,
+                         cudaStream_t st) {
+  Run r{p, st, nb};
+  const int H = p->H, H1 = p->Hl[1], H2 = p->Hl[2], H3 = p->Hl[3];
+  auto S = [&](const std::string& n) { return p->stage[n].first; };
+  float *f0 = S("f0"), *f1 = S("f1"), *f2 = S("f2");
+  // head: conv5x5 + ResBlock (v3.py:395)
+  RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, 0));
+  RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H, H, CF_RELU));
+  RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, f2, H, H, CF_RES));
+  RET(run_conv_in_relu(r, "ds_conv_e01", f2, S("xf"), H1, H1, H1, H1, 24));
+  // shared encoder (v3.py:403-539)
+  RET(run_block(r, 0, S("xf"), S("e1")));
+  RET(run_conv_in_relu(r, "ds_conv_e02", S("e1"), S("e1d"), H2, H2, H2, H2, 48));
+  RET(run_block(r, 1, S("e1d"), S("e2")));
+  RET(run_conv_in_relu(r, "ds_conv_e03", S("e2"), S("e2d"), H3, H3, H3, H3, 96));
+  RET(run_block(r, 2, S("e2d"), S("e3")));
+  // decoders (v3.py:549-1009)
+  const char* brs[3] = {"r", "s", "d"};
+  float* outs[3] = {xr, xs, xd};
+  const char* tails[3] = {"tail_R", "tail_S", "tail_D"};
+  for (int bi = 0; bi < 3; ++bi) {
+    const std::string b(brs[bi]);
+    const int s3 = 3 + bi * 3;  // stage indices decoder_03x, 02x, 01x
+    RET(run_block(r, s3, S("e3"), S("d3" + b)));
+    RET(run_conv_in_relu(r, "us_conv_d03" + b, S("d3" + b), S("u3" + b), H3, H3, H2, H2, 48));
+    if (bi < 2) {
+      RET(run_conv(r, "sk_conv_d03" + b, S("u3" + b), S("e2"), nullptr, S("d2in" + b), H2, H2, CF_RELU));
+    } else {
+      RET(run_cfsm(r, 0, S("u3d"), S("u3r"), S("u3s"), S("d2ind"), H2, H2));
+    }
+    RET(run_block(r, s3 + 1, S("d2in" + b), S("d2" + b)));
+    RET(run_conv(r, "us_conv_d02" + b, S("d2" + b), nullptr, nullptr, S("u2" + b), H2, H2, CF_RELU));
+    if (bi < 2) {
+      RET(run_conv(r, "sk_conv_d02" + b, S("u2" + b), S("e1"), nullptr, S("d1in" + b), H1, H1, CF_RELU));
+    } else {
+      RET(run_cfsm(r, 1, S("u2d"), S("u2r"), S("u2s"), S("d1ind"), H1, H1));
+    }
+    RET(run_block(r, s3 + 2, S("d1in" + b), S("d1" + b)));
+    // us_conv_d01(block_out + xf) (v3.py:696,852,1008), then the tail (v3.py:348-383)
+    RET(run_conv(r, "us_conv_d01" + b, S("d1" + b), S("xf"), nullptr, f0, H1, H1, CF_RELU));
+    RET(run_conv(r, std::string(tails[bi]) + ".c1", f0, nullptr, nullptr, f1, H, H, CF_RELU));
+    RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H, H, CF_TANH | CF_OUT_NCHW));
+  }
+  return 0;
+}
+
+static int forward_impl(cfen_plan* p, int batch, const float* in, float* xr, float* xs, float* xd, void* stream,
+                        bool calibrate) {
+  if (!p) return fail(1, "cfen_forward: null plan");
+  if (!p->packed) return fail(8, "cfen_forward: weights not packed (call cfen_plan_pack_weights)");
+  if (batch < 0 || !in || !xr || !xs || !xd) return fail(1, "cfen_forward: bad argument");
+  if (calibrate && batch > p->nbmax)
+    return fail(9, "calibration batch %d exceeds plan max_batch %d (ActNorm statistics span the whole batch)",
+                batch, p->nbmax);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(p->cfg.device));
+  const size_t HW = (size_t)p->H * p->W;
+  p->launches = 0;
+  p->calibrating = calibrate;
+
+  int rc = 0;
+  for (int b0 = 0; b0 < batch && rc == 0; b0 += p->nbmax) {
+    const int nb = batch - b0 < p->nbmax ? batch - b0 : p->nbmax;
+    rc = forward_chunk(p, nb, in + b0 * 3 * HW, xr + b0 * 3 * HW, xs + b0 * HW, xd + b0 * 3 * HW, st);
+    if (b0 == 0) p->launches_last = p->launches;
+  }
+  p->calibrating = false;
+  return rc;
+}
+
+extern "C" int32_t cfen_forward(cfen_plan* p, int32_t batch, const float* in, float* xr, float* xs, float* xd,
+                                void* stream) {
+  return forward_impl(p, batch, in, xr, xs, xd, stream, false);
+}
+extern "C" int32_t cfen_forward_calibrate(cfen_plan* p, int32_t batch, const float* in, float* xr, float* xs,
+                                          float* xd, void* stream) {
+  return forward_impl(p, batch, in, xr, xs, xd, stream, true);
+}
+
+extern "C" int32_t cfen_forward_u8(cfen_plan* p, int32_t batch, const uint8_t* in, uint8_t* xr, uint8_t* xs,
+                                   uint8_t* xd, void* stream) {
+  if (!p || !in || !xr || !xs || !xd) return fail(1, "cfen_forward_u8: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(p->cfg.device));
+  const int HW = p->H * p->W;
+  for (int b0 = 0; b0 < batch; b0 += p->nbmax) {
+    const int nb = batch - b0 < p->nbmax ? batch - b0 : p->nbmax;
+    const long long n = (long long)nb * HW;
+    u8hwc_to_f32nchw_kernel<<<ew_blocks(n), 256, 0, st>>>(in + (size_t)b0 * HW * 3, p->u8_in, nb, HW);
+    CU(cudaGetLastError());
+    RET(forward_impl(p, nb, p->u8_in, p->u8_xr, p->u8_xs, p->u8_xd, stream, false));
+    f32nchw_to_u8hwc_kernel<<<ew_blocks(n), 256, 0, st>>>(p->u8_xr, xr + (size_t)b0 * HW * 3, nb, 3, HW);
+    f32nchw_to_u8hwc_kernel<<<ew_blocks(n), 256, 0, st>>>(p->u8_xs, xs + (size_t)b0 * HW * 3, nb, 1, HW);
+    f32nchw_to_u8hwc_kernel<<<ew_blocks(n), 256, 0, st>>>(p->u8_xd, xd + (size_t)b0 * HW * 3, nb, 3, HW);
+    CU(cudaGetLastError());
+    p->launches_last += 4;
+  }
+  return 0;
+}
+
+extern "C" int32_t cfen_plan_stage_ptr(cfen_plan* p, const char* name, void** dev_ptr, int64_t* numel) {
+  if (!p || !name || !dev_ptr || !numel) return fail(1, "cfen_plan_stage_ptr: null argument");
+  std::string n(name);
+  auto it = p->stage.find(n);
+  if (it != p->stage.end()) {
+    *dev_ptr = it->second.first;
+    *numel = it->second.second;
+    return 0;
+  }
+  if (n == "local_tokens") { *dev_ptr = p->lws.t1; *numel = 6LL * p->H * p->H; return 0; }
+  if (n == "global_tokens") { *dev_ptr = p->gws.t1; *numel = (int64_t)(p->H / 32) * (p->H / 32) * 384; return 0; }
+  return fail(5, "unknown stage '%s'", name);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-kernel entry points (unit parity tests)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t cfen_gemm_tf32(const float* A, const float* W, float* C, int32_t M, int32_t N, int32_t K,
+                                  const float* bias, const float* residual, const float* pos,
+                                  int32_t pos_period, int32_t relu, void* stream) {
+  if (!A || !W || !C) return fail(1, "cfen_gemm_tf32: null argument");
+  if (N % 96 != 0 || K % 32 != 0) return fail(1, "cfen_gemm_tf32: N must be a multiple of 96 and K of 32");
+  CU(set_kernel_attributes());
+  GemmEpilogue ep{bias, residual, pos, pos_period > 0 ? pos_period : 1, relu};
+  CU(launch_gemm_tf32(A, W, C, M, N, K, ep, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int32_t cfen_layernorm(const float* x, float* y, const float* gamma, const float* beta, int32_t rows,
+                                  int32_t E, float eps, void* stream) {
+  if (!x || !y || !gamma || !beta) return fail(1, "cfen_layernorm: null argument");
+  CU(launch_layernorm(x, y, gamma, beta, rows, E, eps, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int32_t cfen_attention(const float* qkv, float* out, int32_t nseq, int32_t L, int32_t E, int32_t heads,
+                                  void* stream) {
+  if (!qkv || !out) return fail(1, "cfen_attention: null argument");
+  if (heads <= 0 || E % heads != 0 || (E / heads != 24 && E / heads != 96))
+    return fail(1, "cfen_attention: head dim must be 24 or 96");
+  CU(set_kernel_attributes());
+  CU(launch_attention(qkv, out, nseq, L, E, heads, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int32_t cfen_tokenize_local(const float* map, float* tokens, int32_t B, int32_t H, int32_t W, int32_t C,
+                                       int32_t window, void* stream) {
+  if (!map || !tokens) return fail(1, "cfen_tokenize_local: null argument");
+  if (C % 4 || window % 2 || H % window || W % window) return fail(1, "cfen_tokenize_local: bad shape");
+  const long long n4 = (long long)B * H * W * C / 4;
+  tokenize_local_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(map, tokens, B, H, W, C,
+                                                                                    window);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t cfen_tokenize_global(const float* map, float* tokens, int32_t B, int32_t H, int32_t W, int32_t C,
+                                        void* stream) {
+  if (!map || !tokens) return fail(1, "cfen_tokenize_global: null argument");
+  if (C % 4 || H % 16 || W % 16) return fail(1, "cfen_tokenize_global: bad shape");
+  const long long n4 = (long long)B * (H / 16) * (W / 16) * 16 * C / 4;
+  tokenize_global_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(map, tokens, B, H, W, C);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int conv_kind_from_name(const char* kind) {
+  static const std::pair<const char*, int> tab[] = {
+      {"head5x5", K_HEAD5}, {"conv3x3_12_12", K_C3}, {"ds_12_24", K_DS1}, {"ds_24_48", K_DS2},
+      {"ds_48_96", K_DS3}, {"up_96_48", K_UP3}, {"up_48_24", K_UP2}, {"up_24_12", K_UP1},
+      {"skip_96_48", K_SK3}, {"skip_48_24", K_SK2}, {"tail7x7_3", K_T3}, {"tail7x7_1", K_T1},
+      {"lg_48_24", K_LG1}, {"lg_96_48", K_LG2}, {"lg_192_96", K_LG3}};
+  for (auto& e : tab)
+    if (strcmp(e.first, kind) == 0) return e.second;
+  return -1;
+}
+
+// Test-only convenience: packs the weights into temporaries (cudaMalloc + sync), runs, frees.
+static int conv_oneoff(int kind, const float* in0, const float* in1, const float* res, const float* weight,
+                       const float* bias, const float* an_w, const float* an_b, float* out, int B, int H, int W,
+                       int flags, int win, cudaStream_t st) {
+  CU(set_kernel_attributes());
+  float* tmp = nullptr;
+  const size_t wf = conv_wpack_floats(kind);
+  CU(cudaMalloc(&tmp, (wf + 256) * sizeof(float)));
+  float *scale = tmp + wf, *shift = tmp + wf + 128;
+  cudaError_t e = conv_pack_dispatch(kind, weight, tmp, st);
+  if (e == cudaSuccess) {
+    conv_affine_kernel<<<1, 128, 0, st>>>(bias, an_w, an_b, scale, shift, conv_cout(kind));
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    ConvArgs a;
+    a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = tmp; a.scale = scale; a.shift = shift; a.out = out;
+    a.stats = nullptr; a.B = B; a.H = H; a.W = W; a.flags = flags; a.win = win;
+    e = conv_launch_dispatch(kind, a, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(2, "conv one-off failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const float* extra, const float* weight,
+                                    const float* bias, const float* an_weight, const float* an_bias, float* out,
+                                    int32_t B, int32_t H, int32_t W, int32_t flags, void* stream) {
+  if (!kind || !in || !weight || !out) return fail(1, "cfen_conv2d_nhwc: null argument");
+  const int k = conv_kind_from_name(kind);
+  if (k < 0 || k == K_LG1 || k == K_LG2 || k == K_LG3) return fail(1, "cfen_conv2d_nhwc: unknown kind '%s'", kind);
+  // public flag bits: 0 relu, 1 tanh, 2 residual(extra), 3 out NCHW ; bit5: extra is a second input
+  const bool extra_is_input = (flags & 32) != 0;
+  const int f = flags & (CF_RELU | CF_TANH | CF_RES | CF_OUT_NCHW);
+  return conv_oneoff(k, in, extra_is_input ? extra : nullptr, (f & CF_RES) ? extra : nullptr, weight, bias,
+                     an_weight, an_bias, out, B, H, W, f, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t cfen_merge_lg(const float* local_tokens, const float* global_tokens, const float* x,
+                                 const float* weight, const float* bias, const float* an_weight,
+                                 const float* an_bias, float* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                                 int32_t window, void* stream) {
+  if (!local_tokens || !global_tokens || !x || !weight || !out) return fail(1, "cfen_merge_lg: null argument");
+  const int k = C == 24 ? K_LG1 : (C == 48 ? K_LG2 : (C == 96 ? K_LG3 : -1));
+  if (k < 0) return fail(1, "cfen_merge_lg: C must be 24, 48 or 96");
+  return conv_oneoff(k, local_tokens, global_tokens, x, weight, bias, an_weight, an_bias, out, B, H, W,
+                     CF_RELU | CF_RES, window, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t cfen_cfsm(const float* x0, const float* x1, const float* x2, const float* w, float* out,
+                             float* scratch, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  if (!x0 || !x1 || !x2 || !w || !out || !scratch) return fail(1, "cfen_cfsm: null argument");
+  if (C != 24 && C != 48) return fail(1, "cfen_cfsm: C must be 24 or 48");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int HW = H * W, parts = 64;
+  float* part = scratch;                             // [B][64][2][C]
+  float* gates = scratch + (size_t)B * parts * 2 * C;  // [B][2][C]
+  const long long total4 = (long long)B * HW * C / 4;
+  if (C == 48) {
+    cfsm_reduce_kernel<48><<<dim3(parts, B), 192, 0, st>>>(x0, x1, x2, part, HW);
+    cfsm_gate_kernel<48><<<B, 128, 0, st>>>(part, w, gates, parts, HW);
+  } else {
+    cfsm_reduce_kernel<24><<<dim3(parts, B), 192, 0, st>>>(x0, x1, x2, part, HW);
+    cfsm_gate_kernel<24><<<B, 128, 0, st>>>(part, w, gates, parts, HW);
+  }
+  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(x0, x1, x2, gates, out, HW, C, total4);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// dcn (row A14) - implemented in dcn.cuh
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t cfen_deform_conv2d_forward(const float* input, const float* weight, const float* offset,
+                                              float* output, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                                              int32_t Cout, int32_t kH, int32_t kW, int32_t strideH,
+                                              int32_t strideW, int32_t padH, int32_t padW, int32_t dilH,
+                                              int32_t dilW, int32_t group, int32_t deformable_group,
+                                              int32_t im2col_step, void* stream) {
+  return fail(10, "cfen_deform_conv2d_forward: not built yet");
+}
+extern "C" int32_t cfen_modulated_deform_conv2d_forward(const float* input, const float* weight,
+                                                        const float* bias, const float* offset,
+                                                        const float* mask, float* output, int32_t B,
+                                                        int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                                        int32_t kH, int32_t kW, int32_t strideH,
+                                                        int32_t strideW, int32_t padH, int32_t padW,
+                                                        int32_t dilH, int32_t dilW, int32_t group,
+                                                        int32_t deformable_group, int32_t with_bias,
+                                                        void* stream) {
+  return fail(10, "cfen_modulated_deform_conv2d_forward: not built yet");
+}

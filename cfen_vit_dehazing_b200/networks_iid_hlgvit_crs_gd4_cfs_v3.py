@@ -375,12 +375,13 @@ class dec_ipt(nn.Module):
                 % (height, width, 2 * int(opt.loadSize)))
         key = (device.index, height, width)
         plan = self._plans.get(key)
-        if plan is None:
+        need = _native.chunk_images(height, batch)
+        if plan is None or plan.max_batch < need:   # grow the workspace when a larger batch arrives
             plan = _native.Plan(device=device.index, height=height, width=width,
                                 n_feats=opt.n_feats, hidden_dim_ratio=opt.hidden_dim_ratio,
                                 num_heads=opt.num_heads, patch_dim=opt.patch_dim,
                                 patch_size=int(opt.patch_size), load_size=int(opt.loadSize),
-                                max_batch=_native.chunk_images(height, batch))
+                                max_batch=need)
             self._plans[key] = plan
         if plan.weights_version != self._weights_version:
             tensors = {k: v for k, v in self.state_dict(keep_vars=True).items()}

@@ -69,7 +69,11 @@ int32_t cfen_plan_pack_weights(cfen_plan* plan, void* stream);
 
 int64_t cfen_plan_workspace_bytes(const cfen_plan* plan);
 int64_t cfen_plan_launches_per_forward(const cfen_plan* plan); /* kernels per max_batch pass */
+/* options: "timing" (0/1): bracket every kernel launch with CUDA events on the launching stream */
 int32_t cfen_plan_set_option(cfen_plan* plan, const char* name, int64_t value);
+/* JSON text with per-kernel-class {launches, ms, flops, bytes} of the last forward run with
+ * "timing" on (algorithmic flops/bytes; used by bench.py's roofline).  Synchronises the device. */
+int32_t cfen_plan_profile_json(cfen_plan* plan, char* buf, int64_t cap);
 
 /* ---- the hot path: dec_ipt.forward (v3.py:392-1020) ----
  * in  [batch,3,H,W];  xr [batch,3,H,W], xs [batch,1,H,W], xd [batch,3,H,W]  (v3.py:1020). */

@@ -1,0 +1,153 @@
+"""GPU: whole-generator parity of the product (through define_G / dec_ipt.forward -> C ABI) against
+the oracle on identical seeded, primed weights and synthetic inputs.
+
+Gate: max|diff| <= 1e-2 on the [0,1] scale ((y+1)/2) and PSNR >= 45 dB for each of
+xr, xs, xd.  The oracle itself is pinned to the real reference by tests/test_oracle_golden.py.
+"""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cfen_oracle as orc  # noqa: E402
+from tests import _gpu as G  # noqa: E402
+from tests import _util as U  # noqa: E402
+from tests.golden.make_goldens import CONFIGS  # noqa: E402
+
+MAX_ABS_01 = 1e-2
+MIN_PSNR = 45.0
+
+STAGE_TAPS = {"xf": "xf", "e1": "e1", "e1d": "e1d", "e2": "e2", "e2d": "e2d", "e3": "e3"}
+for _b in "rsd":
+    STAGE_TAPS.update({"d3" + _b: "block_decoder_03" + _b, "u3" + _b: "u3" + _b, "d2" + _b: "block_decoder_02" + _b,
+                       "u2" + _b: "u2" + _b, "d1" + _b: "block_decoder_01" + _b})
+STAGE_ORDER = ["xf", "e1", "e1d", "e2", "e2d", "e3"] + [s + b for b in "rsd" for s in ("d3", "u3", "d2", "u2", "d1")]
+
+
+def _gpu_net(hr, size, primed=True):
+    net, sd0, sd1, x0, opt = U.seeded_state(hr, size)
+    import cfen_vit_dehazing_b200 as prod
+    with contextlib.redirect_stdout(io.StringIO()):
+        gnet = prod.dec_ipt(opt, prod.common.default_conv)
+    gnet.load_state_dict(sd1 if primed else sd0, strict=True)
+    return gnet.cuda(), sd0, sd1, x0
+
+
+def _stage_report(gnet, size, taps, batch):
+    plan = gnet._plans[(torch.cuda.current_device(), size, size)]
+    rep = {}
+    for name in STAGE_ORDER:
+        ref = taps[STAGE_TAPS[name]]
+        p, per = plan.stage_ptr(name)
+        got = G.view_f32(p, per * batch).view(batch, ref.shape[2], ref.shape[3], ref.shape[1]).permute(0, 3, 1, 2)
+        d = (got.cpu().double() - ref.double()).abs()
+        rep[name] = {"max_abs": d.max().item(), "ref_absmax": ref.abs().max().item(),
+                     "rel": d.max().item() / max(ref.abs().max().item(), 1e-30)}
+    return rep
+
+
+def _run_and_check(name, hr, size, batch):
+    gnet, sd0, sd1, x0 = _gpu_net(hr, size)
+    x1 = orc.make_inputs(size, [1, batch])[1]
+    taps = {}
+    ref = orc.forward(sd1, x1, taps=taps)
+    with torch.no_grad():
+        out = gnet(x1.cuda())
+    torch.cuda.synchronize()
+    rep = {"stages": _stage_report(gnet, size, taps, batch)}
+    ok = True
+    for tag, a, b in zip(("xr", "xs", "xd"), out, ref):
+        assert a.shape == b.shape and a.dtype == torch.float32
+        mx, ps = U.err01(a, b)
+        rep[tag] = {"max_abs_01": mx, "psnr": ps}
+        ok = ok and mx <= MAX_ABS_01 and ps >= MIN_PSNR and bool(torch.isfinite(a).all())
+    G.dump_json("parity_%s.json" % name, rep)
+    assert ok, rep
+    return gnet, out, ref, x1
+
+
+@pytest.mark.parametrize("name", ["v3_hr2_128_b2", "v3_hr4_512_b1", "v3_hr2_512_b1"])
+def test_forward_parity_vs_oracle_and_goldens(name):
+    hr, size, batch, stride = CONFIGS[name]
+    gnet, out, ref, x1 = _run_and_check(name, hr, size, batch)
+    # and directly against the committed samples of the real reference's outputs
+    g = U.load_golden(name)
+    for tag, a in zip(("xr", "xs", "xd"), out):
+        d = np.abs(a[:, :, ::stride, ::stride].cpu().numpy() - g[tag]).max() / 2.0
+        assert d <= MAX_ABS_01, (tag, d)
+
+
+def test_forward_parity_1024():
+    _run_and_check("v3_hr4_1024_b1", 4, 1024, 1)
+
+
+def test_batch_chunking_and_batch_invariance():
+    """B images in one call == the same images one by one (bitwise: kernels are batch-invariant),
+    including a batch larger than the plan's internal chunk (16 images at 512x512)."""
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    x = orc.make_inputs(128, [1, 19])[1].cuda()
+    with torch.no_grad():
+        full = gnet(x)
+        for i in (0, 7, 18):
+            one = gnet(x[i:i + 1].contiguous())
+            for a, b in zip(full, one):
+                assert torch.equal(a[i:i + 1], b)
+
+
+def test_actnorm_first_forward_calibration():
+    """Un-primed state_dict: the first forward initialises ActNorm from batch statistics like the
+    reference (models/actnorm.py:25-37) and writes weight/bias/initialized back into the module."""
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128, primed=False)
+    with torch.no_grad():
+        gnet(x0.cuda())
+    torch.cuda.synchronize()
+    got = gnet.state_dict()
+    worst = 0.0
+    for k, v in sd1.items():
+        if k.endswith(".initialized"):
+            assert int(got[k]) == 1
+        elif (k.rsplit(".", 1)[0] + ".initialized") in sd1:
+            worst = max(worst, (got[k].cpu() - v).abs().max().item())
+    assert worst <= 2e-2, worst   # statistics of TF32 activations vs fp32 oracle
+    x1 = orc.make_inputs(128, [1, 2])[1]
+    ref = orc.forward(sd1, x1)
+    with torch.no_grad():
+        out = gnet(x1.cuda())
+    for a, b in zip(out, ref):
+        mx, ps = U.err01(a, b)
+        assert mx <= 2 * MAX_ABS_01 and ps >= MIN_PSNR - 3, (mx, ps)
+
+
+def test_reload_state_dict_repacks():
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    x1 = orc.make_inputs(128, [1, 1])[1].cuda()
+    with torch.no_grad():
+        a = gnet(x1)[2].clone()
+        sd2 = {k: v.clone() for k, v in sd1.items()}
+        sd2["tail_D.0.5.bias"] = sd2["tail_D.0.5.bias"] + 0.5
+        gnet.load_state_dict(sd2, strict=True)
+        b = gnet(x1)[2]
+    assert not torch.equal(a, b)
+
+
+def test_uint8_boundary_matches_float_path():
+    """cfen_forward_u8 == float path + tensor2im (util/util.py:12-24)."""
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
+    x = ((img.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    with torch.no_grad():
+        fr, fs, fd = gnet(x.cuda())
+    plan = gnet._plans[(torch.cuda.current_device(), 128, 128)]
+    outs = [torch.empty(2, 128, 128, 3, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    plan.forward_u8(2, img.cuda().data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for o, f in zip(outs, (fr, fs, fd)):
+        f3 = f.expand(-1, 3, -1, -1) if f.shape[1] == 1 else f
+        ref = ((f3.permute(0, 2, 3, 1) + 1) / 2.0 * 255.0).to(torch.uint8)
+        assert (o.int() - ref.int()).abs().max().item() <= 1

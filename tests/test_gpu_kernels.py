@@ -1,0 +1,230 @@
+"""GPU: every kernel, called through the C ABI, against a plain PyTorch fp32 reference of the same op.
+
+Tolerances: the contractions run on TF32 tensor cores with fp32 accumulation (10-bit mantissa
+operands): |err| <= 4e-3 * max|ref| per op; pure fp32 kernels (LayerNorm, tokenisers, CFSM): 2e-5.
+"""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from cfen_vit_dehazing_b200 import _native  # noqa: E402
+from oracle import cfen_oracle as orc  # noqa: E402
+from tests import _gpu as G  # noqa: E402
+from tests import _util as U  # noqa: E402
+
+TF32_TOL = 4e-3
+FP32_TOL = 2e-5
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _strict_fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def dev(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 96, 96), (300, 288, 96), (16, 1536, 1536), (64, 6144, 1536),
+                                   (129, 384, 384), (2048, 96, 384), (4096, 192, 768)])
+@pytest.mark.parametrize("mode", ["plain", "bias_relu", "bias_res_pos", "inplace_res"])
+def test_gemm_tf32(M, N, K, mode):
+    L = _native.lib()
+    A, W = dev(M, K, seed=1), dev(N, K, seed=2, scale=K ** -0.5)
+    bias, res, pos = dev(N, seed=3), dev(M, N, seed=4), dev(16, N, seed=5)
+    C = torch.empty(M, N, device="cuda")
+    ref = A.double() @ W.double().t()
+    if mode == "plain":
+        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, None, None, None, 0, 0, G.stream()))
+    elif mode == "bias_relu":
+        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, G.ptr(bias), None, None, 0, 1, G.stream()))
+        ref = torch.relu(ref + bias.double())
+    elif mode == "bias_res_pos":
+        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, G.ptr(bias), G.ptr(res), G.ptr(pos), 16, 0,
+                                 G.stream()))
+        ref = ref + bias.double() + res.double() + pos.double()[torch.arange(M, device="cuda") % 16]
+    else:
+        C = res.clone()
+        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, None, G.ptr(C), None, 0, 0, G.stream()))
+        ref = ref + res.double()
+    torch.cuda.synchronize()
+    assert U.rel_err(C, ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("rows,E", [(1001, 96), (257, 192), (64, 384), (33, 768), (16, 1536)])
+def test_layernorm(rows, E):
+    L = _native.lib()
+    x, gm, bt = dev(rows, E, seed=1, scale=3.0) + 0.7, dev(E, seed=2), dev(E, seed=3)
+    y = torch.empty_like(x)
+    G.check(L.cfen_layernorm(G.ptr(x), G.ptr(y), G.ptr(gm), G.ptr(bt), rows, E, 1e-5, G.stream()))
+    ref = F.layer_norm(x.double(), (E,), gm.double(), bt.double(), 1e-5)
+    assert U.rel_err(y, ref) <= FP32_TOL
+
+
+@pytest.mark.parametrize("nseq,Lq,E,heads", [(3, 256, 96, 4), (2, 256, 384, 16), (2, 256, 384, 4), (2, 64, 768, 8),
+                                             (5, 16, 1536, 16), (1, 1024, 96, 4), (2, 80, 192, 8), (1, 1024, 384, 4)])
+def test_attention(nseq, Lq, E, heads):
+    L = _native.lib()
+    hd = E // heads
+    qkv = dev(nseq * Lq, 3 * E, seed=1)
+    out = torch.empty(nseq * Lq, E, device="cuda")
+    G.check(L.cfen_attention(G.ptr(qkv), G.ptr(out), nseq, Lq, E, heads, G.stream()))
+    q, k, v = (z.view(nseq, Lq, heads, hd).transpose(1, 2).double() for z in qkv.split(E, dim=-1))
+    att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(nseq * Lq, E)
+    assert U.rel_err(out, ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("B,H,C,win", [(2, 64, 24, 8), (1, 256, 24, 32), (3, 32, 48, 8), (2, 16, 96, 8), (1, 128, 48, 64)])
+def test_tokenize_local(B, H, C, win):
+    L = _native.lib()
+    x = dev(B, C, H, H, seed=1)
+    tok = torch.empty(B * (H // 2) ** 2, 4 * C, device="cuda")
+    G.check(L.cfen_tokenize_local(G.ptr(U.to_nhwc(x)), G.ptr(tok), B, H, H, C, win, G.stream()))
+    assert torch.equal(tok, G.local_tokens_ref(x, win))
+    # and the layout is a feature permutation of the reference's unfold tokens (v3.py:1140)
+    ny = H // win
+    tiles = x.view(B, C, ny, win, ny, win).permute(0, 2, 4, 1, 3, 5).reshape(-1, C, win, win)
+    unf = F.unfold(tiles, 2, stride=2).transpose(1, 2)              # [N, L, (c,ky,kx)]
+    unf = unf.reshape(unf.shape[0], unf.shape[1], C, 4).transpose(2, 3).reshape(-1, 4 * C)
+    assert torch.equal(tok, unf)
+
+
+@pytest.mark.parametrize("B,H,C", [(2, 64, 24), (1, 256, 24), (3, 32, 48), (2, 16, 96)])
+def test_tokenize_global(B, H, C):
+    L = _native.lib()
+    x = dev(B, C, H, H, seed=1)
+    tok = torch.empty(B * (H // 16) ** 2, 16 * C, device="cuda")
+    G.check(L.cfen_tokenize_global(G.ptr(U.to_nhwc(x)), G.ptr(tok), B, H, H, C, G.stream()))
+    q = F.avg_pool2d(F.avg_pool2d(x, 2, 2), 2, 2)
+    assert U.rel_err(tok, G.global_tokens_ref(q)) <= FP32_TOL
+
+
+def _conv(kind, x_nhwc_or_nchw, extra, w, b, an_w, an_b, out, B, H, W, flags):
+    L = _native.lib()
+    G.check(L.cfen_conv2d_nhwc(kind.encode(), G.ptr(x_nhwc_or_nchw), G.ptr(extra), G.ptr(w), G.ptr(b), G.ptr(an_w),
+                               G.ptr(an_b), G.ptr(out), B, H, W, flags, G.stream()))
+    torch.cuda.synchronize()
+
+
+RELU, TANH, RES, ONCHW, EXTRA_IN = 1, 2, 4, 8, 32
+
+
+def test_conv_head5x5():
+    B, H = 2, 64
+    x, w, b = dev(B, 3, H, H, seed=1), dev(12, 3, 5, 5, seed=2, scale=0.1), dev(12, seed=3)
+    out = torch.empty(B, H, H, 12, device="cuda")
+    _conv("head5x5", x, None, w, b, None, None, out, B, H, H, 0)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=2)
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("flags", [0, RELU, RES, RELU | RES])
+def test_conv3x3_12_12(flags):
+    B, H = 2, 48
+    x, w, b = dev(B, 12, H, H, seed=1), dev(12, 12, 3, 3, seed=2, scale=0.1), dev(12, seed=3)
+    res = dev(B, 12, H, H, seed=4)
+    anw, anb = dev(12, seed=5, scale=0.3), dev(12, seed=6)
+    out = torch.empty(B, H, H, 12, device="cuda")
+    _conv("conv3x3_12_12", U.to_nhwc(x), U.to_nhwc(res) if flags & RES else None, w, b, anw, anb, out, B, H, H, flags)
+    ref = (F.conv2d(x.double(), w.double(), b.double(), padding=1) + anb.double().view(1, -1, 1, 1)) * torch.exp(
+        anw.double()).view(1, -1, 1, 1)
+    if flags & RELU:
+        ref = torch.relu(ref)
+    if flags & RES:
+        ref = ref + res.double()
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("ds_12_24", 12, 24), ("ds_24_48", 24, 48), ("ds_48_96", 48, 96)])
+def test_conv_strided(kind, cin, cout):
+    B, Ho = 2, 32
+    x, w, b = dev(B, cin, 2 * Ho, 2 * Ho, seed=1), dev(cout, cin, 3, 3, seed=2, scale=0.1), dev(cout, seed=3)
+    out = torch.empty(B, Ho, Ho, cout, device="cuda")
+    _conv(kind, U.to_nhwc(x), None, w, b, None, None, out, B, Ho, Ho, 0)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1)
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("up_96_48", 96, 48), ("up_48_24", 48, 24), ("up_24_12", 24, 12)])
+def test_conv_transposed(kind, cin, cout):
+    B, Hi = 2, 16
+    x, w, b = dev(B, cin, Hi, 2 * Hi, seed=1), dev(cin, cout, 4, 4, seed=2, scale=0.1), dev(cout, seed=3)
+    x2 = dev(B, cin, Hi, 2 * Hi, seed=7)
+    out = torch.empty(B, 2 * Hi, 4 * Hi, cout, device="cuda")
+    if kind == "up_24_12":   # consumes block_out + xf (v3.py:696)
+        _conv(kind, U.to_nhwc(x), U.to_nhwc(x2), w, b, None, None, out, B, Hi, 2 * Hi, RELU | EXTRA_IN)
+        ref = torch.relu(F.conv_transpose2d((x + x2).double(), w.double(), b.double(), stride=2, padding=1))
+    else:
+        _conv(kind, U.to_nhwc(x), None, w, b, None, None, out, B, Hi, 2 * Hi, 0)
+        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2, padding=1)
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("kind,c", [("skip_96_48", 48), ("skip_48_24", 24)])
+def test_conv_skip_concat(kind, c):
+    B, H = 2, 32
+    a, s = dev(B, c, H, H, seed=1), dev(B, c, H, H, seed=2)
+    w, b = dev(c, 2 * c, 1, 1, seed=3, scale=0.1), dev(c, seed=4)
+    anw, anb = dev(c, seed=5, scale=0.3), dev(c, seed=6)
+    out = torch.empty(B, H, H, c, device="cuda")
+    _conv(kind, U.to_nhwc(a), U.to_nhwc(s), w, b, anw, anb, out, B, H, H, RELU | EXTRA_IN)
+    y = F.conv2d(torch.cat((a, s), 1).double(), w.double(), b.double())
+    ref = torch.relu((y + anb.double().view(1, -1, 1, 1)) * torch.exp(anw.double()).view(1, -1, 1, 1))
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("kind,cout", [("tail7x7_3", 3), ("tail7x7_1", 1)])
+def test_conv_tail_reflect_tanh(kind, cout):
+    B, H = 2, 32
+    x, w, b = dev(B, 12, H, H, seed=1), dev(cout, 12, 7, 7, seed=2, scale=0.05), dev(cout, seed=3, scale=0.1)
+    out = torch.empty(B, cout, H, H, device="cuda")
+    _conv(kind, U.to_nhwc(x), None, w, b, None, None, out, B, H, H, TANH | ONCHW)
+    ref = torch.tanh(F.conv2d(F.pad(x.double(), (3, 3, 3, 3), mode="reflect"), w.double(), b.double()))
+    assert (out.double() - ref).abs().max().item() <= TF32_TOL
+
+
+@pytest.mark.parametrize("C,H,win", [(24, 64, 8), (48, 32, 8), (96, 16, 8), (24, 256, 32)])
+def test_merge_local_global(C, H, win):
+    L = _native.lib()
+    B = 2
+    loc, x = dev(B, C, H, H, seed=1), dev(B, C, H, H, seed=2)
+    gq = dev(B, C, H // 4, H // 4, seed=3)
+    w, b = dev(C, 2 * C, 1, 1, seed=4, scale=0.1), dev(C, seed=5)
+    anw, anb = dev(C, seed=6, scale=0.3), dev(C, seed=7)
+    out = torch.empty(B, H, H, C, device="cuda")
+    G.check(L.cfen_merge_lg(G.ptr(G.local_tokens_ref(loc, win)), G.ptr(G.global_tokens_ref(gq)), G.ptr(U.to_nhwc(x)),
+                            G.ptr(w), G.ptr(b), G.ptr(anw), G.ptr(anb), G.ptr(out), B, H, H, C, win, G.stream()))
+    up = gq.double()
+    for _ in range(2):
+        up = F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False)
+    y = F.conv2d(torch.cat((loc.double(), up), 1), w.double(), b.double())
+    ref = torch.relu((y + anb.double().view(1, -1, 1, 1)) * torch.exp(anw.double()).view(1, -1, 1, 1)) + x.double()
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("C,H", [(48, 32), (24, 64), (24, 256)])
+def test_cfsm(C, H):
+    L = _native.lib()
+    B, R = 3, C // 4
+    xs = [dev(B, C, H, H, seed=i) for i in (1, 2, 3)]
+    names = ["fc_avg_cf1.0", "fc_avg_cf1.2", "fc_avg_cf2.0", "fc_avg_cf2.2",
+             "fc_max_cf1.0", "fc_max_cf1.2", "fc_max_cf2.0", "fc_max_cf2.2"]
+    sd = {}
+    for i, n in enumerate(names):
+        shape = (R, C, 1, 1) if n.endswith(".0") else (C, R, 1, 1)
+        sd["m." + n + ".weight"] = dev(*shape, seed=10 + i, scale=0.3)
+    wcat = torch.cat([sd["m." + n + ".weight"].reshape(-1) for n in names]).contiguous()
+    out = torch.empty(B, H, H, C, device="cuda")
+    scratch = torch.empty(B * 64 * 2 * C + B * 2 * C, device="cuda")
+    G.check(L.cfen_cfsm(*(G.ptr(U.to_nhwc(t)) for t in xs), G.ptr(wcat), G.ptr(out), G.ptr(scratch), B, H, H, C,
+                        G.stream()))
+    ref = orc.cfsm({k: v.cpu() for k, v in sd.items()}, "m", *(t.cpu() for t in xs))
+    assert U.rel_err(U.to_nchw(out), ref) <= FP32_TOL * 5

@@ -1,0 +1,75 @@
+"""CPU: pin the oracle (and the product's init-stream mirror) to outputs of the real reference.
+
+The golden files were produced by tests/golden/make_goldens.py from /root/reference (unmodified
+define_G / dec_ipt.forward).  Here the same weights are rebuilt from the seed with the product's
+parameter containers, primed and run by the oracle, and compared with the stored reference values.
+Tolerance 1e-4 on the raw [-1,1] outputs (fp32 summation-order noise is ~5e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cfen_oracle as orc
+from tests import _util as U
+from tests.golden.make_goldens import ACTNORM_KEYS, CONFIGS, WEIGHT_KEYS
+
+TOL = 1e-4
+
+
+def _check(name):
+    hr, size, batch, stride = CONFIGS[name]
+    g = U.load_golden(name)
+    net, sd0, sd1, x0, opt = U.seeded_state(hr, size)
+    # 1) init-stream mirror: seeded weights equal the reference's
+    for k in WEIGHT_KEYS:
+        assert abs(sd0[k].double().sum().item() - float(g["w_sum/" + k])) <= 1e-6 * max(1.0, abs(float(g["w_abs/" + k]))), k
+        assert abs(sd0[k].double().abs().sum().item() - float(g["w_abs/" + k])) <= 1e-6 * float(g["w_abs/" + k]), k
+    # 2) ActNorm priming equals the reference's first forward
+    for k in ACTNORM_KEYS:
+        np.testing.assert_allclose(sd1[k].numpy(), g["an/" + k], rtol=0, atol=2e-5, err_msg=k)
+    # 3) outputs
+    x1 = orc.make_inputs(size, [1, batch])[1]
+    np.testing.assert_array_equal(x1[:, :, ::stride, ::stride].numpy(), g["x_sample"])
+    outs = orc.forward(sd1, x1)
+    for tag, y in zip(("xr", "xs", "xd"), outs):
+        d = np.abs(y[:, :, ::stride, ::stride].numpy() - g[tag]).max()
+        assert d <= TOL, (name, tag, d)
+        assert abs(y.double().mean().item() - float(g[tag + "_mean"])) <= TOL
+        assert abs((y.double() ** 2).mean().item() - float(g[tag + "_sqmean"])) <= TOL
+
+
+def test_oracle_matches_reference_128_hr2():
+    _check("v3_hr2_128_b2")
+
+
+def test_oracle_matches_reference_512_hr4():
+    _check("v3_hr4_512_b1")
+
+
+def test_oracle_matches_reference_512_hr2():
+    _check("v3_hr2_512_b1")
+
+
+@pytest.mark.slow
+def test_oracle_matches_reference_1024_hr4():
+    _check("v3_hr4_1024_b1")
+
+
+def test_oracle_upsample_stencil_equals_two_bilinear_passes():
+    """The 3-tap composite stencil used by the merge kernel."""
+    import torch.nn.functional as F
+    x = torch.randn(1, 1, 6, 5)
+    y = F.interpolate(F.interpolate(x, scale_factor=2, mode="bilinear"), scale_factor=2, mode="bilinear")
+    taps = {0: (.375, .625, 0.), 1: (.1875, .75, .0625), 2: (.0625, .75, .1875), 3: (0., .625, .375)}
+    h, w = x.shape[-2:]
+    z = torch.zeros_like(y)
+    for oy in range(4 * h):
+        for ox in range(4 * w):
+            acc = 0.0
+            for a, wa in enumerate(taps[oy % 4]):
+                for b, wb in enumerate(taps[ox % 4]):
+                    sy = min(max(oy // 4 - 1 + a, 0), h - 1)
+                    sx = min(max(ox // 4 - 1 + b, 0), w - 1)
+                    acc += wa * wb * x[0, 0, sy, sx].item()
+            z[0, 0, oy, ox] = acc
+    assert (y - z).abs().max().item() < 1e-6
