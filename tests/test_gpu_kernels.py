@@ -87,7 +87,9 @@ def test_tokenize_local(B, H, C, win):
     L = _native.lib()
     x = dev(B, C, H, H, seed=1)
     tok = torch.empty(B * (H // 2) ** 2, 4 * C, device="cuda")
-    G.check(L.cfen_tokenize_local(G.ptr(U.to_nhwc(x)), G.ptr(tok), B, H, H, C, win, G.stream()))
+    xn = U.to_nhwc(x)
+    G.check(L.cfen_tokenize_local(G.ptr(xn), G.ptr(tok), B, H, H, C, win, G.stream()))
+    torch.cuda.synchronize()
     assert torch.equal(tok, G.local_tokens_ref(x, win))
     # and the layout is a feature permutation of the reference's unfold tokens (v3.py:1140)
     ny = H // win
@@ -102,7 +104,9 @@ def test_tokenize_global(B, H, C):
     L = _native.lib()
     x = dev(B, C, H, H, seed=1)
     tok = torch.empty(B * (H // 16) ** 2, 16 * C, device="cuda")
-    G.check(L.cfen_tokenize_global(G.ptr(U.to_nhwc(x)), G.ptr(tok), B, H, H, C, G.stream()))
+    xn = U.to_nhwc(x)
+    G.check(L.cfen_tokenize_global(G.ptr(xn), G.ptr(tok), B, H, H, C, G.stream()))
+    torch.cuda.synchronize()
     q = F.avg_pool2d(F.avg_pool2d(x, 2, 2), 2, 2)
     assert U.rel_err(tok, G.global_tokens_ref(q)) <= FP32_TOL
 
@@ -200,8 +204,10 @@ def test_merge_local_global(C, H, win):
     w, b = dev(C, 2 * C, 1, 1, seed=4, scale=0.1), dev(C, seed=5)
     anw, anb = dev(C, seed=6, scale=0.3), dev(C, seed=7)
     out = torch.empty(B, H, H, C, device="cuda")
-    G.check(L.cfen_merge_lg(G.ptr(G.local_tokens_ref(loc, win)), G.ptr(G.global_tokens_ref(gq)), G.ptr(U.to_nhwc(x)),
-                            G.ptr(w), G.ptr(b), G.ptr(anw), G.ptr(anb), G.ptr(out), B, H, H, C, win, G.stream()))
+    lt, gt, xn = G.local_tokens_ref(loc, win), G.global_tokens_ref(gq), U.to_nhwc(x)  # keep alive across the call
+    G.check(L.cfen_merge_lg(G.ptr(lt), G.ptr(gt), G.ptr(xn), G.ptr(w), G.ptr(b), G.ptr(anw), G.ptr(anb),
+                            G.ptr(out), B, H, H, C, win, G.stream()))
+    torch.cuda.synchronize()
     up = gq.double()
     for _ in range(2):
         up = F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False)
@@ -224,7 +230,9 @@ def test_cfsm(C, H):
     wcat = torch.cat([sd["m." + n + ".weight"].reshape(-1) for n in names]).contiguous()
     out = torch.empty(B, H, H, C, device="cuda")
     scratch = torch.empty(B * 64 * 2 * C + B * 2 * C, device="cuda")
-    G.check(L.cfen_cfsm(*(G.ptr(U.to_nhwc(t)) for t in xs), G.ptr(wcat), G.ptr(out), G.ptr(scratch), B, H, H, C,
+    nh = [U.to_nhwc(t) for t in xs]  # keep alive across the call
+    G.check(L.cfen_cfsm(G.ptr(nh[0]), G.ptr(nh[1]), G.ptr(nh[2]), G.ptr(wcat), G.ptr(out), G.ptr(scratch), B, H, H, C,
                         G.stream()))
+    torch.cuda.synchronize()
     ref = orc.cfsm({k: v.cpu() for k, v in sd.items()}, "m", *(t.cpu() for t in xs))
     assert U.rel_err(U.to_nchw(out), ref) <= FP32_TOL * 5
