@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "cfen_plan_profile_json",
     "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
     "cfen_plan_stage_ptr",
-    "cfen_gemm_tf32", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
+    "cfen_gemm_tf32", "cfen_gemm_tc", "cfen_mlp_tc", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
     "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_cfsm", "cfen_merge_lg",
     "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward",
 )
@@ -60,6 +60,8 @@ def lib():
         L.cfen_forward_u8.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_plan_stage_ptr.argtypes = [vp, cp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
         L.cfen_gemm_tf32.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]
+        L.cfen_gemm_tc.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]
+        L.cfen_mlp_tc.argtypes = [vp] * 7 + [i32] * 3 + [vp]
         L.cfen_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
         L.cfen_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.cfen_tokenize_local.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]

@@ -10,9 +10,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
+#include <tuple>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -21,8 +23,10 @@
 #include "common.cuh"
 #include "conv_igemm.cuh"
 #include "dcn.cuh"
+#include "gemm_tc.cuh"
 #include "gemm_tf32.cuh"
 #include "map_kernels.cuh"
+#include "mlp_tc.cuh"
 #include "vit_kernels.cuh"
 
 using namespace cfen;
@@ -71,6 +75,8 @@ static cudaError_t set_kernel_attributes() {
   SETC(ConvUp96_48) SETC(ConvUp48_24) SETC(ConvUp24_12) SETC(ConvLg1) SETC(ConvLg2) SETC(ConvLg3)
   SETC(ConvSk96_48) SETC(ConvSk48_24) SETC(ConvTail7_3) SETC(ConvTail7_1)
 #undef SETC
+  if ((e = gemm_tc_set_attr()) != cudaSuccess) return e;
+  if ((e = mlp_tc_set_attr()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -154,8 +160,8 @@ static int conv_parts(int kind, int H, int W) {  // H, W = tile domain
   return (kind == K_UP3 || kind == K_UP2 || kind == K_UP1) ? tiles * 4 : tiles;
 }
 
-enum ProfClass { PC_GEMM, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
-static const char* kProfNames[PC_COUNT] = {"gemm_tf32", "attention", "layernorm", "tokenize", "conv_igemm",
+enum ProfClass { PC_GEMM, PC_MLP, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"gemm_tf32", "mlp_tc", "attention", "layernorm", "tokenize", "conv_igemm",
                                            "merge_lg", "instnorm", "cfsm", "misc"};
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
 
@@ -205,6 +211,9 @@ struct cfen_plan {
   float *u8_in = nullptr, *u8_xr = nullptr, *u8_xs = nullptr, *u8_xd = nullptr;
   long long launches = 0, launches_last = 0;
   bool calibrating = false;
+  int gemm_path = 0;  // 0: mma.sync TF32 (gemm_tf32.cuh), 1: tcgen05 + TMA (gemm_tc.cuh)
+  int fuse_mlp = 1;   // with gemm_path 1: FFN / MLP-head pairs run as one tcgen05 kernel (mlp_tc.cuh)
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
   // optional per-launch CUDA-event timing (cfen_plan_set_option("timing", 1))
   bool timing = false;
   std::vector<ProfRec> prof;
@@ -360,6 +369,8 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->cfg = *cfg;
   p->H = cfg->height; p->W = cfg->width; p->nbmax = cfg->max_batch; p->hr = cfg->hidden_dim_ratio;
   p->win = cfg->patch_size;
+  if (const char* gp = getenv("CFEN_GEMM_PATH")) p->gemm_path = atoi(gp) == 1 ? 1 : 0;
+  if (const char* fm = getenv("CFEN_FUSE_MLP")) p->fuse_mlp = atoi(fm) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
   plan_layout(p, true, true);  // dry run: sizes
@@ -405,6 +416,12 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
     p->timing = value != 0;
     return 0;
   }
+  if (strcmp(name, "gemm_path") == 0) {
+    if (value != 0 && value != 1) return fail(5, "gemm_path must be 0 (mma.sync) or 1 (tcgen05)");
+    p->gemm_path = (int)value;
+    return 0;
+  }
+  if (strcmp(name, "fuse_mlp") == 0) { p->fuse_mlp = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
     CU(cudaSetDevice(p->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -551,15 +568,55 @@ struct Launch {
   }
 };
 
+static int get_tmap(cfen_plan* p, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box,
+                    const CUtensorMap** out) {
+  auto key = std::make_tuple((const void*)ptr, rows, cols, box);
+  auto it = p->tmaps.find(key);
+  if (it == p->tmaps.end()) {
+    CUtensorMap m;
+    if (!make_tmap_rowmajor(&m, ptr, rows, cols, box))
+      return fail(11, "cuTensorMapEncodeTiled failed for [%llu x %llu] box %u", (unsigned long long)rows,
+                  (unsigned long long)cols, box);
+    it = p->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
 static int run_gemm(Run& r, const float* A, const float* W, float* C, int M, int N, int K, const float* bias,
                     const float* res, const float* pos, int period, int relu) {
   GemmEpilogue ep{bias, res, pos, period > 0 ? period : 1, relu};
   Launch l(r, PC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)));
+  if (r.p->gemm_path == 1) {
+    const int BN = gemm_tc_pick_bn(M, N);
+    const CUtensorMap *ta, *tw, *tcm, *trm;
+    RET(get_tmap(r.p, A, M, K, 128, &ta));
+    RET(get_tmap(r.p, W, N, K, BN, &tw));
+    RET(get_tmap(r.p, C, M, N, 128, &tcm));
+    trm = tcm;
+    if (res && res != C) RET(get_tmap(r.p, res, M, N, 128, &trm));
+    CU(launch_gemm_tc(*ta, *tw, *tcm, *trm, BN, M, N, K, ep, r.st));
+    return 0;
+  }
   CU(launch_gemm_tf32(A, W, C, M, N, K, ep, r.st));
   return 0;
 }
 
 // Token algebra of one LViT/GViT call (reference v3.py:1143-1173 + encoder layer :1382-1390).
+// Y = R + b2 + relu(X W1^T + b1) W2^T as one kernel (hidden stays on chip)
+static int run_mlp(Run& r, const float* X, const float* W1, const float* b1, const float* W2, const float* b2,
+                   const float* R, float* Y, int M, int E, int hid) {
+  const CUtensorMap *tx, *t1, *t2, *tr, *ty;
+  RET(get_tmap(r.p, X, M, E, 128, &tx));
+  RET(get_tmap(r.p, W1, hid, E, MlpTcCfg::HC, &t1));
+  RET(get_tmap(r.p, W2, E, hid, E < 192 ? E : 192, &t2));
+  RET(get_tmap(r.p, Y, M, E, 128, &ty));
+  RET(get_tmap(r.p, R ? R : Y, M, E, 128, &tr));
+  MlpTcArgs a{b1, b2, R != nullptr, M, E, hid, {}};
+  Launch l(r, PC_MLP, 4.0 * M * E * hid, 4.0 * ((X == R ? 2.0 : 3.0) * M * E + 2.0 * E * hid));
+  CU(launch_mlp_tc(*tx, *t1, *t2, *tr, *ty, a, r.st));
+  return 0;
+}
 static int run_ln(Run& r, const float* x, float* y, const float* g, const float* b, int M, int E) {
   Launch l(r, PC_LN, 0.0, 8.0 * M * E);
   CU(launch_layernorm(x, y, g, b, M, E, 1e-5f, r.st));
@@ -578,6 +635,11 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq) {
   RET(run_attn(r, w.qkv, w.o, nseq, v.L, E, v.heads));
   RET(run_gemm(r, w.o, v.w_out, w.t1, M, E, E, nullptr, w.t1, nullptr, 0, 0));
   RET(run_ln(r, w.t1, w.h, v.ln2g, v.ln2b, M, E));
+  if (r.p->gemm_path == 1 && r.p->fuse_mlp && mlp_tc_supported(E, hid)) {
+    RET(run_mlp(r, w.h, v.w1, v.b1, v.w2, v.b2, w.t1, w.t1, M, E, hid));
+    RET(run_mlp(r, w.t1, v.wm0, v.bm0, v.wm3, v.bm3, w.t1, w.t1, M, E, hid));
+    return 0;
+  }
   RET(run_gemm(r, w.h, v.w1, w.f, M, hid, E, v.b1, nullptr, nullptr, 0, 1));
   RET(run_gemm(r, w.f, v.w2, w.t1, M, E, hid, v.b2, w.t1, nullptr, 0, 0));
   RET(run_gemm(r, w.t1, v.wm0, w.f, M, hid, E, v.bm0, nullptr, nullptr, 0, 1));
@@ -816,6 +878,37 @@ extern "C" int32_t cfen_gemm_tf32(const float* A, const float* W, float* C, int3
   CU(set_kernel_attributes());
   GemmEpilogue ep{bias, residual, pos, pos_period > 0 ? pos_period : 1, relu};
   CU(launch_gemm_tf32(A, W, C, M, N, K, ep, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int32_t cfen_gemm_tc(const float* A, const float* W, float* C, int32_t M, int32_t N, int32_t K,
+                                const float* bias, const float* residual, const float* pos, int32_t pos_period,
+                                int32_t relu, void* stream) {
+  if (!A || !W || !C) return fail(1, "cfen_gemm_tc: null argument");
+  if (N % 96 != 0 || K % 32 != 0) return fail(1, "cfen_gemm_tc: N must be a multiple of 96 and K of 32");
+  CU(set_kernel_attributes());
+  GemmEpilogue ep{bias, residual, pos, pos_period > 0 ? pos_period : 1, relu};
+  const int BN = gemm_tc_pick_bn(M, N);
+  CUtensorMap ta, tw, tcm, trm;
+  if (!make_tmap_rowmajor(&ta, A, M, K, 128) || !make_tmap_rowmajor(&tw, W, N, K, BN) ||
+      !make_tmap_rowmajor(&tcm, C, M, N, 128) || !make_tmap_rowmajor(&trm, residual ? residual : C, M, N, 128))
+    return fail(11, "cfen_gemm_tc: cuTensorMapEncodeTiled failed");
+  CU(launch_gemm_tc(ta, tw, tcm, trm, BN, M, N, K, ep, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int32_t cfen_mlp_tc(const float* X, const float* R, const float* W1, const float* b1, const float* W2,
+                               const float* b2, float* Y, int32_t M, int32_t E, int32_t hid, void* stream) {
+  if (!X || !R || !W1 || !b1 || !W2 || !b2 || !Y) return fail(1, "cfen_mlp_tc: null argument");
+  if (!mlp_tc_supported(E, hid)) return fail(1, "cfen_mlp_tc: E must be 96/192/384 and hid a multiple of 64");
+  CU(set_kernel_attributes());
+  CUtensorMap tx, t1, t2, tr, ty;
+  if (!make_tmap_rowmajor(&tx, X, M, E, 128) || !make_tmap_rowmajor(&t1, W1, hid, E, MlpTcCfg::HC) ||
+      !make_tmap_rowmajor(&t2, W2, E, hid, E < 192 ? E : 192) || !make_tmap_rowmajor(&tr, R, M, E, 128) ||
+      !make_tmap_rowmajor(&ty, Y, M, E, 128))
+    return fail(11, "cfen_mlp_tc: cuTensorMapEncodeTiled failed");
+  MlpTcArgs a{b1, b2, 1, M, E, hid, {}};
+  CU(launch_mlp_tc(tx, t1, t2, tr, ty, a, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

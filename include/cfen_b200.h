@@ -69,7 +69,8 @@ int32_t cfen_plan_pack_weights(cfen_plan* plan, void* stream);
 
 int64_t cfen_plan_workspace_bytes(const cfen_plan* plan);
 int64_t cfen_plan_launches_per_forward(const cfen_plan* plan); /* kernels per max_batch pass */
-/* options: "timing" (0/1): bracket every kernel launch with CUDA events on the launching stream */
+/* options: "timing" (0/1): bracket every kernel launch with CUDA events on the launching stream;
+ * "timing_reset"; "gemm_path" 0 = mma.sync TF32, 1 = tcgen05+TMA (env CFEN_GEMM_PATH sets the default) */
 int32_t cfen_plan_set_option(cfen_plan* plan, const char* name, int64_t value);
 /* JSON text with per-kernel-class {launches, ms, flops, bytes} of the last forward run with
  * "timing" on (algorithmic flops/bytes; used by bench.py's roofline).  Synchronises the device. */
@@ -103,6 +104,18 @@ int32_t cfen_plan_stage_ptr(cfen_plan* plan, const char* name, void** dev_ptr, i
 int32_t cfen_gemm_tf32(const float* A, const float* W, float* C, int32_t M, int32_t N, int32_t K,
                        const float* bias, const float* residual, const float* pos,
                        int32_t pos_period, int32_t relu, void* stream);
+
+/* Same contract on the tcgen05 path: TMA-fed 128xBNx32 tiles (SWIZZLE_128B), tcgen05.mma kind::tf32
+ * into a TMEM accumulator, tcgen05.ld epilogue. */
+int32_t cfen_gemm_tc(const float* A, const float* W, float* C, int32_t M, int32_t N, int32_t K,
+                     const float* bias, const float* residual, const float* pos,
+                     int32_t pos_period, int32_t relu, void* stream);
+
+/* Fused two-layer MLP, one tcgen05 kernel:  Y = R + b2 + relu(X W1^T + b1) W2^T  with X,R,Y [M,E],
+ * W1 [hid,E], W2 [E,hid] (nn.Linear layout).  FFN (v3.py:1387-1389) and mlp_head (v3.py:1173).
+ * E in {96,192,384}, hid % 64 == 0.  R may alias Y and X. */
+int32_t cfen_mlp_tc(const float* X, const float* R, const float* W1, const float* b1, const float* W2,
+                    const float* b2, float* Y, int32_t M, int32_t E, int32_t hid, void* stream);
 
 /* y[rows,E] = LayerNorm(x) * gamma + beta, biased variance (nn.LayerNorm, v3.py:1370-1371). */
 int32_t cfen_layernorm(const float* x, float* y, const float* gamma, const float* beta,

@@ -35,27 +35,48 @@ def dev(*shape, seed=0, scale=1.0):
 @pytest.mark.parametrize("M,N,K", [(1000, 96, 96), (300, 288, 96), (16, 1536, 1536), (64, 6144, 1536),
                                    (129, 384, 384), (2048, 96, 384), (4096, 192, 768)])
 @pytest.mark.parametrize("mode", ["plain", "bias_relu", "bias_res_pos", "inplace_res"])
-def test_gemm_tf32(M, N, K, mode):
+@pytest.mark.parametrize("path", ["mma_sync", "tcgen05"])
+def test_gemm_tf32(M, N, K, mode, path):
     L = _native.lib()
+    fn = L.cfen_gemm_tf32 if path == "mma_sync" else L.cfen_gemm_tc
     A, W = dev(M, K, seed=1), dev(N, K, seed=2, scale=K ** -0.5)
     bias, res, pos = dev(N, seed=3), dev(M, N, seed=4), dev(16, N, seed=5)
     C = torch.empty(M, N, device="cuda")
     ref = A.double() @ W.double().t()
     if mode == "plain":
-        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, None, None, None, 0, 0, G.stream()))
+        G.check(fn(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, None, None, None, 0, 0, G.stream()))
     elif mode == "bias_relu":
-        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, G.ptr(bias), None, None, 0, 1, G.stream()))
+        G.check(fn(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, G.ptr(bias), None, None, 0, 1, G.stream()))
         ref = torch.relu(ref + bias.double())
     elif mode == "bias_res_pos":
-        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, G.ptr(bias), G.ptr(res), G.ptr(pos), 16, 0,
+        G.check(fn(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, G.ptr(bias), G.ptr(res), G.ptr(pos), 16, 0,
                                  G.stream()))
         ref = ref + bias.double() + res.double() + pos.double()[torch.arange(M, device="cuda") % 16]
     else:
         C = res.clone()
-        G.check(L.cfen_gemm_tf32(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, None, G.ptr(C), None, 0, 0, G.stream()))
+        G.check(fn(G.ptr(A), G.ptr(W), G.ptr(C), M, N, K, None, G.ptr(C), None, 0, 0, G.stream()))
         ref = ref + res.double()
     torch.cuda.synchronize()
     assert U.rel_err(C, ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("M,E,hid", [(1000, 96, 384), (256, 96, 192), (4096, 192, 768), (130, 192, 384),
+                                     (1024, 384, 1536), (64, 384, 768), (16384, 96, 384)])
+@pytest.mark.parametrize("alias", ["none", "ffn_inplace", "head_inplace"])
+def test_mlp_tc(M, E, hid, alias):
+    """Fused FFN / MLP-head kernel vs fp64 torch; also the in-place forms the plan uses."""
+    L = _native.lib()
+    X, R = dev(M, E, seed=1), dev(M, E, seed=2)
+    W1, b1 = dev(hid, E, seed=3, scale=E ** -0.5), dev(hid, seed=4, scale=0.1)
+    W2, b2 = dev(E, hid, seed=5, scale=hid ** -0.5), dev(E, seed=6, scale=0.1)
+    if alias == "head_inplace":
+        R = X
+    ref = R.double() + b2.double() + torch.relu(X.double() @ W1.double().t() + b1.double()) @ W2.double().t()
+    Y = torch.empty(M, E, device="cuda") if alias == "none" else R
+    G.check(L.cfen_mlp_tc(G.ptr(X), G.ptr(R), G.ptr(W1), G.ptr(b1), G.ptr(W2), G.ptr(b2), G.ptr(Y), M, E, hid,
+                          G.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(Y, ref) <= TF32_TOL
 
 
 @pytest.mark.parametrize("rows,E", [(1001, 96), (257, 192), (64, 384), (33, 768), (16, 1536)])
