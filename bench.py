@@ -241,6 +241,8 @@ def run_ours(args):
             barrier()
         ms_total = e0.elapsed_time(e1)
         prof = plan.profile()
+        if os.environ.get("CFEN_BENCH_TRACE") and rank == 0:
+            plan.profile_trace(os.environ["CFEN_BENCH_TRACE"])
         plan.set_option("timing", 0)
         chunks = (B + plan.max_batch - 1) // plan.max_batch
         launches_per_step = plan.launches_per_forward * chunks

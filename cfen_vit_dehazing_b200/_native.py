@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     "cfen_abi_version", "cfen_last_error",
     "cfen_plan_create", "cfen_plan_destroy", "cfen_plan_set_weight", "cfen_plan_pack_weights",
     "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option",
-    "cfen_plan_profile_json",
+    "cfen_plan_profile_json", "cfen_plan_profile_trace",
     "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
     "cfen_plan_stage_ptr",
     "cfen_gemm_tf32", "cfen_gemm_tc", "cfen_mlp_tc", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
@@ -55,6 +55,7 @@ def lib():
         L.cfen_plan_launches_per_forward.restype = i64
         L.cfen_plan_set_option.argtypes = [vp, cp, i64]
         L.cfen_plan_profile_json.argtypes = [vp, cp, i64]
+        L.cfen_plan_profile_trace.argtypes = [vp, cp]
         L.cfen_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_forward_calibrate.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_forward_u8.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -86,6 +87,9 @@ def check(status):
 def chunk_images(height, batch):
     """Images processed per internal pass: bounds the workspace (~70 MB/image at 512x512)."""
     per = 16 if height <= 512 else 4
+    env = os.environ.get("CFEN_CHUNK_IMAGES")
+    if env:
+        per = max(1, int(env))
     return max(1, min(per, batch))
 
 
@@ -140,6 +144,10 @@ class Plan:
         buf = ctypes.create_string_buffer(4096)
         check(lib().cfen_plan_profile_json(self._h, buf, 4096))
         return json.loads(buf.value.decode())
+
+    def profile_trace(self, path):
+        """Per-launch CSV of the records profile() aggregates."""
+        check(lib().cfen_plan_profile_trace(self._h, str(path).encode()))
 
     def stage_ptr(self, name):
         p, n = ctypes.c_void_p(), ctypes.c_int64()

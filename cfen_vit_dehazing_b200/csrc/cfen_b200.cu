@@ -163,7 +163,7 @@ static int conv_parts(int kind, int H, int W) {  // H, W = tile domain
 enum ProfClass { PC_GEMM, PC_MLP, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"gemm_tf32", "mlp_tc", "attention", "layernorm", "tokenize", "conv_igemm",
                                            "merge_lg", "instnorm", "cfsm", "misc"};
-struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; char tag[56]; };
 
 struct ConvLayer {
   int kind = 0;
@@ -211,7 +211,7 @@ struct cfen_plan {
   float *u8_in = nullptr, *u8_xr = nullptr, *u8_xs = nullptr, *u8_xd = nullptr;
   long long launches = 0, launches_last = 0;
   bool calibrating = false;
-  int gemm_path = 0;  // 0: mma.sync TF32 (gemm_tf32.cuh), 1: tcgen05 + TMA (gemm_tc.cuh)
+  int gemm_path = 1;  // 1: tcgen05 + TMA (gemm_tc.cuh, default), 0: mma.sync TF32 (gemm_tf32.cuh, kept for A/B runs)
   int fuse_mlp = 1;   // with gemm_path 1: FFN / MLP-head pairs run as one tcgen05 kernel (mlp_tc.cuh)
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
   // optional per-launch CUDA-event timing (cfen_plan_set_option("timing", 1))
@@ -457,6 +457,23 @@ extern "C" int32_t cfen_plan_profile_json(cfen_plan* p, char* buf, int64_t cap) 
   return 0;
 }
 
+// Per-launch records (class, tag, ms, flops, bytes) as CSV into `path`; same lifetime as profile_json.
+extern "C" int32_t cfen_plan_profile_trace(cfen_plan* p, const char* path) {
+  if (!p || !path) return fail(1, "cfen_plan_profile_trace: bad argument");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaDeviceSynchronize());
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(1, "cfen_plan_profile_trace: cannot open %s", path);
+  fprintf(f, "class,tag,us,gflop,mbytes\n");
+  for (const ProfRec& r : p->prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    fprintf(f, "%s,%s,%.3f,%.4f,%.4f\n", kProfNames[r.cls], r.tag, t * 1e3, r.flops * 1e-9, r.bytes * 1e-6);
+  }
+  fclose(f);
+  return 0;
+}
+
 static int lookup(cfen_plan* p, const std::string& key, int64_t numel, const float** out) {
   auto it = p->reg.find(key);
   if (it == p->reg.end()) return fail(6, "weight '%s' was not registered", key.c_str());
@@ -553,9 +570,12 @@ struct Run {
 // Counts the launch and, when timing is on, brackets it with CUDA events on the launching stream.
 struct Launch {
   cfen_plan* p; cudaStream_t st; bool on; ProfRec rec;
-  Launch(Run& r, int cls, double flops, double bytes) : p(r.p), st(r.st), on(r.p->timing) {
+  Launch(Run& r, int cls, double flops, double bytes, const char* fmt = nullptr, ...)
+      : p(r.p), st(r.st), on(r.p->timing) {
     p->launches++;
     if (!on) return;
+    rec.tag[0] = 0;
+    if (fmt) { va_list ap; va_start(ap, fmt); vsnprintf(rec.tag, sizeof(rec.tag), fmt, ap); va_end(ap); }
     while (p->ev_pool.size() < p->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->ev_pool.push_back(e); }
     rec.cls = cls; rec.flops = flops; rec.bytes = bytes;
     rec.a = p->ev_pool[p->ev_used++]; rec.b = p->ev_pool[p->ev_used++];
@@ -586,7 +606,8 @@ static int get_tmap(cfen_plan* p, const float* ptr, uint64_t rows, uint64_t cols
 static int run_gemm(Run& r, const float* A, const float* W, float* C, int M, int N, int K, const float* bias,
                     const float* res, const float* pos, int period, int relu) {
   GemmEpilogue ep{bias, res, pos, period > 0 ? period : 1, relu};
-  Launch l(r, PC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)));
+  Launch l(r, PC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)),
+           "gemm M%d N%d K%d", M, N, K);
   if (r.p->gemm_path == 1) {
     const int BN = gemm_tc_pick_bn(M, N);
     const CUtensorMap *ta, *tw, *tcm, *trm;
@@ -613,17 +634,18 @@ static int run_mlp(Run& r, const float* X, const float* W1, const float* b1, con
   RET(get_tmap(r.p, Y, M, E, 128, &ty));
   RET(get_tmap(r.p, R ? R : Y, M, E, 128, &tr));
   MlpTcArgs a{b1, b2, R != nullptr, M, E, hid, {}};
-  Launch l(r, PC_MLP, 4.0 * M * E * hid, 4.0 * ((X == R ? 2.0 : 3.0) * M * E + 2.0 * E * hid));
+  Launch l(r, PC_MLP, 4.0 * M * E * hid, 4.0 * ((X == R ? 2.0 : 3.0) * M * E + 2.0 * E * hid), "mlp M%d E%d hid%d", M,
+           E, hid);
   CU(launch_mlp_tc(*tx, *t1, *t2, *tr, *ty, a, r.st));
   return 0;
 }
 static int run_ln(Run& r, const float* x, float* y, const float* g, const float* b, int M, int E) {
-  Launch l(r, PC_LN, 0.0, 8.0 * M * E);
+  Launch l(r, PC_LN, 0.0, 8.0 * M * E, "ln M%d E%d", M, E);
   CU(launch_layernorm(x, y, g, b, M, E, 1e-5f, r.st));
   return 0;
 }
 static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, int heads) {
-  Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 16.0 * nseq * L * E);
+  Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 16.0 * nseq * L * E, "attn n%d L%d E%d h%d", nseq, L, E, heads);
   CU(launch_attention(qkv, o, nseq, L, E, heads, r.st));
   return 0;
 }
@@ -635,7 +657,9 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq) {
   RET(run_attn(r, w.qkv, w.o, nseq, v.L, E, v.heads));
   RET(run_gemm(r, w.o, v.w_out, w.t1, M, E, E, nullptr, w.t1, nullptr, 0, 0));
   RET(run_ln(r, w.t1, w.h, v.ln2g, v.ln2b, M, E));
-  if (r.p->gemm_path == 1 && r.p->fuse_mlp && mlp_tc_supported(E, hid)) {
+  // the fused kernel parallelises over 128-row tiles only: below ~2/3 of a wave the unfused GEMMs
+  // (tiles over M x N) fill the machine better
+  if (r.p->gemm_path == 1 && r.p->fuse_mlp && mlp_tc_supported(E, hid) && (M + 127) / 128 >= 96) {
     RET(run_mlp(r, w.h, v.w1, v.b1, v.w2, v.b2, w.t1, w.t1, M, E, hid));
     RET(run_mlp(r, w.t1, v.wm0, v.bm0, v.wm3, v.bm3, w.t1, w.t1, M, E, hid));
     return 0;
@@ -670,7 +694,7 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
     const int cout = conv_cout(c.kind);
     const int parts = conv_parts(c.kind, H, W);
     a.scale = p->ones; a.shift = c.bias_src; a.flags = 0; a.stats = p->partials;
-    { Launch l(r, pcls, cflops, cbytes); CU(conv_launch_dispatch(c.kind, a, r.st)); }
+    { Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str()); CU(conv_launch_dispatch(c.kind, a, r.st)); }
     const long long count = (long long)r.nb * H * W * (is_up ? 4 : 1);
     Launch l(r, PC_NORM, 0.0, 0.0);
     actnorm_calibrate_kernel<<<1, 128, 0, r.st>>>(p->partials, r.nb * parts, cout, count, c.bias_src, c.an_w,
@@ -678,7 +702,7 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
     CU(cudaGetLastError());
   }
   a.scale = c.scale; a.shift = c.shift; a.flags = flags; a.stats = stats;
-  Launch l(r, pcls, cflops, cbytes);
+  Launch l(r, pcls, cflops, cbytes, "%s %dx%d", name.c_str(), H, W);
   CU(conv_launch_dispatch(c.kind, a, r.st));
   return 0;
 }
@@ -733,7 +757,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
   {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
-      Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4);
+      Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4, "tok_local H%d C%d", Hl, C);
       tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->lws.t0, r.nb, Hl, Hl, C, p->win);
       CU(cudaGetLastError());
     }
@@ -742,7 +766,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
   {
     const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
     {
-      Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17);
+      Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17, "tok_global H%d C%d", Hl, C);
       tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->gws.t0, r.nb, Hl, Hl, C);
       CU(cudaGetLastError());
     }
@@ -1033,15 +1057,49 @@ extern "C" int32_t cfen_cfsm(const float* x0, const float* x1, const float* x2, 
 }
 
 // ------------------------------------------------------------------------------------------
-// dcn (row A14) - implemented in dcn.cuh
+// dcn (row A14) - kernels in dcn.cuh
 // ------------------------------------------------------------------------------------------
+// Shape rules of shape_check (dcn/src/deform_conv_cuda.cpp:61-149) and of
+// modulated_deform_conv_cuda_forward (:503-509); errors come back as status 1 + message.
+static int dcn_check(const char* who, int B, int Cin, int H, int W, int Cout, int kH, int kW, int sH, int sW,
+                     int pH, int pW, int dH, int dW, int group, int dg, int* Ho, int* Wo) {
+  if (kW <= 0 || kH <= 0) return fail(1, "%s: kernel size should be greater than zero, but got kH: %d kW: %d", who, kH, kW);
+  if (sW <= 0 || sH <= 0) return fail(1, "%s: stride should be greater than zero, but got dH: %d dW: %d", who, sH, sW);
+  if (dW <= 0 || dH <= 0)
+    return fail(1, "%s: dilation should be greater than 0, but got dilationH: %d dilationW: %d", who, dH, dW);
+  if (B < 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || pH < 0 || pW < 0)
+    return fail(1, "%s: bad tensor extents", who);
+  if (group <= 0 || dg <= 0 || Cin % group != 0 || Cout % group != 0)
+    return fail(1, "%s: channels (%d in, %d out) must be divisible by group %d", who, Cin, Cout, group);
+  if (Cin % dg != 0) return fail(1, "%s: input channels must divide deformable group size", who);
+  *Ho = (H + 2 * pH - (dH * (kH - 1) + 1)) / sH + 1;
+  *Wo = (W + 2 * pW - (dW * (kW - 1) + 1)) / sW + 1;
+  if (*Ho < 1 || *Wo < 1 || H + 2 * pH < dH * (kH - 1) + 1 || W + 2 * pW < dW * (kW - 1) + 1)
+    return fail(1, "%s: Given input size: (%d x %d x %d). Calculated output size: (%d x %d x %d). Output size is too small",
+                who, Cin, H, W, Cout, *Ho, *Wo);
+  return 0;
+}
+
 extern "C" int32_t cfen_deform_conv2d_forward(const float* input, const float* weight, const float* offset,
                                               float* output, int32_t B, int32_t Cin, int32_t H, int32_t W,
                                               int32_t Cout, int32_t kH, int32_t kW, int32_t strideH,
                                               int32_t strideW, int32_t padH, int32_t padW, int32_t dilH,
                                               int32_t dilW, int32_t group, int32_t deformable_group,
                                               int32_t im2col_step, void* stream) {
-  return fail(10, "cfen_deform_conv2d_forward: not built yet");
+  if (!input || !weight || !offset || !output) return fail(1, "cfen_deform_conv2d_forward: null argument");
+  DcnArgs a{input, weight, nullptr, offset, nullptr, output, B, Cin, H, W, Cout, kH, kW, strideH, strideW,
+            padH, padW, dilH, dilW, group, deformable_group, 0, 0};
+  RET(dcn_check("cfen_deform_conv2d_forward", B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW, dilH, dilW,
+                group, deformable_group, &a.Ho, &a.Wo));
+  if (H < kH || W < kW) return fail(1, "cfen_deform_conv2d_forward: input image is smaller than kernel");
+  // the reference processes im2col_step images per im2col+GEMM round (deform_conv.py:39-40)
+  if (im2col_step <= 0 || (B > 0 && B % (im2col_step < B ? im2col_step : B) != 0))
+    return fail(1, "cfen_deform_conv2d_forward: im2col step must divide batchsize");
+  cudaError_t e = launch_deform_conv(a, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidConfiguration)
+    return fail(3, "cfen_deform_conv2d_forward: deformable_group*kH*kW = %d exceeds the on-chip offset tile", deformable_group * kH * kW);
+  CU(e);
+  return 0;
 }
 extern "C" int32_t cfen_modulated_deform_conv2d_forward(const float* input, const float* weight,
                                                         const float* bias, const float* offset,
@@ -1052,5 +1110,16 @@ extern "C" int32_t cfen_modulated_deform_conv2d_forward(const float* input, cons
                                                         int32_t dilH, int32_t dilW, int32_t group,
                                                         int32_t deformable_group, int32_t with_bias,
                                                         void* stream) {
-  return fail(10, "cfen_modulated_deform_conv2d_forward: not built yet");
+  if (!input || !weight || !offset || !mask || !output || (with_bias && !bias))
+    return fail(1, "cfen_modulated_deform_conv2d_forward: null argument");
+  DcnArgs a{input, weight, with_bias ? bias : nullptr, offset, mask, output, B, Cin, H, W, Cout, kH, kW,
+            strideH, strideW, padH, padW, dilH, dilW, group, deformable_group, 0, 0};
+  RET(dcn_check("cfen_modulated_deform_conv2d_forward", B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW,
+                dilH, dilW, group, deformable_group, &a.Ho, &a.Wo));
+  cudaError_t e = launch_deform_conv(a, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidConfiguration)
+    return fail(3, "cfen_modulated_deform_conv2d_forward: deformable_group*kH*kW = %d exceeds the on-chip offset tile",
+                deformable_group * kH * kW);
+  CU(e);
+  return 0;
 }

@@ -75,6 +75,8 @@ int32_t cfen_plan_set_option(cfen_plan* plan, const char* name, int64_t value);
 /* JSON text with per-kernel-class {launches, ms, flops, bytes} of the last forward run with
  * "timing" on (algorithmic flops/bytes; used by bench.py's roofline).  Synchronises the device. */
 int32_t cfen_plan_profile_json(cfen_plan* plan, char* buf, int64_t cap);
+/* Per-launch CSV (class,tag,us,gflop,mbytes) of the same records, written to `path`. */
+int32_t cfen_plan_profile_trace(cfen_plan* plan, const char* path);
 
 /* ---- the hot path: dec_ipt.forward (v3.py:392-1020) ----
  * in  [batch,3,H,W];  xr [batch,3,H,W], xs [batch,1,H,W], xd [batch,3,H,W]  (v3.py:1020). */

@@ -1,0 +1,114 @@
+"""CPU experiment (build container): output error of the v3 forward when GEMM operands are rounded to
+TF32 / fp16 / bf16 (fp32 accumulation), measured against the fp32 oracle.  Decides which operand
+formats the tensor-core kernels may use under the 1e-2 max-abs gate.
+
+    python tools/precision_probe.py [--size 512] [--hr 4] [--seeds 1 2]
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cfen_vit_dehazing_b200 as prod  # noqa: E402
+from oracle import cfen_oracle as orc  # noqa: E402
+
+
+def r_tf32(x):
+    xi = x.contiguous().view(torch.int32)
+    xi = (xi + 0x1000) & ~0x1FFF   # round-to-nearest (ties away), 10-bit mantissa
+    return xi.view(torch.float32)
+
+
+def r_f16(x):
+    return x.half().float()
+
+
+def r_bf16(x):
+    return x.bfloat16().float()
+
+
+ROUND = {"f32": lambda x: x, "tf32": r_tf32, "f16": r_f16, "bf16": r_bf16}
+
+
+@contextlib.contextmanager
+def patched(lin_a, lin_w, conv, attn):
+    lin0, conv0, convt0, sm0 = F.linear, F.conv2d, F.conv_transpose2d, torch.softmax
+    ra, rw, rc, rt = ROUND[lin_a], ROUND[lin_w], ROUND[conv], ROUND[attn]
+
+    def linear(x, w, b=None):
+        return lin0(ra(x), rw(w), b)
+
+    def conv2d(x, w, b=None, **kw):
+        return conv0(rc(x), rc(w), b, **kw)
+
+    def convt(x, w, b=None, **kw):
+        return convt0(rc(x), rc(w), b, **kw)
+
+    F.linear, F.conv2d, F.conv_transpose2d = linear, conv2d, convt
+    # attention operands: patch vit_block's matmuls by wrapping torch.softmax + Tensor.__matmul__ is intrusive;
+    # instead re-implement the attention core with rounding
+    vb0 = orc.vit_block
+
+    def vit_block(sd, prefix, t, heads):
+        import math
+        n, l, e = t.shape
+        hd = e // heads
+        t = F.linear(t, sd[prefix + ".linear_encoding.weight"], sd[prefix + ".linear_encoding.bias"]) + t
+        t = t + sd[prefix + ".position_encoding.pe.weight"][:l].unsqueeze(0)
+        enc = prefix + ".encoder.layers.0"
+        h = F.layer_norm(t, (e,), sd[enc + ".norm1.weight"], sd[enc + ".norm1.bias"], 1e-5)
+        qkv = rt(F.linear(h, sd[enc + ".self_attn.in_proj_weight"]))
+        q, k, v = (z.view(n, l, heads, hd).transpose(1, 2) for z in qkv.split(e, dim=-1))
+        s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))
+        att = rt(torch.softmax(s, dim=-1))
+        o = (att @ v).transpose(1, 2).reshape(n, l, e)
+        t = t + F.linear(o, sd[enc + ".self_attn.out_proj.weight"])
+        h = F.layer_norm(t, (e,), sd[enc + ".norm2.weight"], sd[enc + ".norm2.bias"], 1e-5)
+        h = F.relu(F.linear(h, sd[enc + ".linear1.weight"], sd[enc + ".linear1.bias"]))
+        t = t + F.linear(h, sd[enc + ".linear2.weight"], sd[enc + ".linear2.bias"])
+        h = F.relu(F.linear(t, sd[prefix + ".mlp_head.0.weight"], sd[prefix + ".mlp_head.0.bias"]))
+        t = t + F.linear(h, sd[prefix + ".mlp_head.3.weight"], sd[prefix + ".mlp_head.3.bias"])
+        return t
+
+    orc.vit_block = vit_block
+    try:
+        yield
+    finally:
+        F.linear, F.conv2d, F.conv_transpose2d = lin0, conv0, convt0
+        orc.vit_block = vb0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--hr", type=int, default=4)
+    ap.add_argument("--seeds", type=int, nargs="+", default=[1, 2])
+    a = ap.parse_args()
+    modes = [("tf32 everywhere", "tf32", "tf32", "tf32", "tf32"),
+             ("f16 linears+attn, tf32 convs", "f16", "f16", "tf32", "f16"),
+             ("f16 everywhere", "f16", "f16", "f16", "f16"),
+             ("f16 linears, bf16 attn, tf32 convs", "f16", "f16", "tf32", "bf16"),
+             ("bf16 linears (for scale)", "bf16", "bf16", "tf32", "bf16")]
+    for seed in a.seeds:
+        opt = orc.default_opt(a.hr, a.size)
+        torch.manual_seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = prod.define_G(opt, prod.common.default_conv)
+        x0, x1 = orc.make_inputs(a.size, [1, 1])
+        sd = orc.prime(net.state_dict(), x0)
+        ref = orc.forward(sd, x1)
+        for name, la, lw, cv, at in modes:
+            with patched(la, lw, cv, at):
+                out = orc.forward(sd, x1)
+            worst = max((o - r).abs().max().item() / 2 for o, r in zip(out, ref))
+            ps = min(orc.psnr01(o, r) for o, r in zip(out, ref))
+            print("seed %d  %-38s max|d| on [0,1] = %.5f   min PSNR = %.1f dB" % (seed, name, worst, ps), flush=True)
+
+
+if __name__ == "__main__":
+    main()
