@@ -23,11 +23,15 @@
 #include "common.cuh"
 #include "conv_igemm.cuh"
 #include "dcn.cuh"
+#include "attn16.cuh"
+#include "gemm16.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tf32.cuh"
 #include "map_kernels.cuh"
+#include "mlp16.cuh"
 #include "mlp_tc.cuh"
 #include "vit_kernels.cuh"
+#include "vit_tail16.cuh"
 
 using namespace cfen;
 
@@ -77,6 +81,10 @@ static cudaError_t set_kernel_attributes() {
 #undef SETC
   if ((e = gemm_tc_set_attr()) != cudaSuccess) return e;
   if ((e = mlp_tc_set_attr()) != cudaSuccess) return e;
+  if ((e = gemm16_set_attr()) != cudaSuccess) return e;
+  if ((e = mlp16_set_attr()) != cudaSuccess) return e;
+  if ((e = attention16_set_attr()) != cudaSuccess) return e;
+  if ((e = tail16_set_attr()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -178,9 +186,10 @@ struct VitW {
   int E = 0, hid = 0, L = 0, heads = 0, C = 0, P2 = 0;
   float *w_le, *b_le, *pos, *ln1g, *ln1b, *w_in, *w_out, *w1, *b1, *w2, *b2, *ln2g, *ln2b, *wm0, *bm0,
       *wm3, *bm3;
+  __half *h_le, *h_in, *h_out, *h_1, *h_2, *h_m0, *h_m3;  // fp16 operand copies (gemm_path 2)
 };
 
-struct TokWs { float *t0, *t1, *h, *qkv, *o, *f; };
+struct TokWs { float *t0, *t1, *h, *qkv, *o, *f; __half *x16, *h16, *qkv16, *o16, *f16; };
 
 struct Arena {
   char* base = nullptr;
@@ -191,6 +200,7 @@ struct Arena {
     off += bytes;
     return p;
   }
+  __half* take16(size_t halves) { return reinterpret_cast<__half*>(take((halves + 1) / 2)); }
 };
 
 struct cfen_plan {
@@ -211,9 +221,13 @@ struct cfen_plan {
   float *u8_in = nullptr, *u8_xr = nullptr, *u8_xs = nullptr, *u8_xd = nullptr;
   long long launches = 0, launches_last = 0;
   bool calibrating = false;
-  int gemm_path = 1;  // 1: tcgen05 + TMA (gemm_tc.cuh, default), 0: mma.sync TF32 (gemm_tf32.cuh, kept for A/B runs)
-  int fuse_mlp = 1;   // with gemm_path 1: FFN / MLP-head pairs run as one tcgen05 kernel (mlp_tc.cuh)
+  // 2: fp16 operands on tcgen05 + TMA (gemm16 / mlp16 / attn16, default); 1: TF32 tcgen05 (gemm_tc / mlp_tc);
+  // 0: TF32 mma.sync (gemm_tf32).  1 and 0 are kept for A/B runs.
+  int gemm_path = 2;
+  int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
+  int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
+  std::map<std::tuple<const void*, int, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> tmaps2;
   // optional per-launch CUDA-event timing (cfen_plan_set_option("timing", 1))
   bool timing = false;
   std::vector<ProfRec> prof;
@@ -258,6 +272,8 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
         v.w1 = a.take(hd * E); v.b1 = a.take(hd); v.w2 = a.take(E * hd); v.b2 = a.take(E);
         v.ln2g = a.take(E); v.ln2b = a.take(E); v.wm0 = a.take(hd * E); v.bm0 = a.take(hd);
         v.wm3 = a.take(E * hd); v.bm3 = a.take(E);
+        v.h_le = a.take16(E * E); v.h_in = a.take16(3 * E * E); v.h_out = a.take16(E * E);
+        v.h_1 = a.take16(hd * E); v.h_2 = a.take16(E * hd); v.h_m0 = a.take16(hd * E); v.h_m3 = a.take16(E * hd);
       }
     }
     for (auto& kv : p->conv) {
@@ -278,9 +294,13 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
     const size_t lt = 6 * HH * nb;
     p->lws.t0 = a.take(lt); p->lws.t1 = a.take(lt); p->lws.h = a.take(lt); p->lws.o = a.take(lt);
     p->lws.qkv = a.take(3 * lt); p->lws.f = a.take(lt * hr);
+    p->lws.x16 = a.take16(lt); p->lws.h16 = a.take16(lt); p->lws.o16 = a.take16(lt);
+    p->lws.qkv16 = a.take16(3 * lt); p->lws.f16 = a.take16(lt * hr);
     const size_t gt = (size_t)(H / 32) * (H / 32) * 384 * nb;  // global: Lg*E largest on level 1
     p->gws.t0 = a.take(gt); p->gws.t1 = a.take(gt); p->gws.h = a.take(gt); p->gws.o = a.take(gt);
     p->gws.qkv = a.take(3 * gt); p->gws.f = a.take(gt * hr);
+    p->gws.x16 = a.take16(gt); p->gws.h16 = a.take16(gt); p->gws.o16 = a.take16(gt);
+    p->gws.qkv16 = a.take16(3 * gt); p->gws.f16 = a.take16(gt * hr);
     auto add = [&](const char* name, size_t per_image) {
       p->stage[name] = std::make_pair(a.take(per_image * nb), (int64_t)per_image);
     };
@@ -369,8 +389,12 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->cfg = *cfg;
   p->H = cfg->height; p->W = cfg->width; p->nbmax = cfg->max_batch; p->hr = cfg->hidden_dim_ratio;
   p->win = cfg->patch_size;
-  if (const char* gp = getenv("CFEN_GEMM_PATH")) p->gemm_path = atoi(gp) == 1 ? 1 : 0;
+  if (const char* gp = getenv("CFEN_GEMM_PATH")) {
+    const int v = atoi(gp);
+    p->gemm_path = (v >= 0 && v <= 2) ? v : 2;
+  }
   if (const char* fm = getenv("CFEN_FUSE_MLP")) p->fuse_mlp = atoi(fm) != 0;
+  if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
   plan_layout(p, true, true);  // dry run: sizes
@@ -417,11 +441,12 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
     return 0;
   }
   if (strcmp(name, "gemm_path") == 0) {
-    if (value != 0 && value != 1) return fail(5, "gemm_path must be 0 (mma.sync) or 1 (tcgen05)");
+    if (value < 0 || value > 2) return fail(5, "gemm_path must be 0 (mma.sync tf32), 1 (tcgen05 tf32) or 2 (tcgen05 fp16)");
     p->gemm_path = (int)value;
     return 0;
   }
   if (strcmp(name, "fuse_mlp") == 0) { p->fuse_mlp = value != 0; return 0; }
+  if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
     CU(cudaSetDevice(p->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -485,10 +510,10 @@ static int lookup(cfen_plan* p, const std::string& key, int64_t numel, const flo
 }
 
 static int pack_linear(cfen_plan* p, const std::string& key, float* dst, int rows, int cols, bool prow,
-                       bool pcol, int C, int P2, bool round, cudaStream_t st) {
+                       bool pcol, int C, int P2, bool round, cudaStream_t st, __half* dst16 = nullptr) {
   const float* src;
   RET(lookup(p, key, (int64_t)rows * cols, &src));
-  pack_linear_kernel<<<ew_blocks((long long)rows * cols), 256, 0, st>>>(src, dst, rows, cols, prow, pcol, C,
+  pack_linear_kernel<<<ew_blocks((long long)rows * cols), 256, 0, st>>>(src, dst, dst16, rows, cols, prow, pcol, C,
                                                                        P2, round);
   CU(cudaGetLastError());
   return 0;
@@ -504,22 +529,22 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
       const std::string& pre = v.prefix;
       const std::string enc = pre + ".encoder.layers.0";
       const int E = v.E, hid = v.hid, C = v.C, P2 = v.P2;
-      RET(pack_linear(p, pre + ".linear_encoding.weight", v.w_le, E, E, true, true, C, P2, true, st));
+      RET(pack_linear(p, pre + ".linear_encoding.weight", v.w_le, E, E, true, true, C, P2, true, st, v.h_le));
       RET(pack_linear(p, pre + ".linear_encoding.bias", v.b_le, E, 1, true, false, C, P2, false, st));
       RET(pack_linear(p, pre + ".position_encoding.pe.weight", v.pos, v.L, E, false, true, C, P2, false, st));
       RET(pack_linear(p, enc + ".norm1.weight", v.ln1g, E, 1, true, false, C, P2, false, st));
       RET(pack_linear(p, enc + ".norm1.bias", v.ln1b, E, 1, true, false, C, P2, false, st));
-      RET(pack_linear(p, enc + ".self_attn.in_proj_weight", v.w_in, 3 * E, E, false, true, C, P2, true, st));
-      RET(pack_linear(p, enc + ".self_attn.out_proj.weight", v.w_out, E, E, true, false, C, P2, true, st));
-      RET(pack_linear(p, enc + ".linear1.weight", v.w1, hid, E, false, true, C, P2, true, st));
+      RET(pack_linear(p, enc + ".self_attn.in_proj_weight", v.w_in, 3 * E, E, false, true, C, P2, true, st, v.h_in));
+      RET(pack_linear(p, enc + ".self_attn.out_proj.weight", v.w_out, E, E, true, false, C, P2, true, st, v.h_out));
+      RET(pack_linear(p, enc + ".linear1.weight", v.w1, hid, E, false, true, C, P2, true, st, v.h_1));
       RET(pack_linear(p, enc + ".linear1.bias", v.b1, hid, 1, false, false, C, P2, false, st));
-      RET(pack_linear(p, enc + ".linear2.weight", v.w2, E, hid, true, false, C, P2, true, st));
+      RET(pack_linear(p, enc + ".linear2.weight", v.w2, E, hid, true, false, C, P2, true, st, v.h_2));
       RET(pack_linear(p, enc + ".linear2.bias", v.b2, E, 1, true, false, C, P2, false, st));
       RET(pack_linear(p, enc + ".norm2.weight", v.ln2g, E, 1, true, false, C, P2, false, st));
       RET(pack_linear(p, enc + ".norm2.bias", v.ln2b, E, 1, true, false, C, P2, false, st));
-      RET(pack_linear(p, pre + ".mlp_head.0.weight", v.wm0, hid, E, false, true, C, P2, true, st));
+      RET(pack_linear(p, pre + ".mlp_head.0.weight", v.wm0, hid, E, false, true, C, P2, true, st, v.h_m0));
       RET(pack_linear(p, pre + ".mlp_head.0.bias", v.bm0, hid, 1, false, false, C, P2, false, st));
-      RET(pack_linear(p, pre + ".mlp_head.3.weight", v.wm3, E, hid, true, false, C, P2, true, st));
+      RET(pack_linear(p, pre + ".mlp_head.3.weight", v.wm3, E, hid, true, false, C, P2, true, st, v.h_m3));
       RET(pack_linear(p, pre + ".mlp_head.3.bias", v.bm3, E, 1, true, false, C, P2, false, st));
     }
   for (auto& kv : p->conv) {
@@ -603,6 +628,85 @@ static int get_tmap(cfen_plan* p, const float* ptr, uint64_t rows, uint64_t cols
   return 0;
 }
 
+static int get_tmap2(cfen_plan* p, const void* ptr, int esize, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                     uint32_t box_rows, const CUtensorMap** out) {
+  auto key = std::make_tuple(ptr, esize, rows, cols, box_cols, box_rows);
+  auto it = p->tmaps2.find(key);
+  if (it == p->tmaps2.end()) {
+    CUtensorMap m;
+    if (!make_tmap_2d(&m, ptr, esize, rows, cols, box_cols, box_rows))
+      return fail(11, "cuTensorMapEncodeTiled failed for %d-byte [%llu x %llu] box %u x %u", esize,
+                  (unsigned long long)rows, (unsigned long long)cols, box_cols, box_rows);
+    it = p->tmaps2.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// fp16-operand Linear: C32 and / or C16 = epi(A16 * W16^T)
+static int run_gemm16(Run& r, const __half* A, const __half* W, float* C32, __half* C16, int M, int N, int K,
+                      const float* bias, const float* res, const float* pos, int period, int relu) {
+  const int BN = gemm16_pick_bn(M, N);
+  const CUtensorMap *ta, *tw, *tc32, *tr, *tc16;
+  RET(get_tmap2(r.p, A, 2, M, K, 64, 128, &ta));
+  RET(get_tmap2(r.p, W, 2, N, K, 64, BN, &tw));
+  tc32 = tr = tc16 = ta;  // unused maps still need a valid object
+  if (C32) RET(get_tmap2(r.p, C32, 4, M, N, 32, 128, &tc32));
+  if (res) RET(get_tmap2(r.p, res, 4, M, N, 32, 128, &tr));
+  if (C16) RET(get_tmap2(r.p, C16, 2, M, N, 32, 128, &tc16));
+  Gemm16Epilogue ep{bias, pos, period > 0 ? period : 1, relu, res != nullptr, C32 != nullptr, C16 != nullptr};
+  Launch l(r, PC_GEMM, 2.0 * M * N * K,
+           2.0 * ((double)M * K + (double)N * K) + (double)M * N * ((C32 ? 4 : 0) + (C16 ? 2 : 0) + (res ? 4 : 0)),
+           "gemm16 M%d N%d K%d", M, N, K);
+  CU(launch_gemm16(*ta, *tw, *tc32, *tr, *tc16, BN, M, N, K, ep, r.st));
+  return 0;
+}
+// Y32 / Y16 = R + b2 + relu(X16 W1^T + b1) W2^T as one kernel (hidden stays on chip)
+static int run_mlp16(Run& r, const __half* X, const __half* W1, const float* b1, const __half* W2, const float* b2,
+                     const float* R, float* Y32, __half* Y16, int M, int E, int hid) {
+  const Mlp16Shape sh = mlp16_shape(E);
+  const CUtensorMap *tx, *t1, *t2, *tr, *ty32, *ty16;
+  RET(get_tmap2(r.p, X, 2, M, E, 64, 128, &tx));
+  RET(get_tmap2(r.p, W1, 2, hid, E, 64, 64, &t1));
+  RET(get_tmap2(r.p, W2, 2, E, hid, 64, sh.NB2, &t2));
+  RET(get_tmap2(r.p, R, 4, M, E, 32, 128, &tr));
+  ty32 = ty16 = tr;
+  if (Y32) RET(get_tmap2(r.p, Y32, 4, M, E, 32, 128, &ty32));
+  if (Y16) RET(get_tmap2(r.p, Y16, 2, M, E, 32, 128, &ty16));
+  Mlp16Args a{b1, b2, Y32 != nullptr, Y16 != nullptr, M, E, hid, {}};
+  Launch l(r, PC_MLP, 4.0 * M * E * hid,
+           (double)M * E * (2 + 4 + (Y32 ? 4 : 0) + (Y16 ? 2 : 0)) + 4.0 * E * hid, "mlp16 M%d E%d hid%d", M, E, hid);
+  CU(launch_mlp16(*tx, *t1, *t2, *tr, *ty32, *ty16, a, r.st));
+  return 0;
+}
+// t <- out-proj + LN + FFN + MLP head of one ViT call, in place on the fp32 token matrix t (vit_tail16.cuh)
+static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
+  const int E = v.E, hid = v.hid;
+  const CUtensorMap *to, *tt, *two, *t1, *t2, *m0, *m3;
+  RET(get_tmap2(r.p, O, 2, M, E, 64, 128, &to));
+  RET(get_tmap2(r.p, T, 4, M, E, 32, 128, &tt));
+  RET(get_tmap2(r.p, v.h_out, 2, E, E, 64, E, &two));
+  RET(get_tmap2(r.p, v.h_1, 2, hid, E, 64, 64, &t1));
+  RET(get_tmap2(r.p, v.h_2, 2, E, hid, 64, E, &t2));
+  RET(get_tmap2(r.p, v.h_m0, 2, hid, E, 64, 64, &m0));
+  RET(get_tmap2(r.p, v.h_m3, 2, E, hid, 64, E, &m3));
+  Tail16Args a{v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, E, hid, {}};
+  Launch l(r, PC_MLP, 2.0 * M * E * E + 8.0 * M * E * hid, (double)M * E * (2 + 4 + 4) + 2.0 * (E * E + 4.0 * E * hid),
+           "tail16 M%d E%d hid%d", M, E, hid);
+  CU(launch_tail16(*to, *tt, *two, *t1, *t2, *m0, *m3, *tt, a, r.st));
+  return 0;
+}
+static int run_ln16(Run& r, const float* x, __half* y16, const float* g, const float* b, int M, int E) {
+  Launch l(r, PC_LN, 0.0, 6.0 * M * E, "ln16 M%d E%d", M, E);
+  CU(launch_layernorm(x, nullptr, y16, g, b, M, E, 1e-5f, r.st));
+  return 0;
+}
+static int run_attn16(Run& r, const __half* qkv, __half* o, int nseq, int L, int E, int heads) {
+  Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 8.0 * nseq * L * E, "attn16 n%d L%d E%d h%d", nseq, L, E, heads);
+  CU(launch_attention16(qkv, o, nseq, L, E, heads, r.st));
+  return 0;
+}
+
 static int run_gemm(Run& r, const float* A, const float* W, float* C, int M, int N, int K, const float* bias,
                     const float* res, const float* pos, int period, int relu) {
   GemmEpilogue ep{bias, res, pos, period > 0 ? period : 1, relu};
@@ -641,7 +745,7 @@ static int run_mlp(Run& r, const float* X, const float* W1, const float* b1, con
 }
 static int run_ln(Run& r, const float* x, float* y, const float* g, const float* b, int M, int E) {
   Launch l(r, PC_LN, 0.0, 8.0 * M * E, "ln M%d E%d", M, E);
-  CU(launch_layernorm(x, y, g, b, M, E, 1e-5f, r.st));
+  CU(launch_layernorm(x, y, nullptr, g, b, M, E, 1e-5f, r.st));
   return 0;
 }
 static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, int heads) {
@@ -651,6 +755,26 @@ static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, 
 }
 static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq) {
   const int M = nseq * v.L, E = v.E, hid = v.hid;
+  if (r.p->gemm_path == 2) {  // fp16 operands, fp32 residual stream
+    RET(run_gemm16(r, w.x16, v.h_le, w.t1, nullptr, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
+    RET(run_ln16(r, w.t1, w.h16, v.ln1g, v.ln1b, M, E));
+    RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
+    RET(run_attn16(r, w.qkv16, w.o16, nseq, v.L, E, v.heads));
+    if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= 96) return run_tail16(r, v, w.o16, w.t1, M);
+    RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0));
+    RET(run_ln16(r, w.t1, w.h16, v.ln2g, v.ln2b, M, E));
+    const int bm = 128 * mlp16_shape(E).MH;
+    if (r.p->fuse_mlp && mlp16_supported(E, hid) && (M + bm - 1) / bm >= 64) {
+      RET(run_mlp16(r, w.h16, v.h_1, v.b1, v.h_2, v.b2, w.t1, w.t1, w.x16, M, E, hid));
+      RET(run_mlp16(r, w.x16, v.h_m0, v.bm0, v.h_m3, v.bm3, w.t1, w.t1, nullptr, M, E, hid));
+      return 0;
+    }
+    RET(run_gemm16(r, w.h16, v.h_1, nullptr, w.f16, M, hid, E, v.b1, nullptr, nullptr, 0, 1));
+    RET(run_gemm16(r, w.f16, v.h_2, w.t1, w.x16, M, E, hid, v.b2, w.t1, nullptr, 0, 0));
+    RET(run_gemm16(r, w.x16, v.h_m0, nullptr, w.f16, M, hid, E, v.bm0, nullptr, nullptr, 0, 1));
+    RET(run_gemm16(r, w.f16, v.h_m3, w.t1, nullptr, M, E, hid, v.bm3, w.t1, nullptr, 0, 0));
+    return 0;
+  }
   RET(run_gemm(r, w.t0, v.w_le, w.t1, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
   RET(run_ln(r, w.t1, w.h, v.ln1g, v.ln1b, M, E));
   RET(run_gemm(r, w.h, v.w_in, w.qkv, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
@@ -758,7 +882,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4, "tok_local H%d C%d", Hl, C);
-      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->lws.t0, r.nb, Hl, Hl, C, p->win);
+      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->lws.t0, p->lws.x16, r.nb, Hl, Hl, C, p->win);
       CU(cudaGetLastError());
     }
     RET(run_vit(r, p->lvit[si], p->lws, r.nb * nwin));
@@ -767,7 +891,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17, "tok_global H%d C%d", Hl, C);
-      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->gws.t0, r.nb, Hl, Hl, C);
+      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->gws.t0, p->gws.x16, r.nb, Hl, Hl, C);
       CU(cudaGetLastError());
     }
     RET(run_vit(r, p->gvit[si], p->gws, r.nb));
@@ -939,7 +1063,91 @@ extern "C" int32_t cfen_mlp_tc(const float* X, const float* R, const float* W1, 
 extern "C" int32_t cfen_layernorm(const float* x, float* y, const float* gamma, const float* beta, int32_t rows,
                                   int32_t E, float eps, void* stream) {
   if (!x || !y || !gamma || !beta) return fail(1, "cfen_layernorm: null argument");
-  CU(launch_layernorm(x, y, gamma, beta, rows, E, eps, static_cast<cudaStream_t>(stream)));
+  CU(launch_layernorm(x, y, nullptr, gamma, beta, rows, E, eps, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Debug: device buffer (>= 64 KB) that CTA 0 of mlp16 fills with (tag, clock64) pairs; nullptr disables.
+extern "C" int32_t cfen_debug_set_buffer(void* dev_buf) {
+  long long* p = static_cast<long long*>(dev_buf);
+  CU(cudaMemcpyToSymbol(g_dbg_buf, &p, sizeof(p)));
+  return 0;
+}
+// ---- fp16-operand generation (gemm_path 2) ----
+extern "C" int32_t cfen_f32_to_f16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst) return fail(1, "cfen_f32_to_f16: null argument");
+  f32_to_f16_kernel<<<ew_blocks((n + 1) / 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__half*>(dst), n);
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int32_t cfen_gemm_f16(const void* A16, const void* W16, float* C32, void* C16, int32_t M, int32_t N,
+                                 int32_t K, const float* bias, const float* residual, const float* pos,
+                                 int32_t pos_period, int32_t relu, void* stream) {
+  if (!A16 || !W16 || (!C32 && !C16)) return fail(1, "cfen_gemm_f16: null argument");
+  if (N % 96 != 0 || K % 16 != 0) return fail(1, "cfen_gemm_f16: N must be a multiple of 96 and K of 16");
+  CU(set_kernel_attributes());
+  const int BN = gemm16_pick_bn(M, N);
+  CUtensorMap ta, tw, tc32, tr, tc16;
+  bool ok = make_tmap_2d(&ta, A16, 2, M, K, 64, 128) && make_tmap_2d(&tw, W16, 2, N, K, 64, BN);
+  tc32 = tr = tc16 = ta;
+  if (ok && C32) ok = make_tmap_2d(&tc32, C32, 4, M, N, 32, 128);
+  if (ok && residual) ok = make_tmap_2d(&tr, residual, 4, M, N, 32, 128);
+  if (ok && C16) ok = make_tmap_2d(&tc16, C16, 2, M, N, 32, 128);
+  if (!ok) return fail(11, "cfen_gemm_f16: cuTensorMapEncodeTiled failed");
+  Gemm16Epilogue ep{bias, pos, pos_period > 0 ? pos_period : 1, relu, residual != nullptr, C32 != nullptr, C16 != nullptr};
+  CU(launch_gemm16(ta, tw, tc32, tr, tc16, BN, M, N, K, ep, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int32_t cfen_mlp_f16(const void* X16, const float* R, const void* W1_16, const float* b1,
+                                const void* W2_16, const float* b2, float* Y32, void* Y16, int32_t M, int32_t E,
+                                int32_t hid, void* stream) {
+  if (!X16 || !R || !W1_16 || !b1 || !W2_16 || !b2 || (!Y32 && !Y16)) return fail(1, "cfen_mlp_f16: null argument");
+  if (!mlp16_supported(E, hid)) return fail(1, "cfen_mlp_f16: E must be 96/192/384 and hid a multiple of 64 >= 128");
+  CU(set_kernel_attributes());
+  const Mlp16Shape sh = mlp16_shape(E);
+  CUtensorMap tx, t1, t2, tr, ty32, ty16;
+  bool ok = make_tmap_2d(&tx, X16, 2, M, E, 64, 128) && make_tmap_2d(&t1, W1_16, 2, hid, E, 64, 64) &&
+            make_tmap_2d(&t2, W2_16, 2, E, hid, 64, sh.NB2) && make_tmap_2d(&tr, R, 4, M, E, 32, 128);
+  ty32 = ty16 = tr;
+  if (ok && Y32) ok = make_tmap_2d(&ty32, Y32, 4, M, E, 32, 128);
+  if (ok && Y16) ok = make_tmap_2d(&ty16, Y16, 2, M, E, 32, 128);
+  if (!ok) return fail(11, "cfen_mlp_f16: cuTensorMapEncodeTiled failed");
+  Mlp16Args a{b1, b2, Y32 != nullptr, Y16 != nullptr, M, E, hid, {}};
+  CU(launch_mlp16(tx, t1, t2, tr, ty32, ty16, a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int32_t cfen_vit_tail_f16(const void* O16, const float* T, const void* Wout16, const float* ln_g,
+                                     const float* ln_b, const void* W1_16, const float* b1, const void* W2_16,
+                                     const float* b2, const void* M0_16, const float* bm0, const void* M3_16,
+                                     const float* bm3, float* Y, int32_t M, int32_t E, int32_t hid, void* stream) {
+  if (!O16 || !T || !Wout16 || !ln_g || !ln_b || !W1_16 || !b1 || !W2_16 || !b2 || !M0_16 || !bm0 || !M3_16 || !bm3 || !Y)
+    return fail(1, "cfen_vit_tail_f16: null argument");
+  if (!tail16_supported(E, hid)) return fail(1, "cfen_vit_tail_f16: E must be 96 or 192 and hid a multiple of 64 >= 128");
+  CU(set_kernel_attributes());
+  CUtensorMap to, tt, two, t1, t2, m0, m3, ty;
+  const bool ok = make_tmap_2d(&to, O16, 2, M, E, 64, 128) && make_tmap_2d(&tt, T, 4, M, E, 32, 128) &&
+                  make_tmap_2d(&two, Wout16, 2, E, E, 64, E) && make_tmap_2d(&t1, W1_16, 2, hid, E, 64, 64) &&
+                  make_tmap_2d(&t2, W2_16, 2, E, hid, 64, E) && make_tmap_2d(&m0, M0_16, 2, hid, E, 64, 64) &&
+                  make_tmap_2d(&m3, M3_16, 2, E, hid, 64, E) && make_tmap_2d(&ty, Y, 4, M, E, 32, 128);
+  if (!ok) return fail(11, "cfen_vit_tail_f16: cuTensorMapEncodeTiled failed");
+  Tail16Args a{ln_g, ln_b, b1, b2, bm0, bm3, M, E, hid, {}};
+  CU(launch_tail16(to, tt, two, t1, t2, m0, m3, ty, a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int32_t cfen_layernorm_f16(const float* x, void* y16, const float* gamma, const float* beta, int32_t rows,
+                                      int32_t E, float eps, void* stream) {
+  if (!x || !y16 || !gamma || !beta) return fail(1, "cfen_layernorm_f16: null argument");
+  CU(launch_layernorm(x, nullptr, static_cast<__half*>(y16), gamma, beta, rows, E, eps, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int32_t cfen_attention_f16(const void* qkv16, void* out16, int32_t nseq, int32_t L, int32_t E,
+                                      int32_t heads, void* stream) {
+  if (!qkv16 || !out16) return fail(1, "cfen_attention_f16: null argument");
+  if (heads <= 0 || E % heads != 0 || (E / heads != 24 && E / heads != 96))
+    return fail(1, "cfen_attention_f16: head dim must be 24 or 96");
+  CU(set_kernel_attributes());
+  CU(launch_attention16(static_cast<const __half*>(qkv16), static_cast<__half*>(out16), nseq, L, E, heads,
+                        static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -953,23 +1161,24 @@ extern "C" int32_t cfen_attention(const float* qkv, float* out, int32_t nseq, in
   return 0;
 }
 
-extern "C" int32_t cfen_tokenize_local(const float* map, float* tokens, int32_t B, int32_t H, int32_t W, int32_t C,
-                                       int32_t window, void* stream) {
+extern "C" int32_t cfen_tokenize_local(const float* map, float* tokens, void* tokens16, int32_t B, int32_t H,
+                                       int32_t W, int32_t C, int32_t window, void* stream) {
   if (!map || !tokens) return fail(1, "cfen_tokenize_local: null argument");
   if (C % 4 || window % 2 || H % window || W % window) return fail(1, "cfen_tokenize_local: bad shape");
   const long long n4 = (long long)B * H * W * C / 4;
-  tokenize_local_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(map, tokens, B, H, W, C,
-                                                                                    window);
+  tokenize_local_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      map, tokens, static_cast<__half*>(tokens16), B, H, W, C, window);
   CU(cudaGetLastError());
   return 0;
 }
 
-extern "C" int32_t cfen_tokenize_global(const float* map, float* tokens, int32_t B, int32_t H, int32_t W, int32_t C,
-                                        void* stream) {
+extern "C" int32_t cfen_tokenize_global(const float* map, float* tokens, void* tokens16, int32_t B, int32_t H,
+                                        int32_t W, int32_t C, void* stream) {
   if (!map || !tokens) return fail(1, "cfen_tokenize_global: null argument");
   if (C % 4 || H % 16 || W % 16) return fail(1, "cfen_tokenize_global: bad shape");
   const long long n4 = (long long)B * (H / 16) * (W / 16) * 16 * C / 4;
-  tokenize_global_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(map, tokens, B, H, W, C);
+  tokenize_global_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      map, tokens, static_cast<__half*>(tokens16), B, H, W, C);
   CU(cudaGetLastError());
   return 0;
 }

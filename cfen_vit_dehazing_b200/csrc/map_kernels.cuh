@@ -211,11 +211,21 @@ __global__ void f32nchw_to_u8hwc_kernel(const float* __restrict__ in, uint8_t* _
   }
 }
 
+// fp32 -> fp16 (round-to-nearest-even, saturating): test/bench helper for the fp16-operand kernels
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < n;
+       i += (long long)gridDim.x * blockDim.x * 2) {
+    if (i + 1 < n) *reinterpret_cast<uint32_t*>(dst + i) = pack_half2(src[i], src[i + 1]);
+    else dst[i] = __ushort_as_half((unsigned short)(pack_half2(src[i], 0.f) & 0xffffu));
+  }
+}
+
 // ---- nn.Linear weight packing for the ViTs: optional row/column permutation from unfold's
 // (c, ky, kx) feature order to the kernels' (ky, kx, c) order, TF32 rounding.
 // perm(f) for f = c*P2 + s (s = ky*p + kx):  s*C + c.
-__global__ void pack_linear_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows,
-                                   int cols, int perm_rows, int perm_cols, int C, int P2, int round) {
+__global__ void pack_linear_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                   __half* __restrict__ dst16, int rows, int cols, int perm_rows, int perm_cols,
+                                   int C, int P2, int round) {
   const long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -224,6 +234,7 @@ __global__ void pack_linear_kernel(const float* __restrict__ src, float* __restr
     const int cc = perm_cols ? (c % P2) * C + c / P2 : c;
     const float v = src[i];
     dst[(size_t)rr * cols + cc] = round ? round_tf32(v) : v;
+    if (dst16) dst16[(size_t)rr * cols + cc] = __ushort_as_half((unsigned short)(pack_half2(v, 0.f) & 0xffffu));
   }
 }
 

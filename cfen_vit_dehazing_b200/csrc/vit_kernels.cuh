@@ -12,7 +12,7 @@ namespace cfen {
 // One thread moves one float4.
 // =====================================================================================
 __global__ void tokenize_local_kernel(const float* __restrict__ map, float* __restrict__ tok,
-                                      int B, int H, int W, int C, int win) {
+                                      __half* __restrict__ tok16, int B, int H, int W, int C, int win) {
   const int E4 = C;  // 4C floats per token = C float4
   const int half = win >> 1, L = half * half;
   const int ny = H / win, nx = W / win;
@@ -31,6 +31,7 @@ __global__ void tokenize_local_kernel(const float* __restrict__ map, float* __re
     const int y = wy * win + 2 * ty + ky, x = wx * win + 2 * tx;
     const float4 v = *reinterpret_cast<const float4*>(map + (((size_t)b * H + y) * W + x) * C + rem);
     reinterpret_cast<float4*>(tok)[i] = v;
+    if (tok16) reinterpret_cast<uint2*>(tok16)[i] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
   }
 }
 
@@ -40,7 +41,7 @@ __global__ void tokenize_local_kernel(const float* __restrict__ map, float* __re
 // 4x4 block at (16ty+4ky, 16tx+4kx).  The two 2x2 means are taken in the reference's order.
 // =====================================================================================
 __global__ void tokenize_global_kernel(const float* __restrict__ map, float* __restrict__ tok,
-                                       int B, int H, int W, int C) {
+                                       __half* __restrict__ tok16, int B, int H, int W, int C) {
   const int C4 = C >> 2;
   const int gy = H >> 4, gx = W >> 4;
   const long long total = (long long)B * gy * gx * 16 * C4;
@@ -72,6 +73,7 @@ __global__ void tokenize_global_kernel(const float* __restrict__ map, float* __r
       }
     acc.x *= 0.25f; acc.y *= 0.25f; acc.z *= 0.25f; acc.w *= 0.25f;
     reinterpret_cast<float4*>(tok)[i] = acc;
+    if (tok16) reinterpret_cast<uint2*>(tok16)[i] = make_uint2(pack_half2(acc.x, acc.y), pack_half2(acc.z, acc.w));
   }
 }
 
@@ -82,8 +84,8 @@ __global__ void tokenize_global_kernel(const float* __restrict__ map, float* __r
 // =====================================================================================
 template <int MAXV>  // float4 slots per lane: E/4 <= 32*MAXV
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int rows, int E, float eps) {
+layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, __half* __restrict__ y16,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int E, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nv = E >> 2;
@@ -107,7 +109,8 @@ layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
-  float4* yr = reinterpret_cast<float4*>(y + (size_t)warp * E);
+  float4* yr = y ? reinterpret_cast<float4*>(y + (size_t)warp * E) : nullptr;
+  uint2* yh = y16 ? reinterpret_cast<uint2*>(y16 + (size_t)warp * E) : nullptr;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = i * 32 + lane;
@@ -119,19 +122,20 @@ layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float
       o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
       o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
       o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
-      yr[idx] = o;
+      if (yr) yr[idx] = o;
+      if (yh) yh[idx] = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
     }
   }
 }
 
-inline cudaError_t launch_layernorm(const float* x, float* y, const float* gamma, const float* beta,
+inline cudaError_t launch_layernorm(const float* x, float* y, __half* y16, const float* gamma, const float* beta,
                                     int rows, int E, float eps, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   if (E % 4 != 0 || E > 32 * 4 * 12) return cudaErrorInvalidValue;
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
-  if (E <= 384) layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, y, gamma, beta, rows, E, eps);
-  else layernorm_kernel<12><<<blocks, 256, 0, st>>>(x, y, gamma, beta, rows, E, eps);
+  if (E <= 384) layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, y, y16, gamma, beta, rows, E, eps);
+  else layernorm_kernel<12><<<blocks, 256, 0, st>>>(x, y, y16, gamma, beta, rows, E, eps);
   return cudaGetLastError();
 }
 

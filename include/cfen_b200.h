@@ -70,7 +70,7 @@ int32_t cfen_plan_pack_weights(cfen_plan* plan, void* stream);
 int64_t cfen_plan_workspace_bytes(const cfen_plan* plan);
 int64_t cfen_plan_launches_per_forward(const cfen_plan* plan); /* kernels per max_batch pass */
 /* options: "timing" (0/1): bracket every kernel launch with CUDA events on the launching stream;
- * "timing_reset"; "gemm_path" 0 = mma.sync TF32, 1 = tcgen05+TMA (env CFEN_GEMM_PATH sets the default) */
+ * "timing_reset"; "gemm_path" 2 = fp16 tcgen05+TMA (default), 1 = TF32 tcgen05, 0 = TF32 mma.sync (env CFEN_GEMM_PATH) */
 int32_t cfen_plan_set_option(cfen_plan* plan, const char* name, int64_t value);
 /* JSON text with per-kernel-class {launches, ms, flops, bytes} of the last forward run with
  * "timing" on (algorithmic flops/bytes; used by bench.py's roofline).  Synchronises the device. */
@@ -119,6 +119,33 @@ int32_t cfen_gemm_tc(const float* A, const float* W, float* C, int32_t M, int32_
 int32_t cfen_mlp_tc(const float* X, const float* R, const float* W1, const float* b1, const float* W2,
                     const float* b2, float* Y, int32_t M, int32_t E, int32_t hid, void* stream);
 
+/* ---- fp16-operand generation (the default path): fp16 carries TF32's 10-bit mantissa at twice
+ * the tensor rate and half the bytes; accumulation, residual stream and statistics stay fp32.
+ * fp16 buffers are passed as void* (IEEE binary16, row-major). */
+int32_t cfen_f32_to_f16(const float* src, void* dst_f16, int64_t n, void* stream);
+/* Debug aid: device buffer (>= 64 KB) that CTA 0 of the fused MLP fills with (tag, clock64) pairs; NULL = off. */
+int32_t cfen_debug_set_buffer(void* dev_buf);
+/* C32 and/or C16 [M,N] = epi(A16[M,K] * W16[N,K]^T) on tcgen05 kind::f16 (epi as cfen_gemm_tf32). */
+int32_t cfen_gemm_f16(const void* A16, const void* W16, float* C32, void* C16, int32_t M, int32_t N,
+                      int32_t K, const float* bias, const float* residual, const float* pos,
+                      int32_t pos_period, int32_t relu, void* stream);
+/* Fused MLP: Y = R + b2 + relu(X16 W1_16^T + b1) W2_16^T; X resident in smem, 256-row CTAs for E <= 192. */
+int32_t cfen_mlp_f16(const void* X16, const float* R, const void* W1_16, const float* b1,
+                     const void* W2_16, const float* b2, float* Y32, void* Y16, int32_t M, int32_t E,
+                     int32_t hid, void* stream);
+/* Second half of a ViT call as one kernel (E in {96,192}): Y = t2 + bm3 + relu(t2 Wm0^T + bm0) Wm3^T with
+ * t2 = t1 + b2 + relu(LN(t1) W1^T + b1) W2^T and t1 = T + O16 Wout^T (v3.py:1385-1389, 1173).  Y may alias T. */
+int32_t cfen_vit_tail_f16(const void* O16, const float* T, const void* Wout16, const float* ln_g,
+                          const float* ln_b, const void* W1_16, const float* b1, const void* W2_16,
+                          const float* b2, const void* M0_16, const float* bm0, const void* M3_16,
+                          const float* bm3, float* Y, int32_t M, int32_t E, int32_t hid, void* stream);
+/* LayerNorm with fp16 output (the A operand of the next Linear). */
+int32_t cfen_layernorm_f16(const float* x, void* y16, const float* gamma, const float* beta, int32_t rows,
+                           int32_t E, float eps, void* stream);
+/* Attention core on fp16 qkv[nseq*L,3E] -> fp16 out[nseq*L,E] (mma.sync m16n8k16, fp32 softmax). */
+int32_t cfen_attention_f16(const void* qkv16, void* out16, int32_t nseq, int32_t L, int32_t E,
+                           int32_t heads, void* stream);
+
 /* y[rows,E] = LayerNorm(x) * gamma + beta, biased variance (nn.LayerNorm, v3.py:1370-1371). */
 int32_t cfen_layernorm(const float* x, float* y, const float* gamma, const float* beta,
                        int32_t rows, int32_t E, float eps, void* stream);
@@ -130,12 +157,12 @@ int32_t cfen_attention(const float* qkv, float* out, int32_t nseq, int32_t L, in
 
 /* Window partition + unfold(p=2) of an NHWC map into tokens [B*nW*L, 4C] (v3.py:1025-1040,1140);
  * feature order (ky,kx,c). */
-int32_t cfen_tokenize_local(const float* map_nhwc, float* tokens, int32_t B, int32_t H, int32_t W,
-                            int32_t C, int32_t window, void* stream);
+int32_t cfen_tokenize_local(const float* map_nhwc, float* tokens, void* tokens_f16 /* optional fp16 copy */,
+                            int32_t B, int32_t H, int32_t W, int32_t C, int32_t window, void* stream);
 
 /* AvgPool2 twice + unfold(p=4) of an NHWC map into tokens [B*(H/16)*(W/16), 16C] (v3.py:1274-1275). */
-int32_t cfen_tokenize_global(const float* map_nhwc, float* tokens, int32_t B, int32_t H, int32_t W,
-                             int32_t C, void* stream);
+int32_t cfen_tokenize_global(const float* map_nhwc, float* tokens, void* tokens_f16 /* optional fp16 copy */,
+                             int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* One convolution-family layer on NHWC fp32 maps, selected by `kind`:
  *   "conv3x3_12_12", "ds_12_24", "ds_24_48", "ds_48_96", "up_96_48", "up_48_24", "up_24_12",

@@ -86,16 +86,20 @@ def test_forward_parity_1024():
 
 
 def test_batch_chunking_and_batch_invariance():
-    """B images in one call == the same images one by one (bitwise: kernels are batch-invariant),
-    including a batch larger than the plan's internal chunk (16 images at 512x512)."""
+    """A batch larger than the plan's internal chunk (16 images at <= 512x512) equals the same chunks run as
+    separate calls bit for bit; a single image differs from its in-batch result only by kernel selection
+    (fused / unfused token kernels are picked by tile count), far inside the parity gate."""
     gnet, sd0, sd1, x0 = _gpu_net(2, 128)
     x = orc.make_inputs(128, [1, 19])[1].cuda()
     with torch.no_grad():
         full = gnet(x)
+        head, tail = gnet(x[:16].contiguous()), gnet(x[16:].contiguous())
+        for a, b, c in zip(full, head, tail):
+            assert torch.equal(a[:16], b) and torch.equal(a[16:], c)
         for i in (0, 7, 18):
             one = gnet(x[i:i + 1].contiguous())
             for a, b in zip(full, one):
-                assert torch.equal(a[i:i + 1], b)
+                assert (a[i:i + 1] - b).abs().max().item() <= 4e-3     # raw [-1,1] scale; gate is 2e-2
 
 
 def test_actnorm_first_forward_calibration():

@@ -79,6 +79,139 @@ def test_mlp_tc(M, E, hid, alias):
     assert U.rel_err(Y, ref) <= TF32_TOL
 
 
+# ---------------------------------------------------------------------------------------------
+# fp16-operand generation (default path).  References are fp64 contractions of the SAME fp16-rounded
+# operands, so the tolerances only cover fp32 accumulation order and the fp16 rounding of outputs
+# (2^-11 relative) / of the on-chip hidden activation.
+# ---------------------------------------------------------------------------------------------
+F32OUT_TOL = 3e-5
+F16OUT_TOL = 1e-3
+
+
+def to_f16(x):
+    """fp32 -> fp16 through the library's converter (round-to-nearest-even, saturating)."""
+    y = torch.empty(x.shape, device="cuda", dtype=torch.float16)
+    G.check(_native.lib().cfen_f32_to_f16(G.ptr(x.contiguous()), G.ptr(y), x.numel(), G.stream()))
+    return y
+
+
+def test_f32_to_f16_matches_torch():
+    x = dev(1000, 37, seed=9, scale=50.0)
+    x[0, :4] = torch.tensor([1e6, -1e6, 65504.0, 1e-9], device="cuda")
+    y = to_f16(x)
+    torch.cuda.synchronize()
+    assert torch.equal(y, x.clamp(-65504, 65504).half())
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 96, 96), (300, 288, 96), (16, 1536, 1536), (64, 6144, 1536), (129, 384, 384),
+                                   (2048, 96, 384), (4096, 192, 768), (512, 768, 192), (8192, 576, 192),
+                                   (100, 1152, 384), (64, 768, 3072)])
+@pytest.mark.parametrize("mode", ["f32", "f16_bias_relu", "both_bias_res_pos", "f32_inplace_res"])
+def test_gemm_f16(M, N, K, mode):
+    L = _native.lib()
+    A, W = dev(M, K, seed=1), dev(N, K, seed=2, scale=K ** -0.5)
+    bias, res, pos = dev(N, seed=3), dev(M, N, seed=4), dev(16, N, seed=5)
+    A16, W16 = to_f16(A), to_f16(W)
+    ref = A16.double() @ W16.double().t()
+    C32 = torch.full((M, N), float("nan"), device="cuda")
+    C16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    fn = L.cfen_gemm_f16
+    if mode == "f32":
+        G.check(fn(G.ptr(A16), G.ptr(W16), G.ptr(C32), None, M, N, K, None, None, None, 0, 0, G.stream()))
+        outs = [(C32, F32OUT_TOL)]
+    elif mode == "f16_bias_relu":
+        G.check(fn(G.ptr(A16), G.ptr(W16), None, G.ptr(C16), M, N, K, G.ptr(bias), None, None, 0, 1, G.stream()))
+        ref = torch.relu(ref + bias.double())
+        outs = [(C16, F16OUT_TOL)]
+    elif mode == "both_bias_res_pos":
+        G.check(fn(G.ptr(A16), G.ptr(W16), G.ptr(C32), G.ptr(C16), M, N, K, G.ptr(bias), G.ptr(res), G.ptr(pos), 16, 0,
+                   G.stream()))
+        ref = ref + bias.double() + res.double() + pos.double()[torch.arange(M, device="cuda") % 16]
+        outs = [(C32, F32OUT_TOL), (C16, F16OUT_TOL)]
+    else:
+        C32 = res.clone()
+        G.check(fn(G.ptr(A16), G.ptr(W16), G.ptr(C32), None, M, N, K, None, G.ptr(C32), None, 0, 0, G.stream()))
+        ref = ref + res.double()
+        outs = [(C32, F32OUT_TOL)]
+    torch.cuda.synchronize()
+    for out, tol in outs:
+        assert U.rel_err(out, ref) <= tol
+
+
+@pytest.mark.parametrize("M,E,hid", [(1000, 96, 384), (256, 96, 192), (4096, 192, 768), (130, 192, 384),
+                                     (1024, 384, 1536), (64, 384, 768), (16384, 96, 384), (8200, 192, 384),
+                                     (300, 384, 1536)])
+@pytest.mark.parametrize("mode", ["ffn_inplace_both", "head_inplace_f32", "separate_f16"])
+def test_mlp_f16(M, E, hid, mode):
+    """Fused FFN / MLP-head kernel vs fp64 torch on the same fp16 operands (hidden rounded to fp16 like the kernel)."""
+    L = _native.lib()
+    X, R = dev(M, E, seed=1), dev(M, E, seed=2, scale=3.0)
+    W1, b1 = dev(hid, E, seed=3, scale=E ** -0.5), dev(hid, seed=4, scale=0.1)
+    W2, b2 = dev(E, hid, seed=5, scale=hid ** -0.5), dev(E, seed=6, scale=0.1)
+    X16, W1h, W2h = to_f16(X), to_f16(W1), to_f16(W2)
+    hidden = torch.relu(X16.double() @ W1h.double().t() + b1.double()).float().half().double()
+    ref = R.double() + b2.double() + hidden @ W2h.double().t()
+    Y32 = R.clone() if mode != "separate_f16" else None
+    Y16 = torch.full((M, E), float("nan"), device="cuda", dtype=torch.float16) if mode != "head_inplace_f32" else None
+    G.check(L.cfen_mlp_f16(G.ptr(X16), G.ptr(Y32 if Y32 is not None else R), G.ptr(W1h), G.ptr(b1), G.ptr(W2h),
+                           G.ptr(b2), G.ptr(Y32), G.ptr(Y16), M, E, hid, G.stream()))
+    torch.cuda.synchronize()
+    if Y32 is not None:
+        assert U.rel_err(Y32, ref) <= 2e-4      # fp16 rounding of the hidden activation can flip at ties
+    if Y16 is not None:
+        assert U.rel_err(Y16, ref) <= F16OUT_TOL
+
+
+@pytest.mark.parametrize("M,E,hid", [(1000, 96, 384), (256, 96, 192), (4096, 192, 768), (130, 192, 384), (20000, 96, 384)])
+@pytest.mark.parametrize("inplace", [True, False])
+def test_vit_tail_f16(M, E, hid, inplace):
+    """out-proj + LayerNorm + FFN + MLP head chained in one kernel vs fp64 torch with the kernel's fp16 roundings."""
+    L = _native.lib()
+    O, T = dev(M, E, seed=1), dev(M, E, seed=2, scale=3.0)
+    Wo = dev(E, E, seed=3, scale=E ** -0.5)
+    g, b = 1.0 + 0.1 * dev(E, seed=4), 0.1 * dev(E, seed=5)
+    W1, b1 = dev(hid, E, seed=6, scale=E ** -0.5), dev(hid, seed=7, scale=0.1)
+    W2, b2 = dev(E, hid, seed=8, scale=hid ** -0.5), dev(E, seed=9, scale=0.1)
+    M0, bm0 = dev(hid, E, seed=10, scale=E ** -0.5), dev(hid, seed=11, scale=0.1)
+    M3, bm3 = dev(E, hid, seed=12, scale=hid ** -0.5), dev(E, seed=13, scale=0.1)
+    O16, Wo16, W116, W216, M016, M316 = (to_f16(z) for z in (O, Wo, W1, W2, M0, M3))
+    r16 = lambda z: z.float().half().double()
+    t1 = T.double() + O16.double() @ Wo16.double().t()
+    h = r16(F.layer_norm(t1, (E,), g.double(), b.double(), 1e-5))
+    t2 = t1 + b2.double() + r16(torch.relu(h @ W116.double().t() + b1.double())) @ W216.double().t()
+    ref = t2 + bm3.double() + r16(torch.relu(r16(t2) @ M016.double().t() + bm0.double())) @ M316.double().t()
+    Y = T.clone() if inplace else torch.full((M, E), float("nan"), device="cuda")
+    G.check(L.cfen_vit_tail_f16(G.ptr(O16), G.ptr(Y if inplace else T), G.ptr(Wo16), G.ptr(g), G.ptr(b), G.ptr(W116),
+                                G.ptr(b1), G.ptr(W216), G.ptr(b2), G.ptr(M016), G.ptr(bm0), G.ptr(M316), G.ptr(bm3),
+                                G.ptr(Y), M, E, hid, G.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(Y, ref) <= 5e-4             # three fp16 roundings of on-chip operands (ties may flip)
+
+
+@pytest.mark.parametrize("rows,E", [(1001, 96), (257, 192), (64, 384), (33, 768), (16, 1536)])
+def test_layernorm_f16(rows, E):
+    L = _native.lib()
+    x, gm, bt = dev(rows, E, seed=1, scale=3.0) + 0.7, dev(E, seed=2), dev(E, seed=3)
+    y = torch.empty(rows, E, device="cuda", dtype=torch.float16)
+    G.check(L.cfen_layernorm_f16(G.ptr(x), G.ptr(y), G.ptr(gm), G.ptr(bt), rows, E, 1e-5, G.stream()))
+    ref = F.layer_norm(x.double(), (E,), gm.double(), bt.double(), 1e-5)
+    assert U.rel_err(y, ref) <= F16OUT_TOL
+
+
+@pytest.mark.parametrize("nseq,Lq,E,heads", [(3, 256, 96, 4), (2, 256, 384, 16), (2, 256, 384, 4), (2, 64, 768, 8),
+                                             (5, 16, 1536, 16), (1, 1024, 96, 4), (2, 80, 192, 8), (1, 1024, 384, 4)])
+def test_attention_f16(nseq, Lq, E, heads):
+    L = _native.lib()
+    hd = E // heads
+    qkv16 = to_f16(dev(nseq * Lq, 3 * E, seed=1))
+    out = torch.full((nseq * Lq, E), float("nan"), device="cuda", dtype=torch.float16)
+    G.check(L.cfen_attention_f16(G.ptr(qkv16), G.ptr(out), nseq, Lq, E, heads, G.stream()))
+    q, k, v = (z.view(nseq, Lq, heads, hd).transpose(1, 2).double() for z in qkv16.split(E, dim=-1))
+    att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(nseq * Lq, E)
+    assert U.rel_err(out, ref) <= 2e-3           # P and the output are rounded to fp16
+
+
 @pytest.mark.parametrize("rows,E", [(1001, 96), (257, 192), (64, 384), (33, 768), (16, 1536)])
 def test_layernorm(rows, E):
     L = _native.lib()
@@ -109,9 +242,11 @@ def test_tokenize_local(B, H, C, win):
     x = dev(B, C, H, H, seed=1)
     tok = torch.empty(B * (H // 2) ** 2, 4 * C, device="cuda")
     xn = U.to_nhwc(x)
-    G.check(L.cfen_tokenize_local(G.ptr(xn), G.ptr(tok), B, H, H, C, win, G.stream()))
+    tok16 = torch.empty(tok.shape, device="cuda", dtype=torch.float16)
+    G.check(L.cfen_tokenize_local(G.ptr(xn), G.ptr(tok), G.ptr(tok16), B, H, H, C, win, G.stream()))
     torch.cuda.synchronize()
     assert torch.equal(tok, G.local_tokens_ref(x, win))
+    assert torch.equal(tok16, tok.half())
     # and the layout is a feature permutation of the reference's unfold tokens (v3.py:1140)
     ny = H // win
     tiles = x.view(B, C, ny, win, ny, win).permute(0, 2, 4, 1, 3, 5).reshape(-1, C, win, win)
@@ -126,8 +261,10 @@ def test_tokenize_global(B, H, C):
     x = dev(B, C, H, H, seed=1)
     tok = torch.empty(B * (H // 16) ** 2, 16 * C, device="cuda")
     xn = U.to_nhwc(x)
-    G.check(L.cfen_tokenize_global(G.ptr(xn), G.ptr(tok), B, H, H, C, G.stream()))
+    tok16 = torch.empty(tok.shape, device="cuda", dtype=torch.float16)
+    G.check(L.cfen_tokenize_global(G.ptr(xn), G.ptr(tok), G.ptr(tok16), B, H, H, C, G.stream()))
     torch.cuda.synchronize()
+    assert torch.equal(tok16, tok.half())
     q = F.avg_pool2d(F.avg_pool2d(x, 2, 2), 2, 2)
     assert U.rel_err(tok, G.global_tokens_ref(q)) <= FP32_TOL
 

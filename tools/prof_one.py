@@ -1,0 +1,40 @@
+"""Single launches of the fused token kernels for ncu (--set full --import-source on).
+
+    ncu ... python tools/prof_one.py mlp16|tail16 [E] [hid] [M]
+"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cfen_vit_dehazing_b200 import _native  # noqa: E402
+
+L = _native.lib()
+P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+ST = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def h16(x):
+    y = torch.empty(x.shape, device="cuda", dtype=torch.float16)
+    _native.check(L.cfen_f32_to_f16(P(x), P(y), x.numel(), ST()))
+    return y
+
+
+which = sys.argv[1]
+E = int(sys.argv[2]) if len(sys.argv) > 2 else 96
+hid = int(sys.argv[3]) if len(sys.argv) > 3 else 4 * E
+M = int(sys.argv[4]) if len(sys.argv) > 4 else 148 * 256
+r = lambda *s: torch.randn(*s, device="cuda")
+X, R = h16(r(M, E)), r(M, E)
+W1, W2, M0, M3, Wo = h16(r(hid, E) * 0.1), h16(r(E, hid) * 0.1), h16(r(hid, E) * 0.1), h16(r(E, hid) * 0.1), h16(r(E, E) * 0.1)
+b1, b2, g, b = torch.zeros(hid, device="cuda"), torch.zeros(E, device="cuda"), torch.ones(E, device="cuda"), torch.zeros(E, device="cuda")
+Y, Y16 = torch.empty_like(R), torch.empty(M, E, device="cuda", dtype=torch.float16)
+for _ in range(3):
+    if which == "mlp16":
+        _native.check(L.cfen_mlp_f16(P(X), P(R), P(W1), P(b1), P(W2), P(b2), P(Y), P(Y16), M, E, hid, ST()))
+    else:
+        _native.check(L.cfen_vit_tail_f16(P(X), P(R), P(Wo), P(g), P(b), P(W1), P(b1), P(W2), P(b2), P(M0), P(b1), P(M3), P(b2),
+                                          P(Y), M, E, hid, ST()))
+torch.cuda.synchronize()
