@@ -21,6 +21,7 @@
 
 #include "../../include/cfen_b200.h"
 #include "common.cuh"
+#include "conv16.cuh"
 #include "conv_igemm.cuh"
 #include "dcn.cuh"
 #include "attn16.cuh"
@@ -79,6 +80,11 @@ static cudaError_t set_kernel_attributes() {
   SETC(ConvUp96_48) SETC(ConvUp48_24) SETC(ConvUp24_12) SETC(ConvLg1) SETC(ConvLg2) SETC(ConvLg3)
   SETC(ConvSk96_48) SETC(ConvSk48_24) SETC(ConvTail7_3) SETC(ConvTail7_1)
 #undef SETC
+#define SETC(S) if ((e = conv16_set_attr<S>()) != cudaSuccess) return e;
+  SETC(ConvHead5x5) SETC(Conv3x3_12) SETC(ConvDs12_24) SETC(ConvDs24_48) SETC(ConvDs48_96)
+  SETC(ConvUp96_48) SETC(ConvUp48_24) SETC(ConvUp24_12) SETC(ConvLg1) SETC(ConvLg2) SETC(ConvLg3)
+  SETC(ConvSk96_48) SETC(ConvSk48_24) SETC(ConvTail7_3) SETC(ConvTail7_1)
+#undef SETC
   if ((e = gemm_tc_set_attr()) != cudaSuccess) return e;
   if ((e = mlp_tc_set_attr()) != cudaSuccess) return e;
   if ((e = gemm16_set_attr()) != cudaSuccess) return e;
@@ -116,6 +122,47 @@ static int conv_cout(int kind) {
     case K_T3: return 3; case K_T1: return 1;
   }
   return 0;
+}
+
+// second generation (conv16.cuh): fp16 packed weights, ldmatrix-fed mma.sync m16n8k16
+static int conv16_wpack_halves(int kind) {
+  switch (kind) {
+    case K_HEAD5: return Conv16<ConvHead5x5>::WPACK_HALVES; case K_C3: return Conv16<Conv3x3_12>::WPACK_HALVES;
+    case K_DS1: return Conv16<ConvDs12_24>::WPACK_HALVES;   case K_DS2: return Conv16<ConvDs24_48>::WPACK_HALVES;
+    case K_DS3: return Conv16<ConvDs48_96>::WPACK_HALVES;   case K_UP3: return Conv16<ConvUp96_48>::WPACK_HALVES;
+    case K_UP2: return Conv16<ConvUp48_24>::WPACK_HALVES;   case K_UP1: return Conv16<ConvUp24_12>::WPACK_HALVES;
+    case K_LG1: return Conv16<ConvLg1>::WPACK_HALVES;       case K_LG2: return Conv16<ConvLg2>::WPACK_HALVES;
+    case K_LG3: return Conv16<ConvLg3>::WPACK_HALVES;       case K_SK3: return Conv16<ConvSk96_48>::WPACK_HALVES;
+    case K_SK2: return Conv16<ConvSk48_24>::WPACK_HALVES;   case K_T3: return Conv16<ConvTail7_3>::WPACK_HALVES;
+    case K_T1: return Conv16<ConvTail7_1>::WPACK_HALVES;
+  }
+  return 0;
+}
+static cudaError_t conv16_pack_dispatch(int kind, const float* src, __half* dst, cudaStream_t st) {
+#define PK(S, CS) conv16_pack_kernel<S><<<ew_blocks(Conv16<S>::WPACK_HALVES), 256, 0, st>>>(src, dst, CS); break;
+  switch (kind) {
+    case K_HEAD5: PK(ConvHead5x5, 3) case K_C3: PK(Conv3x3_12, 12) case K_DS1: PK(ConvDs12_24, 12)
+    case K_DS2: PK(ConvDs24_48, 24) case K_DS3: PK(ConvDs48_96, 48) case K_UP3: PK(ConvUp96_48, 96)
+    case K_UP2: PK(ConvUp48_24, 48) case K_UP1: PK(ConvUp24_12, 24) case K_LG1: PK(ConvLg1, 48)
+    case K_LG2: PK(ConvLg2, 96) case K_LG3: PK(ConvLg3, 192) case K_SK3: PK(ConvSk96_48, 96)
+    case K_SK2: PK(ConvSk48_24, 48) case K_T3: PK(ConvTail7_3, 12) case K_T1: PK(ConvTail7_1, 12)
+    default: return cudaErrorInvalidValue;
+  }
+#undef PK
+  return cudaGetLastError();
+}
+static cudaError_t conv16_launch_dispatch(int kind, const ConvArgs& a, const __half* w, cudaStream_t st) {
+  switch (kind) {
+    case K_HEAD5: return launch_conv16<ConvHead5x5>(a, w, st); case K_C3: return launch_conv16<Conv3x3_12>(a, w, st);
+    case K_DS1: return launch_conv16<ConvDs12_24>(a, w, st);   case K_DS2: return launch_conv16<ConvDs24_48>(a, w, st);
+    case K_DS3: return launch_conv16<ConvDs48_96>(a, w, st);   case K_UP3: return launch_conv16<ConvUp96_48>(a, w, st);
+    case K_UP2: return launch_conv16<ConvUp48_24>(a, w, st);   case K_UP1: return launch_conv16<ConvUp24_12>(a, w, st);
+    case K_LG1: return launch_conv16<ConvLg1>(a, w, st);       case K_LG2: return launch_conv16<ConvLg2>(a, w, st);
+    case K_LG3: return launch_conv16<ConvLg3>(a, w, st);       case K_SK3: return launch_conv16<ConvSk96_48>(a, w, st);
+    case K_SK2: return launch_conv16<ConvSk48_24>(a, w, st);   case K_T3: return launch_conv16<ConvTail7_3>(a, w, st);
+    case K_T1: return launch_conv16<ConvTail7_1>(a, w, st);
+  }
+  return cudaErrorInvalidValue;
 }
 
 static cudaError_t conv_pack_dispatch(int kind, const float* src, float* dst, cudaStream_t st) {
@@ -163,9 +210,22 @@ static double conv_cin_bytes(int kind) {  // input floats read per tile-domain p
   }
   return 0;
 }
-static int conv_parts(int kind, int H, int W) {  // H, W = tile domain
+static int conv_parts(int kind, int H, int W) {  // H, W = tile domain (first generation: 8 x 16 tiles)
   const int tiles = (H / 8) * (W / 16);
   return (kind == K_UP3 || kind == K_UP2 || kind == K_UP1) ? tiles * 4 : tiles;
+}
+static int conv16_parts(int kind, int H, int W) {
+  switch (kind) {
+    case K_HEAD5: return conv16_stat_parts<ConvHead5x5>(H, W); case K_C3: return conv16_stat_parts<Conv3x3_12>(H, W);
+    case K_DS1: return conv16_stat_parts<ConvDs12_24>(H, W);   case K_DS2: return conv16_stat_parts<ConvDs24_48>(H, W);
+    case K_DS3: return conv16_stat_parts<ConvDs48_96>(H, W);   case K_UP3: return conv16_stat_parts<ConvUp96_48>(H, W);
+    case K_UP2: return conv16_stat_parts<ConvUp48_24>(H, W);   case K_UP1: return conv16_stat_parts<ConvUp24_12>(H, W);
+    case K_LG1: return conv16_stat_parts<ConvLg1>(H, W);       case K_LG2: return conv16_stat_parts<ConvLg2>(H, W);
+    case K_LG3: return conv16_stat_parts<ConvLg3>(H, W);       case K_SK3: return conv16_stat_parts<ConvSk96_48>(H, W);
+    case K_SK2: return conv16_stat_parts<ConvSk48_24>(H, W);   case K_T3: return conv16_stat_parts<ConvTail7_3>(H, W);
+    case K_T1: return conv16_stat_parts<ConvTail7_1>(H, W);
+  }
+  return 0;
 }
 
 enum ProfClass { PC_GEMM, PC_MLP, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
@@ -177,6 +237,7 @@ struct ConvLayer {
   int kind = 0;
   std::string wkey, bkey, ankey;  // ankey: ActNorm module prefix ("" = none)
   float *wpack = nullptr, *scale = nullptr, *shift = nullptr;
+  __half* wpack16 = nullptr;        // second-generation packing (conv16.cuh)
   const float* bias_src = nullptr;  // registered tensors (reference layout)
   float *an_w = nullptr, *an_b = nullptr;
 };
@@ -225,6 +286,7 @@ struct cfen_plan {
   // 0: TF32 mma.sync (gemm_tf32).  1 and 0 are kept for A/B runs.
   int gemm_path = 2;
   int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
+  int conv_path = 1;  // 1: fp16 ldmatrix / m16n8k16 convolutions (conv16.cuh, default); 0: TF32 first generation
   int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
   std::map<std::tuple<const void*, int, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> tmaps2;
@@ -279,6 +341,7 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
     for (auto& kv : p->conv) {
       ConvLayer& c = kv.second;
       c.wpack = a.take(conv_wpack_floats(c.kind));
+      c.wpack16 = a.take16(conv16_wpack_halves(c.kind));
       c.scale = a.take(96);
       c.shift = a.take(96);
     }
@@ -395,6 +458,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   }
   if (const char* fm = getenv("CFEN_FUSE_MLP")) p->fuse_mlp = atoi(fm) != 0;
   if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
+  if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
   plan_layout(p, true, true);  // dry run: sizes
@@ -447,6 +511,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   }
   if (strcmp(name, "fuse_mlp") == 0) { p->fuse_mlp = value != 0; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
+  if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
     CU(cudaSetDevice(p->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -553,6 +618,7 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
     auto it = p->reg.find(c.wkey);
     if (it == p->reg.end()) return fail(6, "weight '%s' was not registered", c.wkey.c_str());
     CU(conv_pack_dispatch(c.kind, it->second.first, c.wpack, st));
+    CU(conv16_pack_dispatch(c.kind, it->second.first, c.wpack16, st));
     c.bias_src = nullptr; c.an_w = nullptr; c.an_b = nullptr;
     if (!c.bkey.empty()) RET(lookup(p, c.bkey, cout, &c.bias_src));
     if (!c.ankey.empty()) {
@@ -816,9 +882,12 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   if (p->calibrating && !c.ankey.empty()) {
     // pass 1: conv + bias only, per-CTA statistics (models/actnorm.py:25-37)
     const int cout = conv_cout(c.kind);
-    const int parts = conv_parts(c.kind, H, W);
+    const int parts = p->conv_path ? conv16_parts(c.kind, H, W) : conv_parts(c.kind, H, W);
     a.scale = p->ones; a.shift = c.bias_src; a.flags = 0; a.stats = p->partials;
-    { Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str()); CU(conv_launch_dispatch(c.kind, a, r.st)); }
+    {
+      Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str());
+      CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
+    }
     const long long count = (long long)r.nb * H * W * (is_up ? 4 : 1);
     Launch l(r, PC_NORM, 0.0, 0.0);
     actnorm_calibrate_kernel<<<1, 128, 0, r.st>>>(p->partials, r.nb * parts, cout, count, c.bias_src, c.an_w,
@@ -827,7 +896,7 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   }
   a.scale = c.scale; a.shift = c.shift; a.flags = flags; a.stats = stats;
   Launch l(r, pcls, cflops, cbytes, "%s %dx%d", name.c_str(), H, W);
-  CU(conv_launch_dispatch(c.kind, a, r.st));
+  CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
   return 0;
 }
 
@@ -836,7 +905,7 @@ static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, f
                             int Hout, int Wout, int C) {
   cfen_plan* p = r.p;
   RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, 0, p->partials));
-  const int parts = conv_parts(p->conv[name].kind, H, W);
+  const int parts = p->conv_path ? conv16_parts(p->conv[name].kind, H, W) : conv_parts(p->conv[name].kind, H, W);
   {
     Launch l(r, PC_NORM, 0.0, 8.0 * r.nb * parts * C);
     instnorm_finalize_kernel<<<r.nb, 128, 0, r.st>>>(p->partials, p->mean_rstd, parts, C, Hout * Wout, 1e-5f);
@@ -1199,11 +1268,14 @@ static int conv_oneoff(int kind, const float* in0, const float* in1, const float
                        const float* bias, const float* an_w, const float* an_b, float* out, int B, int H, int W,
                        int flags, int win, cudaStream_t st) {
   CU(set_kernel_attributes());
+  const char* cpe = getenv("CFEN_CONV_PATH");
+  const bool gen2 = !cpe || atoi(cpe) != 0;
   float* tmp = nullptr;
-  const size_t wf = conv_wpack_floats(kind);
+  const size_t wf = gen2 ? (size_t)(conv16_wpack_halves(kind) + 1) / 2 + 64 : (size_t)conv_wpack_floats(kind);
   CU(cudaMalloc(&tmp, (wf + 256) * sizeof(float)));
   float *scale = tmp + wf, *shift = tmp + wf + 128;
-  cudaError_t e = conv_pack_dispatch(kind, weight, tmp, st);
+  cudaError_t e = gen2 ? conv16_pack_dispatch(kind, weight, reinterpret_cast<__half*>(tmp), st)
+                       : conv_pack_dispatch(kind, weight, tmp, st);
   if (e == cudaSuccess) {
     conv_affine_kernel<<<1, 128, 0, st>>>(bias, an_w, an_b, scale, shift, conv_cout(kind));
     e = cudaGetLastError();
@@ -1212,7 +1284,7 @@ static int conv_oneoff(int kind, const float* in0, const float* in1, const float
     ConvArgs a;
     a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = tmp; a.scale = scale; a.shift = shift; a.out = out;
     a.stats = nullptr; a.B = B; a.H = H; a.W = W; a.flags = flags; a.win = win;
-    e = conv_launch_dispatch(kind, a, st);
+    e = gen2 ? conv16_launch_dispatch(kind, a, reinterpret_cast<const __half*>(tmp), st) : conv_launch_dispatch(kind, a, st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(tmp);

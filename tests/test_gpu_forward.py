@@ -99,7 +99,7 @@ def test_batch_chunking_and_batch_invariance():
         for i in (0, 7, 18):
             one = gnet(x[i:i + 1].contiguous())
             for a, b in zip(full, one):
-                assert (a[i:i + 1] - b).abs().max().item() <= 4e-3     # raw [-1,1] scale; gate is 2e-2
+                assert (a[i:i + 1] - b).abs().max().item() <= 1e-2     # raw [-1,1] scale (two fp16-operand paths, each ~3e-3 from fp32); gate is 2e-2
 
 
 def test_actnorm_first_forward_calibration():
