@@ -229,7 +229,7 @@ static int conv16_parts(int kind, int H, int W) {
 }
 
 enum ProfClass { PC_GEMM, PC_MLP, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
-static const char* kProfNames[PC_COUNT] = {"gemm_tf32", "mlp_tc", "attention", "layernorm", "tokenize", "conv_igemm",
+static const char* kProfNames[PC_COUNT] = {"linear_gemm", "fused_mlp", "attention", "layernorm", "tokenize", "conv",
                                            "merge_lg", "instnorm", "cfsm", "misc"};
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; char tag[56]; };
 

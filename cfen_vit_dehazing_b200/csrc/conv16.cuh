@@ -50,7 +50,10 @@ struct Conv16 {
   static constexpr int WBUF_HALVES = NPAD * WPITCH;
   static constexpr int TILE_HALVES = IN_H * IN_W * CPITCH + 8;
   static constexpr int STAT_FLOATS = S::NWARPS * NPAD * 2;
-  static constexpr int SMEM_BYTES = (TILE_HALVES + 2 * WBUF_HALVES) * 2 + STAT_FLOATS * 4 + 64;
+  // LD_LG: quarter-resolution patch of the global branch (edge-clamped, fp32) staged before the bilinear x4
+  static constexpr int QH = TH / 4 + 2, QW = TW / 4 + 2;
+  static constexpr int QPATCH_FLOATS = S::LOADER == LD_LG ? QH * QW * (S::CIN / 2) : 0;
+  static constexpr int SMEM_BYTES = (TILE_HALVES + 2 * WBUF_HALVES) * 2 + (STAT_FLOATS + QPATCH_FLOATS) * 4 + 64;
   static constexpr int WPACK_HALVES = NPHASE * NPAD * K_FULL;   // global packed weights [phase][n][K_FULL]
   static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
 };
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
   __half* tile = reinterpret_cast<__half*>(conv16_smem);
   __half* wbuf = tile + ((C::TILE_HALVES + 7) / 8) * 8;
   float* wstat = reinterpret_cast<float*>(wbuf + 2 * C::WBUF_HALVES);
+  float* qpatch = wstat + C::STAT_FLOATS;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -86,6 +90,24 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
   };
   load_w(0, 0, 0);
   cp_async_commit();
+
+  // ---- LD_LG: stage the quarter-resolution patch of the global ViT output this tile interpolates from
+  // (rows / columns clamped to the map like the two align_corners=False x2 passes do)
+  if (S::LOADER == LD_LG) {
+    constexpr int CC = S::CIN / 2, CC4 = CC / 4;
+    const int qh = Hin >> 2, qw = Win >> 2, gwid = qw >> 2;
+    const size_t lg = (size_t)(qh >> 2) * gwid;
+    const int qy0 = (ty0 >> 2) - 1, qx0 = (tx0 >> 2) - 1;
+    for (int i = tid; i < C::QH * C::QW * CC4; i += S::THREADS) {
+      const int c4 = i % CC4, q = i / CC4;
+      const int iy = q / C::QW, ix = q - iy * C::QW;
+      const int qy = min(max(qy0 + iy, 0), qh - 1), qx = min(max(qx0 + ix, 0), qw - 1);
+      const float4 v = *reinterpret_cast<const float4*>(
+          a.in1 + ((size_t)b * lg + (size_t)(qy >> 2) * gwid + (qx >> 2)) * (16 * CC) + ((qy & 3) * 4 + (qx & 3)) * CC + c4 * 4);
+      *reinterpret_cast<float4*>(qpatch + (size_t)q * CC + c4 * 4) = v;
+    }
+    __syncthreads();
+  }
 
   // ---- stage the input halo tile as fp16 [pixel][CPITCH]; channels [CIN, CIN_P) are zero
   {
@@ -132,24 +154,18 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
             v = *reinterpret_cast<const float4*>(a.in0 + m * (4 * CC) + ((ly & 1) * 2 + (lx & 1)) * CC + c);
           } else {
             const int cc = c - CC;
-            const int qh = Hin >> 2, qw = Win >> 2, gwid = qw >> 2;
-            const size_t lg = (size_t)(qh >> 2) * gwid;
             float wy[3], wx[3];
             up4_taps(gy & 3, wy);
             up4_taps(gx & 3, wx);
-            const int ky = gy >> 2, kx = gx >> 2;
+            const int py0 = (gy >> 2) - (ty0 >> 2), px0 = (gx >> 2) - (tx0 >> 2);   // patch row / column of tap 0
 #pragma unroll
             for (int ia = 0; ia < 3; ++ia) {
               if (wy[ia] == 0.f) continue;
-              const int qy = min(max(ky - 1 + ia, 0), qh - 1);
 #pragma unroll
               for (int ib = 0; ib < 3; ++ib) {
                 if (wx[ib] == 0.f) continue;
-                const int qx = min(max(kx - 1 + ib, 0), qw - 1);
                 const float wgt = wy[ia] * wx[ib];
-                const float4 s = *reinterpret_cast<const float4*>(
-                    a.in1 + ((size_t)b * lg + (size_t)(qy >> 2) * gwid + (qx >> 2)) * (16 * CC) +
-                    ((qy & 3) * 4 + (qx & 3)) * CC + cc);
+                const float4 s = *reinterpret_cast<const float4*>(qpatch + ((py0 + ia) * C::QW + (px0 + ib)) * CC + cc);
                 v.x += wgt * s.x; v.y += wgt * s.y; v.z += wgt * s.z; v.w += wgt * s.w;
               }
             }

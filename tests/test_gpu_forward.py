@@ -85,10 +85,11 @@ def test_forward_parity_1024():
     _run_and_check("v3_hr4_1024_b1", 4, 1024, 1)
 
 
-def test_batch_chunking_and_batch_invariance():
-    """A batch larger than the plan's internal chunk (16 images at <= 512x512) equals the same chunks run as
+def test_batch_chunking_and_batch_invariance(monkeypatch):
+    """A batch larger than the plan's internal chunk (set to 16 images here) equals the same chunks run as
     separate calls bit for bit; a single image differs from its in-batch result only by kernel selection
     (fused / unfused token kernels are picked by tile count), far inside the parity gate."""
+    monkeypatch.setenv("CFEN_CHUNK_IMAGES", "16")
     gnet, sd0, sd1, x0 = _gpu_net(2, 128)
     x = orc.make_inputs(128, [1, 19])[1].cuda()
     with torch.no_grad():
