@@ -423,6 +423,71 @@ class dec_ipt(nn.Module):
                 plan.forward(b, x.data_ptr(), xr.data_ptr(), xs.data_ptr(), xd.data_ptr(), stream)
         return [xr, xs, xd]
 
+    def forward_host(self, input, out=None, device=None):
+        """Host-to-host forward for batches that start and end in (pinned) host memory - what
+        DECHLGVIT.set_input (.to(device), model_iid_dehazing.py:126-136) + forward + tensor2im's .cpu()
+        (util/util.py:12-24) do around the generator, restated as a three-stream pipeline: the H2D copy
+        of pass i+1 and the D2H copy of pass i-1 overlap the kernels of pass i (one pass = the plan's
+        images-per-pass chunk).  Returns [xr, xs, xd] as host tensors (`out` if given); they are
+        complete when the current stream of `device` has been synchronised.  No CPU compute path."""
+        if not isinstance(input, torch.Tensor) or input.dim() != 4 or input.size(1) != 3:
+            raise RuntimeError("dec_ipt.forward_host expects a [B, 3, H, W] tensor")
+        if input.is_cuda:
+            raise RuntimeError("forward_host takes a host tensor; use forward() for device tensors")
+        if input.dtype != torch.float32 or not input.is_contiguous():
+            input = input.float().contiguous()
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("cfen_vit_dehazing_b200 runs on sm_100a GPUs only: the module lives on %s "
+                               "and there is no CPU fallback" % dev)
+        b, _, h, w = input.shape
+        if out is None:
+            out = [torch.empty((b, c, h, w), dtype=torch.float32).pin_memory() for c in (3, 1, 3)]
+        with torch.cuda.device(dev):
+            plan = self._plan_for(dev, h, w, b)
+            if plan.needs_calibration:
+                raise RuntimeError("forward_host needs initialised ActNorm layers: run one forward() first "
+                                   "(models/actnorm.py:25-37 initialises from that batch) or load a checkpoint")
+            nb = plan.max_batch
+            key = (dev.index, h, w, nb)
+            st = getattr(self, "_host_pipe", {}).get(key)
+            if st is None:
+                st = {"in": [torch.empty((nb, 3, h, w), device=dev) for _ in range(2)],
+                      "out": [[torch.empty((nb, c, h, w), device=dev) for c in (3, 1, 3)] for _ in range(2)],
+                      "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev)}
+                self._host_pipe = {key: st}
+            cur = torch.cuda.current_stream(dev)
+            s_in, s_out = st["s_in"], st["s_out"]
+            s_in.wait_stream(cur)
+            s_out.wait_stream(cur)
+            ev_comp, ev_out = {}, {}
+            n_pass = (b + nb - 1) // nb
+            for i in range(n_pass):
+                slot, lo = i & 1, i * nb
+                n = min(nb, b - lo)
+                with torch.cuda.stream(s_in):
+                    if i >= 2:
+                        s_in.wait_event(ev_comp[i - 2])          # the kernels of pass i-2 have consumed this slot
+                    st["in"][slot][:n].copy_(input[lo:lo + n], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(s_in)
+                cur.wait_event(ev_in)
+                if i >= 2:
+                    cur.wait_event(ev_out[i - 2])                # the D2H of pass i-2 has drained this slot
+                o = st["out"][slot]
+                plan.forward(n, st["in"][slot].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                             cur.cuda_stream)
+                ev_comp[i] = torch.cuda.Event()
+                ev_comp[i].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_comp[i])
+                    for dst, src in zip(out, o):
+                        dst[lo:lo + n].copy_(src[:n], non_blocking=True)
+                    ev_out[i] = torch.cuda.Event()
+                    ev_out[i].record(s_out)
+            cur.wait_stream(s_out)
+        return out
+
 
 def _mark_dirty(module, _incompatible):
     module._weights_version = getattr(module, "_weights_version", 0) + 1

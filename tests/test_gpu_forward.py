@@ -156,3 +156,22 @@ def test_uint8_boundary_matches_float_path():
         f3 = f.expand(-1, 3, -1, -1) if f.shape[1] == 1 else f
         ref = ((f3.permute(0, 2, 3, 1) + 1) / 2.0 * 255.0).to(torch.uint8)
         assert (o.int() - ref.int()).abs().max().item() <= 1
+
+
+def test_forward_host_pipeline_matches_forward(monkeypatch):
+    """forward_host (pinned host in / out, H2D - kernels - D2H overlapped over 3 passes of 4 images, the
+    last one ragged) returns bit for bit what forward() returns for the same images."""
+    monkeypatch.setenv("CFEN_CHUNK_IMAGES", "4")
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    x = orc.make_inputs(128, [1, 10])[1]
+    with torch.no_grad():
+        ref = [o.cpu() for o in gnet(x.cuda())]
+        out = gnet.forward_host(x.pin_memory())
+        torch.cuda.synchronize()
+        again = gnet.forward_host(x.pin_memory(), out=out)       # re-uses the staging buffers
+        torch.cuda.synchronize()
+    assert again is out
+    for a, b in zip(out, ref):
+        assert a.device.type == "cpu" and torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        gnet.forward_host(x.cuda())

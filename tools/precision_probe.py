@@ -83,8 +83,38 @@ def patched(lin_a, lin_w, conv, attn):
         orc.vit_block = vb0
 
 
+@contextlib.contextmanager
+def maps16(on, tokens16=False):
+    """Additionally store every stage-boundary map (and optionally the ViT residual stream between the fused
+    token kernels) with a 10-bit mantissa: emulates fp16 activation storage in HBM."""
+    if not on:
+        yield
+        return
+    names = ["_down", "_up", "_skip", "_block", "cfsm", "local_vit", "global_vit"]
+    saved = {n: getattr(orc, n) for n in names}
+    conv0 = orc._conv
+
+    def wrap(f):
+        return lambda *a, **k: r_f16(f(*a, **k))
+
+    def conv(sd, prefix, x, stride=1, padding=0):
+        y = conv0(sd, prefix, x, stride=stride, padding=padding)
+        return r_f16(y) if (prefix.startswith("head") or prefix.endswith(".0.1")) else y
+
+    for n in names:
+        setattr(orc, n, wrap(saved[n]))
+    orc._conv = conv
+    try:
+        yield
+    finally:
+        for n in names:
+            setattr(orc, n, saved[n])
+        orc._conv = conv0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--maps16", action="store_true", help="also run 'f16 everywhere' with fp16 map storage")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--hr", type=int, default=4)
     ap.add_argument("--seeds", type=int, nargs="+", default=[1, 2])
@@ -108,6 +138,12 @@ def main():
             worst = max((o - r).abs().max().item() / 2 for o, r in zip(out, ref))
             ps = min(orc.psnr01(o, r) for o, r in zip(out, ref))
             print("seed %d  %-38s max|d| on [0,1] = %.5f   min PSNR = %.1f dB" % (seed, name, worst, ps), flush=True)
+        if a.maps16:
+            with patched("f16", "f16", "f16", "f16"), maps16(True):
+                out = orc.forward(sd, x1)
+            worst = max((o - r).abs().max().item() / 2 for o, r in zip(out, ref))
+            ps = min(orc.psnr01(o, r) for o, r in zip(out, ref))
+            print("seed %d  %-38s max|d| on [0,1] = %.5f   min PSNR = %.1f dB" % (seed, "f16 everywhere + fp16 maps", worst, ps), flush=True)
 
 
 if __name__ == "__main__":

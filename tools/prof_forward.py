@@ -29,7 +29,11 @@ x0 = (2 * torch.rand(1, 3, a.size, a.size, generator=g) - 1).to(dev)
 x = (2 * torch.rand(a.batch, 3, a.size, a.size, generator=g) - 1).to(dev)
 with torch.no_grad():
     net(x0)
+    out = net(x)                      # warm: tensor maps, L2, clocks
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()       # ncu --profile-from-start off sees only the steady-state passes
     for _ in range(a.iters):
         out = net(x)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 print("launches per forward:", net._plan_for(dev, a.size, a.size, a.batch).launches_per_forward)
