@@ -264,6 +264,17 @@ struct Arena {
   __half* take16(size_t halves) { return reinterpret_cast<__half*>(take((halves + 1) / 2)); }
 };
 
+// One lane = one independent chain of the forward graph with its own streams and scratch: lane 0 runs the
+// shared encoder and then the R decoder, lane 1 the S decoder, lane 2 the D decoder (v3.py:549-1009 are
+// independent given the encoder maps, except D's two CFSM fusion points).  Inside every block the global
+// ViT branch runs on the lane's second stream next to the local branch.
+struct Lane {
+  cudaStream_t st = nullptr, gst = nullptr;   // local / conv chain, global-ViT chain
+  TokWs lws, gws;
+  float *partials = nullptr, *mean_rstd = nullptr, *gates = nullptr, *cfsm_part = nullptr;
+  float *f0 = nullptr, *f1 = nullptr;         // full-resolution 12-channel scratch maps (head / tail)
+};
+
 struct cfen_plan {
   cfen_config cfg;
   int H, W, nbmax, hr, win;
@@ -276,9 +287,12 @@ struct cfen_plan {
   float* cfsm_w[2] = {nullptr, nullptr};  // d03d (C=48), d02d (C=24): 8 weights concatenated
   float* ones = nullptr;
   // workspace
-  TokWs lws, gws;
+  Lane lane[3];
+  cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // lane0.gst, lane1.st/gst, lane2.st/gst
+  std::vector<cudaEvent_t> sync_ev;  // fork / join events (no timing), recycled every pass
+  size_t sync_used = 0;
+  int streams = 1;                   // 1: lanes run concurrently (default); 0: everything on the caller's stream
   std::map<std::string, std::pair<float*, int64_t>> stage;  // named maps (per-image floats)
-  float *partials = nullptr, *mean_rstd = nullptr, *gates = nullptr, *cfsm_part = nullptr;
   float *u8_in = nullptr, *u8_xr = nullptr, *u8_xs = nullptr, *u8_xd = nullptr;
   long long launches = 0, launches_last = 0;
   bool calibrating = false;
@@ -353,23 +367,33 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
     Arena& a = p->ws;
     a.off = 0;
     const size_t HH = (size_t)H * H;
-    // local token workspace (M*E is largest on level 1: 6*H*H floats per image)
+    // token workspaces per lane (local: M*E is largest on level 1, 6*H*H floats per image; global: Lg*E)
     const size_t lt = 6 * HH * nb;
-    p->lws.t0 = a.take(lt); p->lws.t1 = a.take(lt); p->lws.h = a.take(lt); p->lws.o = a.take(lt);
-    p->lws.qkv = a.take(3 * lt); p->lws.f = a.take(lt * hr);
-    p->lws.x16 = a.take16(lt); p->lws.h16 = a.take16(lt); p->lws.o16 = a.take16(lt);
-    p->lws.qkv16 = a.take16(3 * lt); p->lws.f16 = a.take16(lt * hr);
-    const size_t gt = (size_t)(H / 32) * (H / 32) * 384 * nb;  // global: Lg*E largest on level 1
-    p->gws.t0 = a.take(gt); p->gws.t1 = a.take(gt); p->gws.h = a.take(gt); p->gws.o = a.take(gt);
-    p->gws.qkv = a.take(3 * gt); p->gws.f = a.take(gt * hr);
-    p->gws.x16 = a.take16(gt); p->gws.h16 = a.take16(gt); p->gws.o16 = a.take16(gt);
-    p->gws.qkv16 = a.take16(3 * gt); p->gws.f16 = a.take16(gt * hr);
+    const size_t gt = (size_t)(H / 32) * (H / 32) * 384 * nb;
+    for (int li = 0; li < 3; ++li) {
+      Lane& L = p->lane[li];
+      L.lws.t0 = a.take(lt); L.lws.t1 = a.take(lt); L.lws.h = a.take(lt); L.lws.o = a.take(lt);
+      L.lws.qkv = a.take(3 * lt); L.lws.f = a.take(lt * hr);
+      L.lws.x16 = a.take16(lt); L.lws.h16 = a.take16(lt); L.lws.o16 = a.take16(lt);
+      L.lws.qkv16 = a.take16(3 * lt); L.lws.f16 = a.take16(lt * hr);
+      L.gws.t0 = a.take(gt); L.gws.t1 = a.take(gt); L.gws.h = a.take(gt); L.gws.o = a.take(gt);
+      L.gws.qkv = a.take(3 * gt); L.gws.f = a.take(gt * hr);
+      L.gws.x16 = a.take16(gt); L.gws.h16 = a.take16(gt); L.gws.o16 = a.take16(gt);
+      L.gws.qkv16 = a.take16(3 * gt); L.gws.f16 = a.take16(gt * hr);
+      const size_t parts_max = (size_t)(H / 8) * (H / 16) * 2 * 12;  // tail conv / up_24_12 (4 phases on H/2)
+      L.partials = a.take(parts_max * nb * 2);
+      L.mean_rstd = a.take((size_t)nb * 2 * 96);
+      L.gates = a.take((size_t)nb * 2 * 48);
+      L.cfsm_part = a.take((size_t)nb * 64 * 2 * 48);
+      L.f0 = a.take(HH * 12 * nb);
+      L.f1 = a.take(HH * 12 * nb);
+    }
     auto add = [&](const char* name, size_t per_image) {
       p->stage[name] = std::make_pair(a.take(per_image * nb), (int64_t)per_image);
     };
     const size_t F = HH * 12, M1 = (size_t)p->Hl[1] * p->Hl[1] * 24, M2 = (size_t)p->Hl[2] * p->Hl[2] * 48,
                  M3 = (size_t)p->Hl[3] * p->Hl[3] * 96;
-    add("f0", F); add("f1", F); add("f2", F);
+    add("f2", F);
     add("xf", M1); add("e1", M1); add("e1d", M2); add("e2", M2); add("e2d", M3); add("e3", M3);
     for (const char* br : {"r", "s", "d"}) {
       std::string b(br);
@@ -377,11 +401,6 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
       add(("d2" + b).c_str(), M2); add(("u2" + b).c_str(), M1); add(("d1in" + b).c_str(), M1);
       add(("d1" + b).c_str(), M1);
     }
-    const size_t parts_max = (size_t)(H / 8) * (H / 16) * 2 * 12;  // tail conv / up_24_12 (4 phases on H/2)
-    p->partials = a.take(parts_max * nb * 2);
-    p->mean_rstd = a.take((size_t)nb * 2 * 96);
-    p->gates = a.take((size_t)nb * 2 * 48);
-    p->cfsm_part = a.take((size_t)nb * 64 * 2 * 48);
     p->u8_in = a.take(HH * 3 * nb); p->u8_xr = a.take(HH * 3 * nb);
     p->u8_xs = a.take(HH * nb); p->u8_xd = a.take(HH * 3 * nb);
   }
@@ -473,6 +492,13 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->wa.cap = wbytes; p->ws.cap = sbytes;
   plan_layout(p, true, true);
   p->allocated = true;
+  if (const char* sm = getenv("CFEN_STREAMS")) p->streams = atoi(sm) != 0;
+  for (int i = 0; i < 5; ++i) {
+    if (cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking) != cudaSuccess) {
+      cfen_plan_destroy(p);
+      return fail(2, "cudaStreamCreate failed");
+    }
+  }
   *out = p;
   return 0;
 }
@@ -483,6 +509,9 @@ extern "C" int32_t cfen_plan_destroy(cfen_plan* p) {
   if (p->wa.base) cudaFree(p->wa.base);
   if (p->ws.base) cudaFree(p->ws.base);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->sync_ev) cudaEventDestroy(e);
+  for (int i = 0; i < 5; ++i)
+    if (p->side[i]) cudaStreamDestroy(p->side[i]);
   delete p;
   return 0;
 }
@@ -512,6 +541,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_mlp") == 0) { p->fuse_mlp = value != 0; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
+  if (strcmp(name, "streams") == 0) { p->streams = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
     CU(cudaSetDevice(p->cfg.device));
     CU(cudaDeviceSynchronize());
@@ -631,7 +661,7 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
     conv_affine_kernel<<<1, 128, 0, st>>>(c.bias_src, c.an_w, c.an_b, c.scale, c.shift, cout);
     CU(cudaGetLastError());
   }
-  conv_affine_kernel<<<1, 128, 0, st>>>(nullptr, nullptr, nullptr, p->ones, p->mean_rstd /*scratch*/, 96);
+  conv_affine_kernel<<<1, 128, 0, st>>>(nullptr, nullptr, nullptr, p->ones, p->lane[0].mean_rstd /*scratch*/, 96);
   CU(cudaGetLastError());
   static const char* kMlp[8] = {"fc_avg_cf1.0", "fc_avg_cf1.2", "fc_avg_cf2.0", "fc_avg_cf2.2",
                                 "fc_max_cf1.0", "fc_max_cf1.2", "fc_max_cf2.0", "fc_max_cf2.2"};
@@ -654,9 +684,30 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
 // ------------------------------------------------------------------------------------------
 struct Run {
   cfen_plan* p;
-  cudaStream_t st;
+  cudaStream_t st;   // stream the next launch goes to
   int nb;
+  Lane* ln;          // scratch this chain owns
 };
+
+// Fork / join edges between the plan's streams (CUDA-graph capturable): mark everything enqueued on `from`
+// so far; later make `to` wait for that mark.
+static int stream_mark(cfen_plan* p, cudaStream_t from, cudaEvent_t* out) {
+  if (p->sync_used == p->sync_ev.size()) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->sync_ev.push_back(e);
+  }
+  *out = p->sync_ev[p->sync_used++];
+  CU(cudaEventRecord(*out, from));
+  return 0;
+}
+static int stream_edge(cfen_plan* p, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
+  cudaEvent_t e;
+  RET(stream_mark(p, from, &e));
+  CU(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
 
 // Counts the launch and, when timing is on, brackets it with CUDA events on the launching stream.
 struct Launch {
@@ -883,14 +934,14 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
     // pass 1: conv + bias only, per-CTA statistics (models/actnorm.py:25-37)
     const int cout = conv_cout(c.kind);
     const int parts = p->conv_path ? conv16_parts(c.kind, H, W) : conv_parts(c.kind, H, W);
-    a.scale = p->ones; a.shift = c.bias_src; a.flags = 0; a.stats = p->partials;
+    a.scale = p->ones; a.shift = c.bias_src; a.flags = 0; a.stats = r.ln->partials;
     {
       Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str());
       CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
     }
     const long long count = (long long)r.nb * H * W * (is_up ? 4 : 1);
     Launch l(r, PC_NORM, 0.0, 0.0);
-    actnorm_calibrate_kernel<<<1, 128, 0, r.st>>>(p->partials, r.nb * parts, cout, count, c.bias_src, c.an_w,
+    actnorm_calibrate_kernel<<<1, 128, 0, r.st>>>(r.ln->partials, r.nb * parts, cout, count, c.bias_src, c.an_w,
                                                   c.an_b, c.scale, c.shift);
     CU(cudaGetLastError());
   }
@@ -904,16 +955,16 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
 static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, float* out, int H, int W,
                             int Hout, int Wout, int C) {
   cfen_plan* p = r.p;
-  RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, 0, p->partials));
+  RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, 0, r.ln->partials));
   const int parts = p->conv_path ? conv16_parts(p->conv[name].kind, H, W) : conv_parts(p->conv[name].kind, H, W);
   {
     Launch l(r, PC_NORM, 0.0, 8.0 * r.nb * parts * C);
-    instnorm_finalize_kernel<<<r.nb, 128, 0, r.st>>>(p->partials, p->mean_rstd, parts, C, Hout * Wout, 1e-5f);
+    instnorm_finalize_kernel<<<r.nb, 128, 0, r.st>>>(r.ln->partials, r.ln->mean_rstd, parts, C, Hout * Wout, 1e-5f);
     CU(cudaGetLastError());
   }
   const long long total4 = (long long)r.nb * Hout * Wout * C / 4;
   Launch l(r, PC_NORM, 0.0, 32.0 * total4);
-  instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, p->mean_rstd, Hout * Wout, C, total4);
+  instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, r.ln->mean_rstd, Hout * Wout, C, total4);
   CU(cudaGetLastError());
   return 0;
 }
@@ -925,94 +976,133 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
   const long long total4 = (long long)r.nb * HW * C / 4;
   {
     Launch l(r, PC_CFSM, 0.0, 48.0 * total4);
-    if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, p->cfsm_part, HW);
-    else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, p->cfsm_part, HW);
+    if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW);
+    else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW);
     CU(cudaGetLastError());
   }
   {
     Launch l(r, PC_CFSM, 0.0, 0.0);
-    if (C == 48) cfsm_gate_kernel<48><<<r.nb, 128, 0, r.st>>>(p->cfsm_part, p->cfsm_w[0], p->gates, parts, HW);
-    else cfsm_gate_kernel<24><<<r.nb, 128, 0, r.st>>>(p->cfsm_part, p->cfsm_w[1], p->gates, parts, HW);
+    if (C == 48) cfsm_gate_kernel<48><<<r.nb, 128, 0, r.st>>>(r.ln->cfsm_part, p->cfsm_w[0], r.ln->gates, parts, HW);
+    else cfsm_gate_kernel<24><<<r.nb, 128, 0, r.st>>>(r.ln->cfsm_part, p->cfsm_w[1], r.ln->gates, parts, HW);
     CU(cudaGetLastError());
   }
   Launch l(r, PC_CFSM, 0.0, 64.0 * total4);
-  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, p->gates, out, HW, C, total4);
+  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, r.ln->gates, out, HW, C, total4);
   CU(cudaGetLastError());
   return 0;
 }
 
-// block(x) for stage index si (reference e.g. v3.py:403-488)
+// block(x) for stage index si (reference e.g. v3.py:403-488): the global ViT branch runs on the lane's
+// second stream while the local branch runs on the first; the merge conv joins them.
 static int run_block(Run& r, int si, const float* x, float* out) {
   cfen_plan* p = r.p;
+  Lane& L = *r.ln;
   const int lvl = stage_level(kStages[si]);
   const int Hl = p->Hl[lvl], C = p->Cl[lvl];
   const int nwin = (Hl / p->win) * (Hl / p->win);
+  const cudaStream_t main_st = r.st;
+  RET(stream_edge(p, main_st, L.gst));   // x is ready on the lane's main stream
+  {
+    r.st = L.gst;
+    const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
+    {
+      Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17, "tok_global H%d C%d", Hl, C);
+      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.gws.t0, L.gws.x16, r.nb, Hl, Hl, C);
+      CU(cudaGetLastError());
+    }
+    const int rc = run_vit(r, p->gvit[si], L.gws, r.nb);
+    r.st = main_st;
+    RET(rc);
+  }
   {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4, "tok_local H%d C%d", Hl, C);
-      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->lws.t0, p->lws.x16, r.nb, Hl, Hl, C, p->win);
+      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.lws.t0, L.lws.x16, r.nb, Hl, Hl, C, p->win);
       CU(cudaGetLastError());
     }
-    RET(run_vit(r, p->lvit[si], p->lws, r.nb * nwin));
+    RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin));
   }
-  {
-    const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
-    {
-      Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17, "tok_global H%d C%d", Hl, C);
-      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, p->gws.t0, p->gws.x16, r.nb, Hl, Hl, C);
-      CU(cudaGetLastError());
-    }
-    RET(run_vit(r, p->gvit[si], p->gws, r.nb));
-  }
+  RET(stream_edge(p, L.gst, main_st));
   const std::string name = "lgcat_conv_" + stage_tag(kStages[si]);
-  return run_conv(r, name, p->lws.t1, p->gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES);
+  return run_conv(r, name, L.lws.t1, L.gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES);
 }
 
 static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float* xs, float* xd,
                          cudaStream_t st) {
-  Run r{p, st, nb};
   const int H = p->H, H1 = p->Hl[1], H2 = p->Hl[2], H3 = p->Hl[3];
   auto S = [&](const std::string& n) { return p->stage[n].first; };
-  float *f0 = S("f0"), *f1 = S("f1"), *f2 = S("f2");
-  // head: conv5x5 + ResBlock (v3.py:395)
-  RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, 0));
-  RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H, H, CF_RELU));
-  RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, f2, H, H, CF_RES));
-  RET(run_conv_in_relu(r, "ds_conv_e01", f2, S("xf"), H1, H1, H1, H1, 24));
-  // shared encoder (v3.py:403-539)
-  RET(run_block(r, 0, S("xf"), S("e1")));
-  RET(run_conv_in_relu(r, "ds_conv_e02", S("e1"), S("e1d"), H2, H2, H2, H2, 48));
-  RET(run_block(r, 1, S("e1d"), S("e2")));
-  RET(run_conv_in_relu(r, "ds_conv_e03", S("e2"), S("e2d"), H3, H3, H3, H3, 96));
-  RET(run_block(r, 2, S("e2d"), S("e3")));
-  // decoders (v3.py:549-1009)
+  // streams: lanes run concurrently unless disabled, timing every launch (serial per-kernel numbers) or
+  // calibrating (ActNorm statistics are computed layer by layer)
+  const bool multi = p->streams && !p->timing && !p->calibrating;
+  p->lane[0].st = st;
+  p->lane[0].gst = multi ? p->side[0] : st;
+  p->lane[1].st = multi ? p->side[1] : st;
+  p->lane[1].gst = multi ? p->side[2] : st;
+  p->lane[2].st = multi ? p->side[3] : st;
+  p->lane[2].gst = multi ? p->side[4] : st;
+  p->sync_used = 0;
+  Run r0{p, st, nb, &p->lane[0]};
+  {
+    Run& r = r0;
+    float *f0 = r.ln->f0, *f1 = r.ln->f1, *f2 = S("f2");
+    // head: conv5x5 + ResBlock (v3.py:395)
+    RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, 0));
+    RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H, H, CF_RELU));
+    RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, f2, H, H, CF_RES));
+    RET(run_conv_in_relu(r, "ds_conv_e01", f2, S("xf"), H1, H1, H1, H1, 24));
+    // shared encoder (v3.py:403-539)
+    RET(run_block(r, 0, S("xf"), S("e1")));
+    RET(run_conv_in_relu(r, "ds_conv_e02", S("e1"), S("e1d"), H2, H2, H2, H2, 48));
+    RET(run_block(r, 1, S("e1d"), S("e2")));
+    RET(run_conv_in_relu(r, "ds_conv_e03", S("e2"), S("e2d"), H3, H3, H3, H3, 96));
+    RET(run_block(r, 2, S("e2d"), S("e3")));
+  }
+  // decoders (v3.py:549-1009): R on lane 0, S on lane 1, D on lane 2, issued level by level so that D's CFSM
+  // fusion points (v3.py:885, 920) can wait on the R / S up-convolutions of the same level
   const char* brs[3] = {"r", "s", "d"};
   float* outs[3] = {xr, xs, xd};
   const char* tails[3] = {"tail_R", "tail_S", "tail_D"};
+  Run rr[3] = {r0, Run{p, p->lane[1].st, nb, &p->lane[1]}, Run{p, p->lane[2].st, nb, &p->lane[2]}};
+  for (int bi = 1; bi < 3; ++bi) RET(stream_edge(p, st, rr[bi].st));   // encoder maps are ready
+  cudaEvent_t up_done[2] = {nullptr, nullptr};   // R / S up-convolution of the current level
   for (int bi = 0; bi < 3; ++bi) {
+    Run& r = rr[bi];
     const std::string b(brs[bi]);
-    const int s3 = 3 + bi * 3;  // stage indices decoder_03x, 02x, 01x
-    RET(run_block(r, s3, S("e3"), S("d3" + b)));
+    RET(run_block(r, 3 + bi * 3, S("e3"), S("d3" + b)));
     RET(run_conv_in_relu(r, "us_conv_d03" + b, S("d3" + b), S("u3" + b), H3, H3, H2, H2, 48));
+    if (bi < 2 && multi) RET(stream_mark(p, r.st, &up_done[bi]));
+  }
+  for (int bi = 0; bi < 3; ++bi) {
+    Run& r = rr[bi];
+    const std::string b(brs[bi]);
     if (bi < 2) {
       RET(run_conv(r, "sk_conv_d03" + b, S("u3" + b), S("e2"), nullptr, S("d2in" + b), H2, H2, CF_RELU));
     } else {
+      if (multi) { CU(cudaStreamWaitEvent(r.st, up_done[0], 0)); CU(cudaStreamWaitEvent(r.st, up_done[1], 0)); }   // u3r, u3s
       RET(run_cfsm(r, 0, S("u3d"), S("u3r"), S("u3s"), S("d2ind"), H2, H2));
     }
-    RET(run_block(r, s3 + 1, S("d2in" + b), S("d2" + b)));
+    RET(run_block(r, 3 + bi * 3 + 1, S("d2in" + b), S("d2" + b)));
     RET(run_conv(r, "us_conv_d02" + b, S("d2" + b), nullptr, nullptr, S("u2" + b), H2, H2, CF_RELU));
+    if (bi < 2 && multi) RET(stream_mark(p, r.st, &up_done[bi]));
+  }
+  for (int bi = 0; bi < 3; ++bi) {
+    Run& r = rr[bi];
+    const std::string b(brs[bi]);
     if (bi < 2) {
       RET(run_conv(r, "sk_conv_d02" + b, S("u2" + b), S("e1"), nullptr, S("d1in" + b), H1, H1, CF_RELU));
     } else {
+      if (multi) { CU(cudaStreamWaitEvent(r.st, up_done[0], 0)); CU(cudaStreamWaitEvent(r.st, up_done[1], 0)); }   // u2r, u2s
       RET(run_cfsm(r, 1, S("u2d"), S("u2r"), S("u2s"), S("d1ind"), H1, H1));
     }
-    RET(run_block(r, s3 + 2, S("d1in" + b), S("d1" + b)));
+    RET(run_block(r, 3 + bi * 3 + 2, S("d1in" + b), S("d1" + b)));
     // us_conv_d01(block_out + xf) (v3.py:696,852,1008), then the tail (v3.py:348-383)
+    float *f0 = r.ln->f0, *f1 = r.ln->f1;
     RET(run_conv(r, "us_conv_d01" + b, S("d1" + b), S("xf"), nullptr, f0, H1, H1, CF_RELU));
     RET(run_conv(r, std::string(tails[bi]) + ".c1", f0, nullptr, nullptr, f1, H, H, CF_RELU));
     RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H, H, CF_TANH | CF_OUT_NCHW));
   }
+  for (int bi = 1; bi < 3; ++bi) RET(stream_edge(p, rr[bi].st, st));   // join
   return 0;
 }
 
@@ -1079,8 +1169,8 @@ extern "C" int32_t cfen_plan_stage_ptr(cfen_plan* p, const char* name, void** de
     *numel = it->second.second;
     return 0;
   }
-  if (n == "local_tokens") { *dev_ptr = p->lws.t1; *numel = 6LL * p->H * p->H; return 0; }
-  if (n == "global_tokens") { *dev_ptr = p->gws.t1; *numel = (int64_t)(p->H / 32) * (p->H / 32) * 384; return 0; }
+  if (n == "local_tokens") { *dev_ptr = p->lane[0].lws.t1; *numel = 6LL * p->H * p->H; return 0; }
+  if (n == "global_tokens") { *dev_ptr = p->lane[0].gws.t1; *numel = (int64_t)(p->H / 32) * (p->H / 32) * 384; return 0; }
   return fail(5, "unknown stage '%s'", name);
 }
 
