@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcfen_b200.so")
+# CFEN_LIB selects an instrumented build of the same library (csrc/build.py --timeline) for the profiling tools
+LIB_PATH = os.environ.get("CFEN_LIB") or os.path.join(_HERE, "csrc", "libcfen_b200.so")
 
 _lib = None
 

@@ -27,19 +27,23 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, timeline=False):
+    """timeline=True builds the instrumented variant libcfen_b200_tl.so (-DCFEN_TIMELINE: device-side clock
+    stamps in the fused token kernels, tools/timeline_tail16.py); never loaded by the product path."""
+    out = OUT.replace(".so", "_tl.so") if timeline else OUT
+    if not force and not timeline and up_to_date():
         return OUT
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "--use_fast_math" if False else "-DCFEN_NO_FAST_MATH", "-Xcompiler", "-fPIC", "-shared",
-           "-o", OUT, SRC]
+           "-DCFEN_NO_FAST_MATH", "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC]
+    if timeline:
+        cmd.insert(1, "-DCFEN_TIMELINE")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timeline="--timeline" in sys.argv)

@@ -26,6 +26,20 @@ __device__ __forceinline__ void dbg_stamp(int& n, int tag) {
   if (g_dbg_buf && blockIdx.x == 0 && n < 4000) { g_dbg_buf[2 * n] = tag; g_dbg_buf[2 * n + 1] = clock64(); ++n; }
 }
 
+// Compile-time timeline (-DCFEN_TIMELINE, tools/timeline_tail16.py): one lane per role of CTA 0 logs
+// (tag, clock64) pairs into its own 1024-entry region of the debug buffer.  Compiled out otherwise.
+#ifdef CFEN_TIMELINE
+__device__ __forceinline__ void tl_stamp(int role, int& n, int tag) {
+  if (g_dbg_buf && blockIdx.x == 0 && n < 1024) {
+    g_dbg_buf[2 * (role * 1024 + n)] = tag;
+    g_dbg_buf[2 * (role * 1024 + n) + 1] = clock64();
+    ++n;
+  }
+}
+#else
+__device__ __forceinline__ void tl_stamp(int, int&, int) {}
+#endif
+
 struct Mlp16Shape {
   int MH;        // accumulator halves per CTA (BM = 128 * MH)
   int KB1;       // 64-wide k-boxes of GEMM1 (ceil(E / 64))

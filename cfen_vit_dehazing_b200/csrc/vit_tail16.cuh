@@ -96,7 +96,9 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
 
   // Role loops run warp-wide with uniform control flow; one elected lane issues the TMA / tcgen05 instructions.
   const int stsh = ST == 4 ? 2 : 1;   // ST is 2 or 4
+  int tln = 0;   // timeline stamps (compiled out unless -DCFEN_TIMELINE)
   if (warp == 0) {  // ------------------------------------------------ TMA producer
+    if (lane == 0) tl_stamp(0, tln, 100);
     if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(&x_full, KB * 16384);
       for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(xa + kb * 16384, &tmO, &x_full, kb * 64, m0);
@@ -108,6 +110,7 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
     auto acquire = [&]() {
       const int s = seq & (ST - 1);
       tc::mbar_wait(&empty_bar[s], ((seq >> stsh) & 1) ^ 1);
+      if (lane == 0) tl_stamp(0, tln, 110);
       ++seq;
       return s;
     };
@@ -155,8 +158,10 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
     };
     auto ksteps = [&](int kb) { const int krem = E - kb * 64; return krem >= 64 ? 4 : (krem + 15) / 16; };
     // ---- GEMM0: A = O * Wout^T
+    if (lane == 0) tl_stamp(1, tln, 200);
     tc::mbar_wait(&x_full, 0);
     tc::tc_fence_after();
+    if (lane == 0) tl_stamp(1, tln, 201);
     for (int kb = 0; kb < KB; ++kb) {
       const int s = next_full();
       if (tc::elect_one()) {
@@ -173,13 +178,18 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
     int item0 = 0;
     for (int ph = 0; ph < 2; ++ph) {
       const uint32_t ycol = ph == 0 ? COL_B : COL_A;
+      if (lane == 0) tl_stamp(1, tln, 205);
       tc::mbar_wait(&xa_ready[ph], 0);   // epilogue warps have written the new operand tile into Xa
       tc::tc_fence_after();
+      if (lane == 0) tl_stamp(1, tln, 206);
       auto gemm1 = [&](int c) {
         const int w = item0 + c, sl = w & 1;
+        if (lane == 0) tl_stamp(1, tln, 210);
         tc::mbar_wait(&s_empty[sl], ((w >> 1) & 1) ^ 1);
         tc::tc_fence_after();
+        if (lane == 0) tl_stamp(1, tln, 211);
         const int s = next_full();
+        if (lane == 0) tl_stamp(1, tln, 212);
         if (tc::elect_one()) {
           for (int kb = 0; kb < KB; ++kb) {
             const uint64_t ad = tc::umma_desc_sw128(smem_u32(xa + kb * 16384));
@@ -192,12 +202,16 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
           tc::umma_commit(&s_full[sl]);
         }
         __syncwarp();
+        if (lane == 0) tl_stamp(1, tln, 213);
       };
       auto gemm2 = [&](int c) {
         const int w = item0 + c, sl = w & 1;
+        if (lane == 0) tl_stamp(1, tln, 220);
         tc::mbar_wait(&f_full[sl], (w >> 1) & 1);
         tc::tc_fence_after();
+        if (lane == 0) tl_stamp(1, tln, 221);
         const int s = next_full();
+        if (lane == 0) tl_stamp(1, tln, 222);
         if (tc::elect_one()) {
           const uint64_t ad = tc::umma_desc_sw128(smem_u32(fbuf + sl * 16384));
           const uint64_t bd = tc::umma_desc_sw128(smem_u32(ring + s * SLOT));
@@ -208,6 +222,7 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
           if (c == NC - 1) tc::umma_commit(&acc_full[1 + ph]);
         }
         __syncwarp();
+        if (lane == 0) tl_stamp(1, tln, 223);
       };
       gemm1(0);
       gemm1(1);
@@ -227,9 +242,12 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
     // hidden-chunk epilogue of item w (slot w & 1): S -> relu(S + bias) -> fp16 -> F
     auto chunk_epilogue = [&](int w, const float* bias) {
       const int sl = w & 1, it = w >> 1;
+      if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 310);
       tc::mbar_wait(&s_full[sl], it & 1);
       tc::tc_fence_after();
+      if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 311);
       tc::mbar_wait(&f_empty[sl], (it & 1) ^ 1);
+      if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 312);
       uint8_t* fline = fbuf + sl * 16384 + roff;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
@@ -252,6 +270,7 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
       tc::mbar_arrive(&s_empty[sl]);
       tc::fence_async_smem();
       tc::mbar_arrive(&f_full[sl]);
+      if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 313);
     };
     // row epilogue (WG0): t32 <- acc + bias + t32 ; returns nothing, panel by panel
     auto residual_update = [&](uint32_t col, const float* bias) {
@@ -326,14 +345,19 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
     int item0 = 0;
     if (g == 0) {
       // ---- epilogue 0: t1 = t0 + out-proj ; h = LN(t1) -> Xa
+      if (q == 0 && lane == 0) tl_stamp(2, tln, 300);
       tc::mbar_wait(&acc_full[0], 0);
       tc::tc_fence_after();
+      if (q == 0 && lane == 0) tl_stamp(2, tln, 301);
       tc::mbar_wait(&t_full, 0);
+      if (q == 0 && lane == 0) tl_stamp(2, tln, 302);
       residual_update(COL_A, nullptr);
+      if (q == 0 && lane == 0) tl_stamp(2, tln, 303);
       write_xa(true);
       tc::tc_fence_before();
       tc::fence_async_smem();
       tc::mbar_arrive(&xa_ready[0]);
+      if (q == 0 && lane == 0) tl_stamp(2, tln, 304);
     }
     for (int ph = 0; ph < 2; ++ph) {
       const float* hb = ph == 0 ? a.b1 : a.bm0;
@@ -341,14 +365,18 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
         if (((item0 + c) & 1) == g) chunk_epilogue(item0 + c, hb + c * HC);
       item0 += NC;
       if (g == 0) {
+        if (q == 0 && lane == 0) tl_stamp(2, tln, 320);
         tc::mbar_wait(&acc_full[1 + ph], 0);
         tc::tc_fence_after();
+        if (q == 0 && lane == 0) tl_stamp(2, tln, 321);
         if (ph == 0) {   // t2 = t1 + b2 + FFN ; fp16(t2) -> Xa
           residual_update(COL_B, a.b2);
+          if (q == 0 && lane == 0) tl_stamp(2, tln, 322);
           write_xa(false);
           tc::tc_fence_before();
           tc::fence_async_smem();
           tc::mbar_arrive(&xa_ready[1]);
+          if (q == 0 && lane == 0) tl_stamp(2, tln, 323);
         } else {         // out = t2 + bm3 + MLP head -> TMA store from the residual panels
           residual_update(COL_A, a.bm3);
           tc::fence_async_smem();
@@ -358,6 +386,7 @@ vit_tail16_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constant
             tc::tma_store_commit();
             tc::tma_store_wait_read();
           }
+          if (q == 0 && lane == 0) tl_stamp(2, tln, 330);
         }
       }
     }
