@@ -5,8 +5,9 @@
 // out is [nseq*L, E] fp16 (the A operand of the out-projection).  One CTA = 64 queries of one
 // (sequence, head): 4 warps x 16 query rows.  K/V stream through a double-buffered cp.async ring in
 // 64-key tiles; S = Q K^T and O += P V run on mma.sync m16n8k16 (fp16 in, fp32 accumulate) with
-// ldmatrix-fed B fragments (V through ldmatrix.trans); online softmax in fp32 in the log2 domain, row
-// max / row sum reduced with warp shuffles over the 4 lanes that share a row.  The S accumulator layout
+// ldmatrix-fed B fragments (V through ldmatrix.trans); online softmax in the log2 domain: fp32 row max (warp
+// shuffles over the 4 lanes that share a row), exponentials as packed fp16 pairs, row sums accumulated in
+// fp32 by the PV MMAs through an extra all-ones column tile of V.  The S accumulator layout
 // of two adjacent key tiles is exactly the A fragment of the PV step, so P never leaves registers.
 // Head dim 24 is zero-padded to 32 along the QK^T contraction only.
 #pragma once
@@ -19,6 +20,12 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two base-2 exponentials on a packed fp16 pair (one MUFU.EX2 for both)
+__device__ __forceinline__ uint32_t exp2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -94,12 +101,12 @@ attention16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int
     }
   }
 
-  float o[NT][4];
+  float o[NT + 1][4];   // o[NT]: row sums (every column of that tile holds the same sum)
 #pragma unroll
-  for (int n = 0; n < NT; ++n)
+  for (int n = 0; n <= NT; ++n)
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY;
 
   const int ntiles = (L + TK - 1) / TK;
   load_kv(0, 0);
@@ -129,16 +136,19 @@ attention16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int
         mma_f16_16x8x16(s[j + 1], qa[kk], b[2], b[3]);
       }
     }
-    // ---- scale to the log2 domain, mask keys beyond L, online softmax
+    // ---- online softmax on the raw scores: the 1/sqrt(hd) * log2(e) factor is folded into the exponent FFMA
+    // (max commutes with a positive scale); keys beyond L only exist in a ragged last tile
+    if ((kt + 1) * TK > L) {
+#pragma unroll
+      for (int j = 0; j < TK / 8; ++j) {
+        const int key = kt * TK + j * 8 + 2 * t;
+        if (key >= L) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= L) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < TK / 8; ++j) {
-      const int key = kt * TK + j * 8 + 2 * t;
-      const bool ok0 = key < L, ok1 = key + 1 < L;
-      s[j][0] = ok0 ? s[j][0] * scale_log2e : -INFINITY;
-      s[j][1] = ok1 ? s[j][1] * scale_log2e : -INFINITY;
-      s[j][2] = ok0 ? s[j][2] * scale_log2e : -INFINITY;
-      s[j][3] = ok1 ? s[j][3] * scale_log2e : -INFINITY;
       mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
       mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
@@ -147,27 +157,23 @@ attention16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every tile has >= 1 valid key
-    const float al0 = fast_exp2(m0 - mn0), al1 = fast_exp2(m1 - mn1);
+    const float al0 = fast_exp2((m0 - mn0) * scale_log2e), al1 = fast_exp2((m1 - mn1) * scale_log2e);
+    const float nb0 = -mn0 * scale_log2e, nb1 = -mn1 * scale_log2e;
     m0 = mn0; m1 = mn1;
-    l0 *= al0; l1 *= al1;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
+    for (int n = 0; n <= NT; ++n) {   // o[NT] carries the row sums
       o[n][0] *= al0; o[n][1] *= al0; o[n][2] *= al1; o[n][3] *= al1;
     }
-    // ---- P = exp2(S - m) (fp16 A fragments), O += P V
+    // ---- P = exp2(S * c - m * c) as packed fp16 pairs (one MUFU per two probabilities) = the A fragments of
+    // O += P V; the row sums come out of the same MMAs through a ninth "all ones" column tile of V, so they are
+    // accumulated in fp32 from exactly the rounded probabilities the numerator uses
 #pragma unroll
     for (int kk = 0; kk < TK / 16; ++kk) {
-      const float p00 = fast_exp2(s[2 * kk][0] - mn0), p01 = fast_exp2(s[2 * kk][1] - mn0);
-      const float p02 = fast_exp2(s[2 * kk][2] - mn1), p03 = fast_exp2(s[2 * kk][3] - mn1);
-      const float p10 = fast_exp2(s[2 * kk + 1][0] - mn0), p11 = fast_exp2(s[2 * kk + 1][1] - mn0);
-      const float p12 = fast_exp2(s[2 * kk + 1][2] - mn1), p13 = fast_exp2(s[2 * kk + 1][3] - mn1);
-      l0 += (p00 + p01) + (p10 + p11);
-      l1 += (p02 + p03) + (p12 + p13);
       uint32_t a[4];
-      a[0] = pack_half2(p00, p01);  // (row g,   keys 2t, 2t+1)
-      a[1] = pack_half2(p02, p03);  // (row g+8, keys 2t, 2t+1)
-      a[2] = pack_half2(p10, p11);  // (row g,   keys 8+2t, 9+2t)
-      a[3] = pack_half2(p12, p13);  // (row g+8, keys 8+2t, 9+2t)
+      a[0] = exp2_f16x2(pack_half2(fmaf(s[2 * kk][0], scale_log2e, nb0), fmaf(s[2 * kk][1], scale_log2e, nb0)));          // (row g,   keys 2t, 2t+1)
+      a[1] = exp2_f16x2(pack_half2(fmaf(s[2 * kk][2], scale_log2e, nb1), fmaf(s[2 * kk][3], scale_log2e, nb1)));          // (row g+8, keys 2t, 2t+1)
+      a[2] = exp2_f16x2(pack_half2(fmaf(s[2 * kk + 1][0], scale_log2e, nb0), fmaf(s[2 * kk + 1][1], scale_log2e, nb0)));  // (row g,   keys 8+2t, 9+2t)
+      a[3] = exp2_f16x2(pack_half2(fmaf(s[2 * kk + 1][2], scale_log2e, nb1), fmaf(s[2 * kk + 1][3], scale_log2e, nb1)));  // (row g+8, keys 8+2t, 9+2t)
       const __half* vrow = vs + (kk * 16 + (lm_id & 1) * 8 + lm_row) * LD;
 #pragma unroll
       for (int n = 0; n + 1 < NT; n += 2) {
@@ -181,17 +187,14 @@ attention16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int
         ldmatrix_x2_trans(b, vrow + (NT - 1) * 8);
         mma_f16_16x8x16(o[NT - 1], a, b[0], b[1]);
       }
+      mma_f16_16x8x16(o[NT], a, 0x3C003C00u, 0x3C003C00u);   // V column tile of ones -> row sums
     }
     __syncthreads();  // all warps done with this buffer before it is refilled
   }
   cp_async_wait<0>();
 
-  // ---- finalize: row sums across the 4 lanes of a row, normalise, store fp16
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  // ---- finalize: normalise by the row sums, store fp16
+  const float inv0 = 1.f / o[NT][0], inv1 = 1.f / o[NT][2];
   const int r0 = q0 + g, r1 = q0 + g + 8;
   __half* ob = out + (size_t)seq * L * E + h * HD;
 #pragma unroll

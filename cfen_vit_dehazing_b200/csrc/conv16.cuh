@@ -25,11 +25,29 @@ namespace cfen {
 template <class S, bool BIG>
 struct Conv16Tile {
   static constexpr int MR = (BIG && S::STRIDE == 1 && S::CIN <= 24 && S::COUT <= 24) ? 2 : 1;   // strided halos grow 2x per row
-  static constexpr int MC = (BIG && S::CIN <= 48 && S::COUT <= 48) ? 2 : 1;
+  static constexpr int MC = (BIG && S::CIN <= 48 && S::COUT <= 48 && (S::STRIDE == 1 || S::CIN <= 12)) ? 2 : 1;   // strided halos: smem
 };
+
+constexpr int c16_max(int a, int b) { return a > b ? a : b; }
+constexpr int c16_min(int a, int b) { return a < b ? a : b; }
 
 // BIG = false is the 8 x 16 tile every map size (multiples of 8 x 16) accepts; BIG = true is used when the map
 // divides into the larger tile.
+//
+// Third revision (profiles/r1_v4_conv_*.md: the kernels were instruction- and latency-bound - 13 % IMAD,
+// 12 % IADD3, 7 % HMMA, long-scoreboard stalls on the synchronous residual loads, 3 CTAs per SM):
+//   * loaders enumerate real channel groups only (padding is zero-filled separately), keep 8 independent
+//     16-byte loads in flight per thread and do their index arithmetic in 32 bits;
+//   * the local/global merge loader is specialised: the tile lies inside one attention window, so the token
+//     address is shifts and adds, and the bilinear x4 of the global branch is done separably on 1 x 4 pixel
+//     strips (vertical taps shared by the strip, horizontal weights as immediates);
+//   * non-transposed geometries leave through shared memory: the accumulators (after affine / ReLU / tanh) are
+//     staged as the dense output tile over the dead input tile, then copied out with coalesced 16-byte
+//     stores, the residual fetched by the same coalesced pattern with all loads issued up front;
+//   * contraction steps are fully unrolled when the whole weight set is one chunk (tap offsets fold to
+//     immediates), otherwise they come from a small shared-memory table;
+//   * one weight buffer when there is a single chunk; max-shared carveout and a register cap for 4 CTAs / SM
+//     on the thin layers.
 template <class S, bool BIG = true>
 struct Conv16 {
   static constexpr int MR = Conv16Tile<S, BIG>::MR, MC = Conv16Tile<S, BIG>::MC, MB = MR * MC;
@@ -42,30 +60,49 @@ struct Conv16 {
   static constexpr int NPAD = S::NPAD, NT = S::NT;
   static constexpr int KTAP = S::KTAP, NPHASE = S::NPHASE;
   static constexpr int K_FULL = KTAP * CIN_P;               // contraction length per phase
-  // weight chunk = whole taps; at most ~20 KB of smem per buffer
-  static constexpr int TPC_MAX = (10240 / NPAD - 8) / CIN_P;
+  // weight chunk = whole taps; at most ~32 KB of smem per buffer
+  static constexpr int TPC_MAX = (16384 / NPAD - 8) / CIN_P;
   static constexpr int TPC = TPC_MAX >= KTAP ? KTAP : (TPC_MAX < 1 ? 1 : TPC_MAX);
   static constexpr int NCHUNK = (KTAP + TPC - 1) / TPC;
+  static constexpr int NWBUF = NCHUNK * NPHASE > 1 ? 2 : 1;
+  static constexpr bool UNROLLED = NCHUNK == 1 && NPHASE == 1;   // contraction steps are compile-time constants
   static constexpr int WPITCH = TPC * CIN_P + 8;            // halves between output-channel rows of a chunk
   static constexpr int WBUF_HALVES = NPAD * WPITCH;
   static constexpr int TILE_HALVES = IN_H * IN_W * CPITCH + 8;
   static constexpr int STAT_FLOATS = S::NWARPS * NPAD * 2;
+  // staged epilogue: dense output tile [TH][TW][COUT] (NHWC) or [COUT][TH][TW] (NCHW) over the input tile
+  static constexpr bool STAGED = !S::TRANSPOSED;
+  static constexpr int OST_FLOATS = STAGED ? TH * TW * S::COUT : 0;
+  static constexpr int REGION_BYTES = (c16_max(TILE_HALVES * 2, OST_FLOATS * 4) + 15) / 16 * 16;
   // LD_LG: quarter-resolution patch of the global branch (edge-clamped, fp32) staged before the bilinear x4
   static constexpr int QH = TH / 4 + 2, QW = TW / 4 + 2;
   static constexpr int QPATCH_FLOATS = S::LOADER == LD_LG ? QH * QW * (S::CIN / 2) : 0;
-  static constexpr int SMEM_BYTES = (TILE_HALVES + 2 * WBUF_HALVES) * 2 + (STAT_FLOATS + QPATCH_FLOATS) * 4 + 64;
+  static constexpr int TOFF_INTS = UNROLLED ? 0 : NPHASE * KTAP;
+  static constexpr int LGTAB_INTS = S::LOADER == LD_LG ? TH + TW : 0;   // token offsets of the tile's rows / columns
+  static constexpr int SMEM_BYTES =
+      REGION_BYTES + NWBUF * WBUF_HALVES * 2 + (STAT_FLOATS + QPATCH_FLOATS + TOFF_INTS + LGTAB_INTS) * 4 + 64;
   static constexpr int WPACK_HALVES = NPHASE * NPAD * K_FULL;   // global packed weights [phase][n][K_FULL]
+  // CTAs per SM the register allocation is capped for: shared memory allows it and the accumulators are small
+  static constexpr int BLK_SMEM = (227 * 1024) / (SMEM_BYTES + 1024);
+  static constexpr int ACC_REGS = MB * NT * 4;
+  static constexpr int MINB = c16_max(1, c16_min(BLK_SMEM, (ACC_REGS <= 32 && S::KS < 5) ? 4 : (ACC_REGS <= 48 ? 3 : 2)));   // 5x5 / 7x7: unrolled taps spill at 64 registers
   static_assert(SMEM_BYTES <= 227 * 1024, "tile does not fit shared memory");
 };
 
+// sixteenths of the bilinear x4 stencil weights (common.cuh up4_taps) as nibbles indexed by the phase r
+__device__ __forceinline__ float up4_w(uint32_t table, int r) { return (float)((table >> (4 * r)) & 15u) * 0.0625f; }
+
 template <class S, bool BIG>
-__global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __half* __restrict__ wpack) {
+__global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const ConvArgs a, const __half* __restrict__ wpack) {
   using C = Conv16<S, BIG>;
   extern __shared__ __align__(16) unsigned char conv16_smem[];
   __half* tile = reinterpret_cast<__half*>(conv16_smem);
-  __half* wbuf = tile + ((C::TILE_HALVES + 7) / 8) * 8;
-  float* wstat = reinterpret_cast<float*>(wbuf + 2 * C::WBUF_HALVES);
+  float* ost = reinterpret_cast<float*>(conv16_smem);           // aliases the input tile after the main loop
+  __half* wbuf = reinterpret_cast<__half*>(conv16_smem + C::REGION_BYTES);
+  float* wstat = reinterpret_cast<float*>(wbuf + C::NWBUF * C::WBUF_HALVES);
   float* qpatch = wstat + C::STAT_FLOATS;
+  int* toff = reinterpret_cast<int*>(qpatch + C::QPATCH_FLOATS);
+  int* lgtab = toff + C::TOFF_INTS;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -91,92 +128,156 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
   load_w(0, 0, 0);
   cp_async_commit();
 
-  // ---- LD_LG: stage the quarter-resolution patch of the global ViT output this tile interpolates from
-  // (rows / columns clamped to the map like the two align_corners=False x2 passes do)
-  if (S::LOADER == LD_LG) {
-    constexpr int CC = S::CIN / 2, CC4 = CC / 4;
-    const int qh = Hin >> 2, qw = Win >> 2, gwid = qw >> 2;
-    const size_t lg = (size_t)(qh >> 2) * gwid;
-    const int qy0 = (ty0 >> 2) - 1, qx0 = (tx0 >> 2) - 1;
-    for (int i = tid; i < C::QH * C::QW * CC4; i += S::THREADS) {
-      const int c4 = i % CC4, q = i / CC4;
-      const int iy = q / C::QW, ix = q - iy * C::QW;
-      const int qy = min(max(qy0 + iy, 0), qh - 1), qx = min(max(qx0 + ix, 0), qw - 1);
-      const float4 v = *reinterpret_cast<const float4*>(
-          a.in1 + ((size_t)b * lg + (size_t)(qy >> 2) * gwid + (qx >> 2)) * (16 * CC) + ((qy & 3) * 4 + (qx & 3)) * CC + c4 * 4);
-      *reinterpret_cast<float4*>(qpatch + (size_t)q * CC + c4 * 4) = v;
+  // smem offset (halves) of tap `tap` of phase `ph`, relative to a pixel's a_base
+  auto tap_offset = [&](int ph, int tap) -> int {
+    if (S::TRANSPOSED) {
+      const int dy = convt_doff(ph >> 1, tap >> 1), dx = convt_doff(ph & 1, tap & 1);
+      return ((1 + dy) * C::IN_W + (1 + dx)) * C::CPITCH;
     }
-    __syncthreads();
+    return ((tap / S::KS) * C::IN_W + (tap % S::KS)) * C::CPITCH;
+  };
+  if (!C::UNROLLED) {
+    for (int i = tid; i < C::NPHASE * C::KTAP; i += S::THREADS) toff[i] = tap_offset(i / C::KTAP, i % C::KTAP);
   }
 
-  // ---- stage the input halo tile as fp16 [pixel][CPITCH]; channels [CIN, CIN_P) are zero
-  {
-    constexpr int C4 = C::CIN_P / 4;   // 4-channel groups per pixel (incl. zero padding)
-    const int oy0 = S::TRANSPOSED ? ty0 - 1 : ty0 * S::STRIDE - S::PAD;
-    const int ox0 = S::TRANSPOSED ? tx0 - 1 : tx0 * S::STRIDE - S::PAD;
+  const int oy0 = S::TRANSPOSED ? ty0 - 1 : ty0 * S::STRIDE - S::PAD;
+  const int ox0 = S::TRANSPOSED ? tx0 - 1 : tx0 * S::STRIDE - S::PAD;
+
+  if constexpr (S::LOADER == LD_LG) {
+    // ------------------------------------------------------------------ local / global merge (1x1, no halo)
+    // channels [0,CC) = local ViT tokens, [CC,2CC) = bilinear x4 of the global ViT tokens
+    constexpr int CC = S::CIN / 2, CC4 = CC / 4;
+    // (1) quarter-resolution patch of the global ViT output this tile interpolates from (rows / columns clamped
+    //     to the map like the two align_corners=False x2 passes do)
+    {
+      const int qh = Hin >> 2, qw = Win >> 2, gwid = qw >> 2;
+      const size_t lg = (size_t)(qh >> 2) * gwid;
+      const int qy0 = (ty0 >> 2) - 1, qx0 = (tx0 >> 2) - 1;
+      const float* gbase = a.in1 + (size_t)b * lg * (16 * CC);
+      for (int i = tid; i < C::QH * C::QW * CC4; i += S::THREADS) {
+        const int c4 = i % CC4, q = i / CC4;
+        const int iy = q / C::QW, ix = q - iy * C::QW;
+        const int qy = min(max(qy0 + iy, 0), qh - 1), qx = min(max(qx0 + ix, 0), qw - 1);
+        const float4 v = *reinterpret_cast<const float4*>(
+            gbase + (uint32_t)(((qy >> 2) * gwid + (qx >> 2)) * (16 * CC) + ((qy & 3) * 4 + (qx & 3)) * CC + c4 * 4));
+        *reinterpret_cast<float4*>(qpatch + q * CC + c4 * 4) = v;
+      }
+    }
+    // (2) local half.  The token address of pixel (gy, gx) separates into a row part and a column part
+    //     (window row / column, token row / column inside the window, sub-position inside the 2x2 patch);
+    //     both are tabulated once per tile so the per-item address is two table reads and two adds.
+    {
+      const int win = a.win, half = win >> 1, nwx = Win / win;
+      if (tid < C::TH) {
+        const int gy = ty0 + tid, wy = gy / win, ly = gy - wy * win;
+        lgtab[tid] = (wy * nwx * half * half + (ly >> 1) * half) * (4 * CC) + (ly & 1) * 2 * CC;
+      } else if (tid < C::TH + C::TW) {
+        const int gx = tx0 + tid - C::TH, wx = gx / win, lx = gx - wx * win;
+        lgtab[tid] = (wx * half * half + (lx >> 1)) * (4 * CC) + (lx & 1) * CC;
+      }
+      __syncthreads();
+      const float* lbase = a.in0 + (size_t)b * Hin * Win * CC;   // tokens of image b: Hin * Win / 4 rows of 4 CC
+      constexpr int U = 8, TOTAL = C::TH * C::TW * CC4;
+      for (int i0 = tid; i0 < TOTAL; i0 += S::THREADS * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * S::THREADS;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < TOTAL) {
+            const int c4 = i % CC4, pix = i / CC4;
+            const uint32_t off = (uint32_t)(lgtab[pix / C::TW] + lgtab[C::TH + pix % C::TW] + c4 * 4);
+            v[u] = *reinterpret_cast<const float4*>(lbase + off);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * S::THREADS;
+          if (i < TOTAL) {
+            const int c4 = i % CC4, pix = i / CC4;
+            *reinterpret_cast<uint2*>(tile + pix * C::CPITCH + c4 * 4) = make_uint2(pack_half2(v[u].x, v[u].y), pack_half2(v[u].z, v[u].w));
+          }
+        }
+      }
+    }
+    __syncthreads();   // qpatch complete
+    // (3) global half: one work item = (row iy, source column kx, channel group) -> the 4 output pixels
+    //     4 kx .. 4 kx + 3 of that row.  Vertical taps first (shared by the strip), then the four horizontal
+    //     stencils with immediate weights.  Patch row / column p holds source sample (tile origin / 4) - 1 + p.
+    {
+      constexpr int SW = C::TW / 4, NSTRIP = C::TH * SW * CC4;
+      for (int u = tid; u < NSTRIP; u += S::THREADS) {
+        const int c4 = u % CC4, rem = u / CC4;
+        const int kx = rem % SW, iy = rem / SW;
+        const int r = iy & 3, ky = iy >> 2;
+        const float wy0 = up4_w(0x0136u, r), wy1 = up4_w(0xACCAu, r), wy2 = up4_w(0x6310u, r);
+        const float* p = qpatch + (ky * C::QW + kx) * CC + c4 * 4;
+        float4 V[3];
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+          const float4 s0 = *reinterpret_cast<const float4*>(p + ib * CC);
+          const float4 s1 = *reinterpret_cast<const float4*>(p + (C::QW + ib) * CC);
+          const float4 s2 = *reinterpret_cast<const float4*>(p + (2 * C::QW + ib) * CC);
+          V[ib].x = wy0 * s0.x + wy1 * s1.x + wy2 * s2.x;
+          V[ib].y = wy0 * s0.y + wy1 * s1.y + wy2 * s2.y;
+          V[ib].z = wy0 * s0.z + wy1 * s1.z + wy2 * s2.z;
+          V[ib].w = wy0 * s0.w + wy1 * s1.w + wy2 * s2.w;
+        }
+        __half* dst = tile + (iy * C::TW + 4 * kx) * C::CPITCH + CC + c4 * 4;
+        auto put = [&](int rr, float w0, float w1, float w2) {
+          const float x = w0 * V[0].x + w1 * V[1].x + w2 * V[2].x;
+          const float y = w0 * V[0].y + w1 * V[1].y + w2 * V[2].y;
+          const float z = w0 * V[0].z + w1 * V[1].z + w2 * V[2].z;
+          const float w = w0 * V[0].w + w1 * V[1].w + w2 * V[2].w;
+          *reinterpret_cast<uint2*>(dst + rr * C::CPITCH) = make_uint2(pack_half2(x, y), pack_half2(z, w));
+        };
+        put(0, 0.375f, 0.625f, 0.f);
+        put(1, 0.1875f, 0.75f, 0.0625f);
+        put(2, 0.0625f, 0.75f, 0.1875f);
+        put(3, 0.f, 0.625f, 0.375f);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ pixel-major inputs: halo tile as fp16
+    // [pixel][CPITCH]; real channel groups only, channels [CIN_REAL, CIN_P) are zero-filled below
+    constexpr int C4R = S::LOADER == LD_NCHW3 ? 1 : S::CIN / 4;
+    constexpr int U = S::LOADER == LD_SUM2 ? 4 : 8, TOTAL = C::IN_H * C::IN_W * C4R;
+    const size_t img = (size_t)b * Hin * Win;   // first pixel of this image
     auto fetch = [&](int i) -> float4 {
-      const int c4 = i % C4, pix = i / C4;
+      const int c4 = i % C4R, pix = i / C4R;
       const int iy = pix / C::IN_W, ix = pix - iy * C::IN_W;
       int gy = oy0 + iy, gx = ox0 + ix;
-      bool inside = c4 * 4 < S::CIN;
+      bool inside = true;
       if (S::REFLECT) {
         gy = gy < 0 ? -gy : (gy >= Hin ? 2 * (Hin - 1) - gy : gy);
         gx = gx < 0 ? -gx : (gx >= Win ? 2 * (Win - 1) - gx : gx);
       } else {
-        inside = inside && gy >= 0 && gy < Hin && gx >= 0 && gx < Win;
+        inside = (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win;
       }
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (inside) {
-        const size_t pidx = ((size_t)b * Hin + gy) * Win + gx;
+        const uint32_t pidx = (uint32_t)(gy * Win + gx);   // pixel inside the image
         if (S::LOADER == LD_NHWC) {
-          v = *reinterpret_cast<const float4*>(a.in0 + pidx * S::CIN + c4 * 4);
+          v = *reinterpret_cast<const float4*>(a.in0 + img * S::CIN + (pidx * S::CIN + c4 * 4));
         } else if (S::LOADER == LD_SUM2) {
-          const float4 p = *reinterpret_cast<const float4*>(a.in0 + pidx * S::CIN + c4 * 4);
-          const float4 q = *reinterpret_cast<const float4*>(a.in1 + pidx * S::CIN + c4 * 4);
+          const float4 p = *reinterpret_cast<const float4*>(a.in0 + img * S::CIN + (pidx * S::CIN + c4 * 4));
+          const float4 q = *reinterpret_cast<const float4*>(a.in1 + img * S::CIN + (pidx * S::CIN + c4 * 4));
           v = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
         } else if (S::LOADER == LD_CAT2) {
           constexpr int C1 = S::CIN / 2;
           const int c = c4 * 4;
-          v = c < C1 ? *reinterpret_cast<const float4*>(a.in0 + pidx * C1 + c)
-                     : *reinterpret_cast<const float4*>(a.in1 + pidx * C1 + (c - C1));
-        } else if (S::LOADER == LD_NCHW3) {
+          v = c < C1 ? *reinterpret_cast<const float4*>(a.in0 + img * C1 + (pidx * C1 + c))
+                     : *reinterpret_cast<const float4*>(a.in1 + img * C1 + (pidx * C1 + (c - C1)));
+        } else {  // LD_NCHW3
           const size_t plane = (size_t)Hin * Win;
-          const float* p = a.in0 + (size_t)b * 3 * plane + (size_t)gy * Win + gx;
+          const float* p = a.in0 + img * 3 + pidx;
           v = make_float4(p[0], p[plane], p[2 * plane], 0.f);
-        } else {  // LD_LG: channels [0,C) = local ViT tokens, [C,2C) = bilinear x4 of global ViT tokens
-          constexpr int CC = S::CIN / 2;
-          const int c = c4 * 4;
-          if (c < CC) {
-            const int win = a.win, half = win >> 1;
-            const int wy = gy / win, ly = gy - wy * win, wx = gx / win, lx = gx - wx * win;
-            const size_t m = (((size_t)b * (Hin / win) + wy) * (Win / win) + wx) * (half * half) +
-                             (ly >> 1) * half + (lx >> 1);
-            v = *reinterpret_cast<const float4*>(a.in0 + m * (4 * CC) + ((ly & 1) * 2 + (lx & 1)) * CC + c);
-          } else {
-            const int cc = c - CC;
-            float wy[3], wx[3];
-            up4_taps(gy & 3, wy);
-            up4_taps(gx & 3, wx);
-            const int py0 = (gy >> 2) - (ty0 >> 2), px0 = (gx >> 2) - (tx0 >> 2);   // patch row / column of tap 0
-#pragma unroll
-            for (int ia = 0; ia < 3; ++ia) {
-              if (wy[ia] == 0.f) continue;
-#pragma unroll
-              for (int ib = 0; ib < 3; ++ib) {
-                if (wx[ib] == 0.f) continue;
-                const float wgt = wy[ia] * wx[ib];
-                const float4 s = *reinterpret_cast<const float4*>(qpatch + ((py0 + ia) * C::QW + (px0 + ib)) * CC + cc);
-                v.x += wgt * s.x; v.y += wgt * s.y; v.z += wgt * s.z; v.w += wgt * s.w;
-              }
-            }
-          }
         }
       }
       return v;
     };
     // batches of U independent items per thread: all global loads of a batch are issued before the first
     // conversion / shared-memory store, so each thread keeps U requests in flight
-    constexpr int U = 4, TOTAL = C::IN_H * C::IN_W * C4;
     for (int i0 = tid; i0 < TOTAL; i0 += S::THREADS * U) {
       float4 v[U];
 #pragma unroll
@@ -188,9 +289,16 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * S::THREADS;
         if (i < TOTAL) {
-          const int c4 = i % C4, pix = i / C4;
+          const int c4 = i % C4R, pix = i / C4R;
           *reinterpret_cast<uint2*>(tile + pix * C::CPITCH + c4 * 4) = make_uint2(pack_half2(v[u].x, v[u].y), pack_half2(v[u].z, v[u].w));
         }
+      }
+    }
+    if (C::CIN_P > C4R * 4) {   // zero the contraction padding
+      constexpr int PADG = (C::CIN_P - C4R * 4) / 4;
+      for (int i = tid; i < C::IN_H * C::IN_W * PADG; i += S::THREADS) {
+        const int pg = i % PADG, pix = i / PADG;
+        *reinterpret_cast<uint2*>(tile + pix * C::CPITCH + (C4R + pg) * 4) = make_uint2(0u, 0u);
       }
     }
   }
@@ -221,126 +329,134 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
         for (int e = 0; e < 4; ++e) acc[mb][j][e] = 0.f;
 
     for (int ch = 0; ch < C::NCHUNK; ++ch, ++it) {
-      {
+      if (C::NWBUF == 2) {
         int nph = ph, nch = ch + 1;
         if (nch == C::NCHUNK) { nch = 0; ++nph; }
         if (nph < C::NPHASE) load_w((it + 1) & 1, nph, nch);
         cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
-      cp_async_wait<1>();
       __syncthreads();
-      const __half* wb = wbuf + (it & 1) * C::WBUF_HALVES;
-      const int tap0 = ch * C::TPC;
-      const int ntaps = (C::KTAP - tap0) < C::TPC ? (C::KTAP - tap0) : C::TPC;
-      const int nsteps = ntaps * C::KG;       // k16 steps in this chunk
-      auto tap_off = [&](int s) {             // smem offset (halves) of k-step s of this chunk, relative to a_base
-        const int tap = tap0 + s / C::KG, kg = s - (s / C::KG) * C::KG;
-        int toff;
-        if (S::TRANSPOSED) {
-          const int dy = convt_doff(ph >> 1, tap >> 1), dx = convt_doff(ph & 1, tap & 1);
-          toff = ((1 + dy) * C::IN_W + (1 + dx)) * C::CPITCH;
-        } else {
-          toff = ((tap / S::KS) * C::IN_W + (tap % S::KS)) * C::CPITCH;
-        }
-        return toff + kg * 16;
-      };
-      if (C::NT == 1) {
-        for (int s = 0; s < nsteps; s += 2) {
-          uint32_t bf[4];
-          // rows n = b_row; k offset = (s + (b_sel >> 1)) * 16 + (b_sel & 1) * 8 ; the pad columns past the
-          // last step of an odd chunk are never multiplied
-          ldmatrix_x4(bf, wb + b_row * C::WPITCH + (s + (b_sel >> 1)) * 16 + (b_sel & 1) * 8);
-          const int o0 = tap_off(s), o1 = s + 1 < nsteps ? tap_off(s + 1) : 0;
+      const __half* wb = wbuf + (C::NWBUF == 2 ? (it & 1) : 0) * C::WBUF_HALVES;
+      // one k16 step: B fragments of every n-tile, then MB A fragments x NT MMAs
+      auto kstep_multi = [&](int s, int o0) {
+        uint32_t bf[C::NT][2];
 #pragma unroll
-          for (int mb = 0; mb < C::MB; ++mb) {
-            uint32_t af[4];
-            ldmatrix_x4(af, tile + a_base[mb] + o0);
-            mma_f16_16x8x16(acc[mb][0], af, bf[0], bf[1]);
-            if (s + 1 < nsteps) {
-              ldmatrix_x4(af, tile + a_base[mb] + o1);
-              mma_f16_16x8x16(acc[mb][0], af, bf[2], bf[3]);
-            }
+        for (int j = 0; j + 1 < C::NT; j += 2) {
+          uint32_t r4[4];
+          ldmatrix_x4(r4, wb + ((j + (b_sel >> 1)) * 8 + b_row) * C::WPITCH + s * 16 + (b_sel & 1) * 8);
+          bf[j][0] = r4[0]; bf[j][1] = r4[1]; bf[j + 1][0] = r4[2]; bf[j + 1][1] = r4[3];
+        }
+        if (C::NT & 1) {   // odd n-tile count (COUT = 24): last tile through an x2 load
+          ldmatrix_x2(bf[C::NT - 1], wb + ((C::NT - 1) * 8 + b_row) * C::WPITCH + s * 16 + (b_sel & 1) * 8);
+        }
+#pragma unroll
+        for (int mb = 0; mb < C::MB; ++mb) {
+          uint32_t af[4];
+          ldmatrix_x4(af, tile + a_base[mb] + o0);
+#pragma unroll
+          for (int j = 0; j < C::NT; ++j) mma_f16_16x8x16(acc[mb][j], af, bf[j][0], bf[j][1]);
+        }
+      };
+      // two k16 steps of the single n-tile geometries: one ldmatrix.x4 carries the B fragments of both
+      auto kstep_pair = [&](int s, int o0, int o1, bool second) {
+        uint32_t bf[4];
+        // rows n = b_row; k offset = (s + (b_sel >> 1)) * 16 + (b_sel & 1) * 8 ; the pad columns past the
+        // last step of an odd chunk are never multiplied
+        ldmatrix_x4(bf, wb + b_row * C::WPITCH + (s + (b_sel >> 1)) * 16 + (b_sel & 1) * 8);
+#pragma unroll
+        for (int mb = 0; mb < C::MB; ++mb) {
+          uint32_t af[4];
+          ldmatrix_x4(af, tile + a_base[mb] + o0);
+          mma_f16_16x8x16(acc[mb][0], af, bf[0], bf[1]);
+          if (second) {
+            ldmatrix_x4(af, tile + a_base[mb] + o1);
+            mma_f16_16x8x16(acc[mb][0], af, bf[2], bf[3]);
           }
+        }
+      };
+      if constexpr (C::UNROLLED) {
+        constexpr int NSTEPS = C::KTAP * C::KG;
+        if constexpr (C::NT == 1) {
+#pragma unroll
+          for (int s = 0; s < NSTEPS; s += 2)
+            kstep_pair(s, tap_offset(0, s / C::KG) + (s % C::KG) * 16,
+                       s + 1 < NSTEPS ? tap_offset(0, (s + 1) / C::KG) + ((s + 1) % C::KG) * 16 : 0, s + 1 < NSTEPS);
+        } else {
+#pragma unroll
+          for (int s = 0; s < NSTEPS; ++s) kstep_multi(s, tap_offset(0, s / C::KG) + (s % C::KG) * 16);
         }
       } else {
-        for (int s = 0; s < nsteps; ++s) {
-          uint32_t bf[C::NT][2];
-#pragma unroll
-          for (int j = 0; j + 1 < C::NT; j += 2) {
-            uint32_t r4[4];
-            ldmatrix_x4(r4, wb + ((j + (b_sel >> 1)) * 8 + b_row) * C::WPITCH + s * 16 + (b_sel & 1) * 8);
-            bf[j][0] = r4[0]; bf[j][1] = r4[1]; bf[j + 1][0] = r4[2]; bf[j + 1][1] = r4[3];
+        const int tap0 = ch * C::TPC;
+        const int ntaps = (C::KTAP - tap0) < C::TPC ? (C::KTAP - tap0) : C::TPC;
+        const int* tp = toff + ph * C::KTAP + tap0;
+        if constexpr (C::NT == 1) {
+          const int nsteps = ntaps * C::KG;
+          for (int s = 0; s < nsteps; s += 2) {
+            const int o0 = tp[s / C::KG] + (s % C::KG) * 16;
+            const bool second = s + 1 < nsteps;
+            const int o1 = second ? tp[(s + 1) / C::KG] + ((s + 1) % C::KG) * 16 : 0;
+            kstep_pair(s, o0, o1, second);
           }
-          if (C::NT & 1) {   // odd n-tile count (COUT = 24): last tile through an x2 load
-            ldmatrix_x2(bf[C::NT - 1], wb + ((C::NT - 1) * 8 + b_row) * C::WPITCH + s * 16 + (b_sel & 1) * 8);
-          }
-          const int o0 = tap_off(s);
+        } else {
+          for (int tp_i = 0; tp_i < ntaps; ++tp_i) {
+            const int o = tp[tp_i];
 #pragma unroll
-          for (int mb = 0; mb < C::MB; ++mb) {
-            uint32_t af[4];
-            ldmatrix_x4(af, tile + a_base[mb] + o0);
-#pragma unroll
-            for (int j = 0; j < C::NT; ++j) mma_f16_16x8x16(acc[mb][j], af, bf[j][0], bf[j][1]);
+            for (int kg = 0; kg < C::KG; ++kg) kstep_multi(tp_i * C::KG + kg, o + kg * 16);
           }
         }
       }
       __syncthreads();
     }
 
-    // ---- epilogue for this phase: folded bias / ActNorm affine, ReLU / tanh, residual, optional statistics
+    // ---- epilogue for this phase: folded bias / ActNorm affine, ReLU / tanh, optional statistics; then either
+    // staged (dense tile in shared memory, coalesced copy-out with the residual) or direct (transposed phases)
     const int ry = ph >> 1, rx = ph & 1;
     const bool want_stats = a.stats != nullptr;
-    float st_s[C::NT][2], st_q[C::NT][2];
+    const int flags = a.flags;
 #pragma unroll
-    for (int j = 0; j < C::NT; ++j) { st_s[j][0] = st_s[j][1] = st_q[j][0] = st_q[j][1] = 0.f; }
+    for (int j = 0; j < C::NT; ++j) {
+      const int c = j * 8 + 2 * t;
+      const bool ok0 = c < S::COUT, ok1 = c + 1 < S::COUT;
+      const float s0 = ok0 ? a.scale[c] : 0.f, h0 = ok0 ? a.shift[c] : 0.f;
+      const float s1 = ok1 ? a.scale[c + 1] : 0.f, h1 = ok1 ? a.shift[c + 1] : 0.f;
+      float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
 #pragma unroll
-    for (int mb = 0; mb < C::MB; ++mb) {
-      const int py = warp * C::MR + mb / C::MC, pxa = (mb % C::MC) * 16 + g, pxb = pxa + 8;
-      const int oy = S::TRANSPOSED ? 2 * (ty0 + py) + ry : ty0 + py;
-      const int oxa = S::TRANSPOSED ? 2 * (tx0 + pxa) + rx : tx0 + pxa;
-      const int oxb = S::TRANSPOSED ? 2 * (tx0 + pxb) + rx : tx0 + pxb;
-#pragma unroll
-      for (int j = 0; j < C::NT; ++j) {
-        const int c = j * 8 + 2 * t;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (c < S::COUT) {
-          const float s0 = a.scale[c], h0 = a.shift[c];
-          v[0] = acc[mb][j][0] * s0 + h0;
-          v[2] = acc[mb][j][2] * s0 + h0;
-        }
-        if (c + 1 < S::COUT) {
-          const float s1 = a.scale[c + 1], h1 = a.shift[c + 1];
-          v[1] = acc[mb][j][1] * s1 + h1;
-          v[3] = acc[mb][j][3] * s1 + h1;
-        }
+      for (int mb = 0; mb < C::MB; ++mb) {
+        const int py = warp * C::MR + mb / C::MC, pxa = (mb % C::MC) * 16 + g, pxb = pxa + 8;
+        float v[4];
+        v[0] = acc[mb][j][0] * s0 + h0;
+        v[1] = acc[mb][j][1] * s1 + h1;
+        v[2] = acc[mb][j][2] * s0 + h0;
+        v[3] = acc[mb][j][3] * s1 + h1;
         if (want_stats) {
-          st_s[j][0] += v[0] + v[2]; st_s[j][1] += v[1] + v[3];
-          st_q[j][0] += v[0] * v[0] + v[2] * v[2]; st_q[j][1] += v[1] * v[1] + v[3] * v[3];
+          st_s0 += v[0] + v[2]; st_s1 += v[1] + v[3];
+          st_q0 += v[0] * v[0] + v[2] * v[2]; st_q1 += v[1] * v[1] + v[3] * v[3];
         }
-        if (a.flags & CF_RELU) {
+        if (flags & CF_RELU) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
         }
-        if (a.flags & CF_TANH) {
+        if (flags & CF_TANH) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = tanhf(v[e]);
         }
-        if (a.flags & CF_OUT_NCHW) {
-          const size_t plane = (size_t)Hout * Wout;
-          if (c < S::COUT) {
-            float* o = a.out + ((size_t)b * S::COUT + c) * plane + (size_t)oy * Wout;
-            o[oxa] = v[0];
-            o[oxb] = v[2];
+        if constexpr (C::STAGED) {
+          if (flags & CF_OUT_NCHW) {   // [COUT][TH][TW]
+            if (ok0) { ost[(c * C::TH + py) * C::TW + pxa] = v[0]; ost[(c * C::TH + py) * C::TW + pxb] = v[2]; }
+            if (ok1) { ost[((c + 1) * C::TH + py) * C::TW + pxa] = v[1]; ost[((c + 1) * C::TH + py) * C::TW + pxb] = v[3]; }
+          } else if (ok0) {            // [TH][TW][COUT]; COUT is even on every NHWC-output geometry
+            *reinterpret_cast<float2*>(ost + (py * C::TW + pxa) * S::COUT + c) = make_float2(v[0], v[1]);
+            *reinterpret_cast<float2*>(ost + (py * C::TW + pxb) * S::COUT + c) = make_float2(v[2], v[3]);
           }
-          if (c + 1 < S::COUT) {
-            float* o = a.out + ((size_t)b * S::COUT + c + 1) * plane + (size_t)oy * Wout;
-            o[oxa] = v[1];
-            o[oxb] = v[3];
-          }
-        } else if (c < S::COUT) {  // NHWC; COUT is even on every NHWC-output geometry
+        } else if (ok0) {              // transposed phases: NHWC, pixels (2y + ry, 2x + rx)
+          const int oy = 2 * (ty0 + py) + ry;
+          const int oxa = 2 * (tx0 + pxa) + rx, oxb = 2 * (tx0 + pxb) + rx;
           const size_t ia = (((size_t)b * Hout + oy) * Wout + oxa) * S::COUT + c;
           const size_t ib = (((size_t)b * Hout + oy) * Wout + oxb) * S::COUT + c;
-          if (a.flags & CF_RES) {
+          if (flags & CF_RES) {
             const float2 ra = *reinterpret_cast<const float2*>(a.res + ia);
             const float2 rb = *reinterpret_cast<const float2*>(a.res + ib);
             v[0] += ra.x; v[1] += ra.y; v[2] += rb.x; v[3] += rb.y;
@@ -349,41 +465,79 @@ __global__ void __launch_bounds__(256) conv16_kernel(const ConvArgs a, const __h
           *reinterpret_cast<float2*>(a.out + ib) = make_float2(v[2], v[3]);
         }
       }
-    }
-    if (want_stats) {
-#pragma unroll
-      for (int j = 0; j < C::NT; ++j) {
-        const int c = j * 8 + 2 * t;
-        float sa = st_s[j][0], sb = st_s[j][1], qa = st_q[j][0], qb = st_q[j][1];
+      if (want_stats) {
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
-          sa += __shfl_xor_sync(0xffffffffu, sa, o);
-          sb += __shfl_xor_sync(0xffffffffu, sb, o);
-          qa += __shfl_xor_sync(0xffffffffu, qa, o);
-          qb += __shfl_xor_sync(0xffffffffu, qb, o);
+          st_s0 += __shfl_xor_sync(0xffffffffu, st_s0, o);
+          st_s1 += __shfl_xor_sync(0xffffffffu, st_s1, o);
+          st_q0 += __shfl_xor_sync(0xffffffffu, st_q0, o);
+          st_q1 += __shfl_xor_sync(0xffffffffu, st_q1, o);
         }
         if (g == 0) {
-          wstat[(warp * C::NPAD + c) * 2 + 0] = sa;
-          wstat[(warp * C::NPAD + c) * 2 + 1] = qa;
-          wstat[(warp * C::NPAD + c + 1) * 2 + 0] = sb;
-          wstat[(warp * C::NPAD + c + 1) * 2 + 1] = qb;
+          wstat[(warp * C::NPAD + c) * 2 + 0] = st_s0;
+          wstat[(warp * C::NPAD + c) * 2 + 1] = st_q0;
+          wstat[(warp * C::NPAD + c + 1) * 2 + 0] = st_s1;
+          wstat[(warp * C::NPAD + c + 1) * 2 + 1] = st_q1;
         }
       }
-      __syncthreads();
-      if (tid < S::COUT) {
-        float s = 0.f, q = 0.f;
+    }
+    if (C::STAGED || want_stats) __syncthreads();
+    if (want_stats && tid < S::COUT) {
+      float s = 0.f, q = 0.f;
 #pragma unroll
-        for (int w = 0; w < S::NWARPS; ++w) {
-          s += wstat[(w * C::NPAD + tid) * 2 + 0];
-          q += wstat[(w * C::NPAD + tid) * 2 + 1];
-        }
-        const int tiles = gridDim.x * gridDim.y;
-        const int part = (blockIdx.y * gridDim.x + blockIdx.x) * C::NPHASE + ph;
-        float* dst = a.stats + (((size_t)b * tiles * C::NPHASE + part) * 2) * S::COUT;
-        dst[tid] = s;
-        dst[S::COUT + tid] = q;
+      for (int w = 0; w < S::NWARPS; ++w) {
+        s += wstat[(w * C::NPAD + tid) * 2 + 0];
+        q += wstat[(w * C::NPAD + tid) * 2 + 1];
       }
-      __syncthreads();
+      const int tiles = gridDim.x * gridDim.y;
+      const int part = (blockIdx.y * gridDim.x + blockIdx.x) * C::NPHASE + ph;
+      float* dst = a.stats + (((size_t)b * tiles * C::NPHASE + part) * 2) * S::COUT;
+      dst[tid] = s;
+      dst[S::COUT + tid] = q;
+    }
+    if constexpr (C::STAGED) {
+      // coalesced copy-out: 16-byte pieces of the tile's output rows; residual loads of a batch go first
+      constexpr int UO = 4;
+      if (flags & CF_OUT_NCHW) {
+        constexpr int RW4 = C::TW / 4, TOTAL4 = S::COUT * C::TH * RW4;
+        const size_t plane = (size_t)Hout * Wout;
+        float* obase = a.out + (size_t)b * S::COUT * plane + (size_t)ty0 * Wout + tx0;
+        for (int i = tid; i < TOTAL4; i += S::THREADS) {
+          const int x4 = i % RW4, rowc = i / RW4;        // rowc = c * TH + y
+          const int y = rowc % C::TH, c = rowc / C::TH;
+          const float4 v = *reinterpret_cast<const float4*>(ost + i * 4);
+          *reinterpret_cast<float4*>(obase + (size_t)c * plane + (uint32_t)(y * Wout + x4 * 4)) = v;
+        }
+      } else {
+        constexpr int RW4 = C::TW * S::COUT / 4, TOTAL4 = C::TH * RW4;
+        const size_t obase = (((size_t)b * Hout + ty0) * Wout + tx0) * S::COUT;
+        const uint32_t rowpitch = (uint32_t)Wout * S::COUT;
+        const bool has_res = (flags & CF_RES) != 0;
+        for (int i0 = tid; i0 < TOTAL4; i0 += S::THREADS * UO) {
+          float4 r[UO];
+#pragma unroll
+          for (int u = 0; u < UO; ++u) {
+            const int i = i0 + u * S::THREADS;
+            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res && i < TOTAL4) {
+              const int y = i / RW4, x4 = i - y * RW4;
+              r[u] = *reinterpret_cast<const float4*>(a.res + obase + (y * rowpitch + x4 * 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UO; ++u) {
+            const int i = i0 + u * S::THREADS;
+            if (i < TOTAL4) {
+              const int y = i / RW4, x4 = i - y * RW4;
+              const float4 v = *reinterpret_cast<const float4*>(ost + i * 4);
+              *reinterpret_cast<float4*>(a.out + obase + (y * rowpitch + x4 * 4)) =
+                  make_float4(v.x + r[u].x, v.y + r[u].y, v.z + r[u].z, v.w + r[u].w);
+            }
+          }
+        }
+      }
+    } else if (want_stats) {
+      __syncthreads();   // wstat is rewritten by the next phase
     }
   }
   cp_async_wait<0>();
@@ -394,8 +548,15 @@ inline cudaError_t conv16_set_attr() {
   cudaError_t e = cudaFuncSetAttribute(conv16_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Conv16<S, true>::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv16_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Conv16<S, false>::SMEM_BYTES);
+  e = cudaFuncSetAttribute(conv16_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           Conv16<S, false>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  // several CTAs per SM hide each other's load / compute / store phases: ask for the largest shared-memory carveout
+  e = cudaFuncSetAttribute(conv16_kernel<S, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv16_kernel<S, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
 }
 // the large tile is used whenever the tile domain divides into it
 template <class S>
