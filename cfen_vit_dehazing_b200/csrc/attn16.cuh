@@ -24,7 +24,7 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
 // two base-2 exponentials on a packed fp16 pair (one MUFU.EX2 for both)
 __device__ __forceinline__ uint32_t exp2_f16x2(uint32_t x) {
   uint32_t y;
-  asm("ex2.approx.ftz.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
