@@ -33,6 +33,7 @@
 #include "mlp_tc.cuh"
 #include "vit_kernels.cuh"
 #include "vit_tail16.cuh"
+#include "vit_tail16r.cuh"
 
 using namespace cfen;
 
@@ -65,6 +66,12 @@ static int ew_blocks(long long n, int threads = 256) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+static int default_tail_variant() {
+  const char* v = getenv("CFEN_TAIL_VARIANT");
+  return v ? atoi(v) : 2;
+}
+static bool tail_in_tmem(int variant, int E) { return (variant == 1 && E == 96) || variant == 2; }
+
 static cudaError_t set_kernel_attributes() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<128, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -91,6 +98,7 @@ static cudaError_t set_kernel_attributes() {
   if ((e = mlp16_set_attr()) != cudaSuccess) return e;
   if ((e = attention16_set_attr()) != cudaSuccess) return e;
   if ((e = tail16_set_attr()) != cudaSuccess) return e;
+  if ((e = tail16r_set_attr()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -302,6 +310,8 @@ struct cfen_plan {
   int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
   int conv_path = 1;  // 1: fp16 ldmatrix / m16n8k16 convolutions (conv16.cuh, default); 0: TF32 first generation
   int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
+  int tail_variant = 1;  // 0: residual tile in shared memory (vit_tail16.cuh); 1: residual in TMEM for E = 96, two CTAs
+                         // per SM (vit_tail16r.cuh); 2: residual in TMEM for E = 96 and 192
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
   std::map<std::tuple<const void*, int, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> tmaps2;
   // optional per-launch CUDA-event timing (cfen_plan_set_option("timing", 1))
@@ -477,6 +487,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   }
   if (const char* fm = getenv("CFEN_FUSE_MLP")) p->fuse_mlp = atoi(fm) != 0;
   if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
+  p->tail_variant = default_tail_variant();
   if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
@@ -540,6 +551,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   }
   if (strcmp(name, "fuse_mlp") == 0) { p->fuse_mlp = value != 0; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
+  if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
   if (strcmp(name, "streams") == 0) { p->streams = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
@@ -807,9 +819,14 @@ static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
   RET(get_tmap2(r.p, v.h_2, 2, E, hid, 64, E, &t2));
   RET(get_tmap2(r.p, v.h_m0, 2, hid, E, 64, 64, &m0));
   RET(get_tmap2(r.p, v.h_m3, 2, E, hid, 64, E, &m3));
-  Tail16Args a{v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, E, hid, {}};
   Launch l(r, PC_MLP, 2.0 * M * E * E + 8.0 * M * E * hid, (double)M * E * (2 + 4 + 4) + 2.0 * (E * E + 4.0 * E * hid),
            "tail16 M%d E%d hid%d", M, E, hid);
+  if (tail_in_tmem(r.p->tail_variant, E)) {
+    Tail16RArgs ra{T, v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, hid};
+    CU(launch_tail16r(E, *to, *two, *t1, *t2, *m0, *m3, *tt, ra, r.st));
+    return 0;
+  }
+  Tail16Args a{v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, E, hid, {}};
   CU(launch_tail16(*to, *tt, *two, *t1, *t2, *m0, *m3, *tt, a, r.st));
   return 0;
 }
@@ -1289,6 +1306,11 @@ extern "C" int32_t cfen_vit_tail_f16(const void* O16, const float* T, const void
                   make_tmap_2d(&t2, W2_16, 2, E, hid, 64, E) && make_tmap_2d(&m0, M0_16, 2, hid, E, 64, 64) &&
                   make_tmap_2d(&m3, M3_16, 2, E, hid, 64, E) && make_tmap_2d(&ty, Y, 4, M, E, 32, 128);
   if (!ok) return fail(11, "cfen_vit_tail_f16: cuTensorMapEncodeTiled failed");
+  if (tail_in_tmem(default_tail_variant(), E)) {
+    Tail16RArgs ra{T, ln_g, ln_b, b1, b2, bm0, bm3, M, hid};
+    CU(launch_tail16r(E, to, two, t1, t2, m0, m3, ty, ra, static_cast<cudaStream_t>(stream)));
+    return 0;
+  }
   Tail16Args a{ln_g, ln_b, b1, b2, bm0, bm3, M, E, hid, {}};
   CU(launch_tail16(to, tt, two, t1, t2, m0, m3, ty, a, static_cast<cudaStream_t>(stream)));
   return 0;

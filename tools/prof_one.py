@@ -31,10 +31,25 @@ X, R = h16(r(M, E)), r(M, E)
 W1, W2, M0, M3, Wo = h16(r(hid, E) * 0.1), h16(r(E, hid) * 0.1), h16(r(hid, E) * 0.1), h16(r(E, hid) * 0.1), h16(r(E, E) * 0.1)
 b1, b2, g, b = torch.zeros(hid, device="cuda"), torch.zeros(E, device="cuda"), torch.ones(E, device="cuda"), torch.zeros(E, device="cuda")
 Y, Y16 = torch.empty_like(R), torch.empty(M, E, device="cuda", dtype=torch.float16)
-for _ in range(3):
+def once():
     if which == "mlp16":
         _native.check(L.cfen_mlp_f16(P(X), P(R), P(W1), P(b1), P(W2), P(b2), P(Y), P(Y16), M, E, hid, ST()))
     else:
         _native.check(L.cfen_vit_tail_f16(P(X), P(R), P(Wo), P(g), P(b), P(W1), P(b1), P(W2), P(b2), P(M0), P(b1), P(M3), P(b2),
                                           P(Y), M, E, hid, ST()))
+
+
+for _ in range(3):
+    once()
 torch.cuda.synchronize()
+if os.environ.get("CFEN_TIME", "1") != "0":
+    N = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(N):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / N
+    fl = (4.0 * M * E * hid) if which == "mlp16" else (2.0 * M * E * E + 8.0 * M * E * hid)
+    print("%s E%d hid%d M%d: %.1f us/launch  %.1f TFLOP/s" % (which, E, hid, M, us, fl / us / 1e6))

@@ -39,10 +39,10 @@ _native.check(L.cfen_debug_set_buffer(P(buf)))
 run(); torch.cuda.synchronize()
 _native.check(L.cfen_debug_set_buffer(None))
 d = buf.cpu().view(4, 1024, 2).tolist()
-names = {100: "P start", 110: "P slot acquired", 200: "M start", 201: "M x_full ok", 205: "M wait xa", 206: "M xa ok",
+names = {100: "P start", 110: "P slot acquired", 200: "M start", 201: "M x_full ok", 202: "M t_ready ok", 205: "M wait xa", 206: "M xa ok",
          210: "M g1 begin", 211: "M g1 s_empty ok", 212: "M g1 ring ok", 213: "M g1 issued", 220: "M g2 begin",
          221: "M g2 f_full ok", 222: "M g2 ring ok", 223: "M g2 issued", 300: "E0 start", 301: "E0 acc0 ok",
-         302: "E0 t_full ok", 303: "E0 resid done", 304: "E0 LN+xa done", 310: "chunk begin", 311: "chunk s_full ok",
+         302: "E0 t0 in TMEM", 303: "E0 resid done", 304: "E0 LN+xa done", 310: "chunk begin", 311: "chunk s_full ok",
          312: "chunk f_empty ok", 313: "chunk done", 320: "E0 wait acc", 321: "E0 acc ok", 322: "E0 resid done",
          323: "E0 xa done", 330: "E0 stored"}
 ev = []
