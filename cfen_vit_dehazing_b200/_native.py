@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "cfen_plan_profile_json", "cfen_plan_profile_trace",
     "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
     "cfen_plan_stage_ptr",
-    "cfen_f32_to_f16", "cfen_debug_set_buffer", "cfen_gemm_f16", "cfen_mlp_f16", "cfen_layernorm_f16", "cfen_attention_f16", "cfen_vit_tail_f16",
+    "cfen_f32_to_f16", "cfen_debug_set_buffer", "cfen_gemm_f16", "cfen_mlp_f16", "cfen_layernorm_f16", "cfen_attention_f16", "cfen_vit_tail_f16", "cfen_vit_front_f16",
     "cfen_gemm_tf32", "cfen_gemm_tc", "cfen_mlp_tc", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
     "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_cfsm", "cfen_merge_lg",
     "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward",
@@ -76,6 +76,7 @@ def lib():
         L.cfen_layernorm_f16.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
         L.cfen_attention_f16.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.cfen_vit_tail_f16.argtypes = [vp] * 14 + [i32] * 3 + [vp]
+        L.cfen_vit_front_f16.argtypes = [vp] + [i32] * 6 + [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp]
         L.cfen_conv2d_nhwc.argtypes = [cp] + [vp] * 7 + [i32] * 4 + [vp]
         L.cfen_cfsm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.cfen_merge_lg.argtypes = [vp] * 8 + [i32] * 5 + [vp]

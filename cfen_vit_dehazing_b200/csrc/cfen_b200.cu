@@ -34,6 +34,7 @@
 #include "vit_kernels.cuh"
 #include "vit_tail16.cuh"
 #include "vit_tail16r.cuh"
+#include "vit_front16.cuh"
 
 using namespace cfen;
 
@@ -99,6 +100,7 @@ static cudaError_t set_kernel_attributes() {
   if ((e = attention16_set_attr()) != cudaSuccess) return e;
   if ((e = tail16_set_attr()) != cudaSuccess) return e;
   if ((e = tail16r_set_attr()) != cudaSuccess) return e;
+  if ((e = front16_set_attr()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -310,6 +312,8 @@ struct cfen_plan {
   int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
   int conv_path = 1;  // 1: fp16 ldmatrix / m16n8k16 convolutions (conv16.cuh, default); 0: TF32 first generation
   int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
+  int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
+                       // as one kernel reading the NHWC map (vit_front16.cuh); tokenize_local is not launched
   int tail_variant = 1;  // 0: residual tile in shared memory (vit_tail16.cuh); 1: residual in TMEM for E = 96, two CTAs
                          // per SM (vit_tail16r.cuh); 2: residual in TMEM for E = 96 and 192
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> tmaps;
@@ -488,6 +492,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* fm = getenv("CFEN_FUSE_MLP")) p->fuse_mlp = atoi(fm) != 0;
   if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
   p->tail_variant = default_tail_variant();
+  if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
   if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
@@ -552,6 +557,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_mlp") == 0) { p->fuse_mlp = value != 0; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
   if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
+  if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
   if (strcmp(name, "streams") == 0) { p->streams = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
@@ -830,6 +836,21 @@ static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
   CU(launch_tail16(*to, *tt, *two, *t1, *t2, *m0, *m3, *tt, a, r.st));
   return 0;
 }
+// Window gather (or token matrix) -> t1 (fp32) and qkv16 of one local ViT call as one kernel (vit_front16.cuh)
+struct FrontSrc { const float* map; int H, W, C, win; };
+static int run_front16(Run& r, const VitW& v, const FrontSrc* src, const float* T0, float* T1, __half* QKV16, int M) {
+  const int E = v.E;
+  const CUtensorMap *twle, *twin, *tt1, *tq;
+  RET(get_tmap2(r.p, v.h_le, 2, E, E, 64, E, &twle));
+  RET(get_tmap2(r.p, v.h_in, 2, 3 * E, E, 64, 96, &twin));
+  RET(get_tmap2(r.p, T1, 4, M, E, 32, 128, &tt1));
+  RET(get_tmap2(r.p, QKV16, 2, M, 3 * E, 32, 128, &tq));
+  Front16Args a{src ? src->map : T0, src != nullptr, src ? src->H : 0, src ? src->W : 0, src ? src->C : 0,
+                src ? src->win : 0, v.b_le, v.pos, v.L, v.ln1g, v.ln1b, M};
+  Launch l(r, PC_GEMM, 8.0 * M * E * E, (double)M * E * (4 + 4 + 6) + 8.0 * E * E, "front16 M%d E%d", M, E);
+  CU(launch_front16(E, *twle, *twin, *tt1, *tq, a, r.st));
+  return 0;
+}
 static int run_ln16(Run& r, const float* x, __half* y16, const float* g, const float* b, int M, int E) {
   Launch l(r, PC_LN, 0.0, 6.0 * M * E, "ln16 M%d E%d", M, E);
   CU(launch_layernorm(x, nullptr, y16, g, b, M, E, 1e-5f, r.st));
@@ -887,12 +908,21 @@ static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, 
   CU(launch_attention(qkv, o, nseq, L, E, heads, r.st));
   return 0;
 }
-static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq) {
+static bool front_fusable(const cfen_plan* p, int E, int M) {
+  return p->gemm_path == 2 && p->fuse_front && front16_supported(E) && (M + 127) / 128 >= 96;
+}
+// `src` != nullptr: the tokens of this (local) call have NOT been materialised; the fused front kernel gathers them.
+static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* src = nullptr) {
   const int M = nseq * v.L, E = v.E, hid = v.hid;
+  if (src && !front_fusable(r.p, E, M)) return fail(20, "run_vit: map source without the fused front kernel");
   if (r.p->gemm_path == 2) {  // fp16 operands, fp32 residual stream
-    RET(run_gemm16(r, w.x16, v.h_le, w.t1, nullptr, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
-    RET(run_ln16(r, w.t1, w.h16, v.ln1g, v.ln1b, M, E));
-    RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
+    if (src) {
+      RET(run_front16(r, v, src, nullptr, w.t1, w.qkv16, M));
+    } else {
+      RET(run_gemm16(r, w.x16, v.h_le, w.t1, nullptr, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
+      RET(run_ln16(r, w.t1, w.h16, v.ln1g, v.ln1b, M, E));
+      RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
+    }
     RET(run_attn16(r, w.qkv16, w.o16, nseq, v.L, E, v.heads));
     if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= 96) return run_tail16(r, v, w.o16, w.t1, M);
     RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0));
@@ -1031,7 +1061,10 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     r.st = main_st;
     RET(rc);
   }
-  {
+  if (front_fusable(p, p->lvit[si].E, r.nb * nwin * p->lvit[si].L)) {
+    const FrontSrc src{x, Hl, Hl, C, p->win};
+    RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin, &src));
+  } else {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4, "tok_local H%d C%d", Hl, C);
@@ -1313,6 +1346,27 @@ extern "C" int32_t cfen_vit_tail_f16(const void* O16, const float* T, const void
   }
   Tail16Args a{ln_g, ln_b, b1, b2, bm0, bm3, M, E, hid, {}};
   CU(launch_tail16(to, tt, two, t1, t2, m0, m3, ty, a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int32_t cfen_vit_front_f16(const float* src, int32_t src_is_map, int32_t B, int32_t H, int32_t W, int32_t C,
+                                      int32_t win, const void* Wle16, const float* b_le, const float* pos, int32_t L,
+                                      const float* ln_g, const float* ln_b, const void* Win16, float* T1, void* QKV16,
+                                      int32_t M, int32_t E, void* stream) {
+  if (!src || !Wle16 || !b_le || !pos || !ln_g || !ln_b || !Win16 || !T1 || !QKV16)
+    return fail(1, "cfen_vit_front_f16: null argument");
+  if (!front16_supported(E) || L <= 0) return fail(1, "cfen_vit_front_f16: E must be 96 or 192 and L > 0");
+  if (src_is_map) {
+    if (C * 4 != E || win < 2 || H % win || W % win || (win / 2) * (win / 2) != L ||
+        (long long)B * (H / win) * (W / win) * L != M)
+      return fail(1, "cfen_vit_front_f16: map geometry does not match M / E / L");
+  }
+  CU(set_kernel_attributes());
+  CUtensorMap twle, twin, tt1, tq;
+  const bool ok = make_tmap_2d(&twle, Wle16, 2, E, E, 64, E) && make_tmap_2d(&twin, Win16, 2, 3 * E, E, 64, 96) &&
+                  make_tmap_2d(&tt1, T1, 4, M, E, 32, 128) && make_tmap_2d(&tq, QKV16, 2, M, 3 * E, 32, 128);
+  if (!ok) return fail(11, "cfen_vit_front_f16: cuTensorMapEncodeTiled failed");
+  Front16Args a{src, src_is_map != 0, H, W, C, win, b_le, pos, L, ln_g, ln_b, M};
+  CU(launch_front16(E, twle, twin, tt1, tq, a, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 extern "C" int32_t cfen_layernorm_f16(const float* x, void* y16, const float* gamma, const float* beta, int32_t rows,

@@ -139,6 +139,15 @@ int32_t cfen_vit_tail_f16(const void* O16, const float* T, const void* Wout16, c
                           const float* ln_b, const void* W1_16, const float* b1, const void* W2_16,
                           const float* b2, const void* M0_16, const float* bm0, const void* M3_16,
                           const float* bm3, float* Y, int32_t M, int32_t E, int32_t hid, void* stream);
+/* First half of a local ViT call as one kernel (E in {96,192}; v3.py:1140-1160, 1382-1384):
+ *   x = token rows (src_is_map: 2x2-patch tokens of win x win windows gathered from the NHWC map [B,H,W,C], C = E/4,
+ *       feature order (ky,kx,c); else the token matrix src[M,E]);
+ *   T1[M,E] = x + fp16(x) Wle16^T + b_le + pos[row % L];  QKV16[M,3E] = fp16(LayerNorm(T1)) Win16^T.
+ * M must equal B*(H/win)*(W/win)*L in map mode. */
+int32_t cfen_vit_front_f16(const float* src, int32_t src_is_map, int32_t B, int32_t H, int32_t W, int32_t C,
+                           int32_t win, const void* Wle16, const float* b_le, const float* pos, int32_t L,
+                           const float* ln_g, const float* ln_b, const void* Win16, float* T1, void* QKV16,
+                           int32_t M, int32_t E, void* stream);
 /* LayerNorm with fp16 output (the A operand of the next Linear). */
 int32_t cfen_layernorm_f16(const float* x, void* y16, const float* gamma, const float* beta, int32_t rows,
                            int32_t E, float eps, void* stream);

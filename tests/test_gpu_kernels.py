@@ -188,6 +188,38 @@ def test_vit_tail_f16(M, E, hid, inplace):
     assert U.rel_err(Y, ref) <= 5e-4             # three fp16 roundings of on-chip operands (ties may flip)
 
 
+@pytest.mark.parametrize("B,H,C,win,from_map", [(2, 64, 24, 32, True), (3, 32, 48, 16, True), (1, 64, 24, 32, False),
+                                                 (5, 32, 48, 32, True), (2, 96, 24, 32, True), (1, 32, 48, 16, False)])
+def test_vit_front_f16(B, H, C, win, from_map):
+    """window gather + linear_encoding (+x, +pos) + LayerNorm + in-projection in one kernel (residual in TMEM) vs
+    fp64 torch with the kernel's fp16 operand roundings; map mode reads the NHWC map, token mode a token matrix."""
+    L = _native.lib()
+    E, Lw = 4 * C, (win // 2) ** 2
+    x = dev(B, C, H, H, seed=1, scale=2.0)
+    tok = G.local_tokens_ref(x, win)                      # [M, E], feature order (ky,kx,c)
+    M = tok.shape[0]
+    if not from_map:
+        M -= 37                                           # ragged last tile
+        tok = tok[:M].contiguous()
+    Wle, ble = dev(E, E, seed=2, scale=E ** -0.5), dev(E, seed=3, scale=0.1)
+    pos = dev(Lw, E, seed=4)
+    g, b = 1.0 + 0.1 * dev(E, seed=5), 0.1 * dev(E, seed=6)
+    Win = dev(3 * E, E, seed=7, scale=E ** -0.5)
+    Wle16, Win16 = to_f16(Wle), to_f16(Win)
+    r16 = lambda z: z.float().half().double()
+    rows = torch.arange(M, device="cuda") % Lw
+    t1 = tok.double() + r16(tok) @ Wle16.double().t() + ble.double() + pos.double()[rows]
+    qkv = r16(F.layer_norm(t1, (E,), g.double(), b.double(), 1e-5)) @ Win16.double().t()
+    T1 = torch.full((M, E), float("nan"), device="cuda")
+    Q16 = torch.full((M, 3 * E), float("nan"), device="cuda", dtype=torch.float16)
+    src = U.to_nhwc(x) if from_map else tok
+    G.check(L.cfen_vit_front_f16(G.ptr(src), int(from_map), B, H, H, C, win, G.ptr(Wle16), G.ptr(ble), G.ptr(pos), Lw,
+                                 G.ptr(g), G.ptr(b), G.ptr(Win16), G.ptr(T1), G.ptr(Q16), M, E, G.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(T1, t1) <= 5e-5             # fp32 tensor-core accumulation over K = E
+    assert U.rel_err(Q16, qkv) <= F16OUT_TOL + 5e-4       # fp16 rounding of LN(t1) can flip at ties, fp16 output
+
+
 @pytest.mark.parametrize("rows,E", [(1001, 96), (257, 192), (64, 384), (33, 768), (16, 1536)])
 def test_layernorm_f16(rows, E):
     L = _native.lib()
