@@ -32,6 +32,7 @@ struct Front16 {
   static constexpr int STAGE = 32768;           // two fp32 panels (t1) or one 128 x 96 fp16 chunk (qkv)
   static constexpr int BAR = 256;
   static constexpr int SMEM = XA + ST * SLOT + STAGE + BAR;
+  static_assert(NP % 3 == 0, "the prologue requests three panels at a time");
   static constexpr int TMEM_COLS = E <= 128 ? 256 : 512;
   static constexpr int Q_COL0 = E <= 128 ? 0 : 256;   // E = 96: chunk slot 0 reuses the (dead) accumulator columns
   static constexpr int MIN_CTAS = E <= 128 ? 2 : 1;
@@ -175,42 +176,69 @@ vit_front16_kernel(const __grid_constant__ CUtensorMap tmWle, const __grid_const
     const int m = m0 + row;
     const bool valid = m < a.M;
     // ---- token row source: two contiguous segments of E/2 floats (ky = 0, 1)
-    const float *seg0, *seg1;
-    if (a.is_map) {
-      const int mm = valid ? m : 0;
-      const int l = mm % a.L, widx = mm / a.L;
-      const int half = a.win >> 1, nx = a.W / a.win, ny = a.H / a.win;
-      const int wx = widx % nx, wy = (widx / nx) % ny, b = widx / (nx * ny);
-      const int ty = l / half, tx = l - ty * half;
-      seg0 = a.src + (((size_t)b * a.H + wy * a.win + 2 * ty) * a.W + wx * a.win + 2 * tx) * a.C;
-      seg1 = seg0 + (size_t)a.W * a.C;
-    } else {
-      seg0 = a.src + (size_t)(valid ? m : 0) * E;
-      seg1 = seg0 + E / 2;
-    }
-    const float* posrow = a.pos + (size_t)(m % a.L) * E;
-    // ---- prologue: ACC <- x + b_le + pos ; Xa <- fp16(x)
-#pragma unroll 1
-    for (int i = 0; i < NP; ++i) {
-      uint32_t v[32], hx[16];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int f = 32 * i + 4 * j;
-        const float* p = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
-        const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 ps = __ldg(reinterpret_cast<const float4*>(posrow + f));
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.ble + f));
-        hx[2 * j] = pack_half2(t.x, t.y);
-        hx[2 * j + 1] = pack_half2(t.z, t.w);
-        v[4 * j + 0] = __float_as_uint(t.x + (ps.x + bb.x)); v[4 * j + 1] = __float_as_uint(t.y + (ps.y + bb.y));
-        v[4 * j + 2] = __float_as_uint(t.z + (ps.z + bb.z)); v[4 * j + 3] = __float_as_uint(t.w + (ps.w + bb.w));
+    auto row_segments = [&](int mm, const float*& s0, const float*& s1) {
+      if (a.is_map) {
+        const int l = mm % a.L, widx = mm / a.L;
+        const int half = a.win >> 1, nx = a.W / a.win, ny = a.H / a.win;
+        const int wx = widx % nx, wy = (widx / nx) % ny, b = widx / (nx * ny);
+        const int ty = l / half, tx = l - ty * half;
+        s0 = a.src + (((size_t)b * a.H + wy * a.win + 2 * ty) * a.W + wx * a.win + 2 * tx) * a.C;
+        s1 = s0 + (size_t)a.W * a.C;
+      } else {
+        s0 = a.src + (size_t)mm * E;
+        s1 = s0 + E / 2;
       }
-      tc::tmem_st32(lane_addr + 32 * i, v);
-      uint8_t* xline = xa + (i >> 1) * 16384 + roff;
+    };
+    const float *seg0, *seg1;
+    row_segments(valid ? m : 0, seg0, seg1);
+    const float* posrow = a.pos + (size_t)(m % a.L) * E;
+    // ---- prologue: ACC <- x + b_le + pos ; Xa <- fp16(x).  Three panels (24 x 16 B per thread) are requested before
+    // the first is consumed: with thread-per-row loads the bytes in flight are what hides the HBM latency.
+    constexpr int PB = 3;
+#pragma unroll 1
+    for (int i0 = 0; i0 < NP; i0 += PB) {
+      float4 t[PB][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(xline + ((((i & 1) * 4 + j) ^ sw) << 4)) =
-            make_uint4(hx[4 * j], hx[4 * j + 1], hx[4 * j + 2], hx[4 * j + 3]);
+      for (int ii = 0; ii < PB; ++ii)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int f = 32 * (i0 + ii) + 4 * j;
+          const float* p = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
+          t[ii][j] = valid ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      if (i0 == 0) {   // pull the same rows of the tile that runs one wave later into L2
+        const int mp = m + 128 * C::MIN_CTAS * 148;
+        if (mp < a.M) {
+          const float *p0, *p1;
+          row_segments(mp, p0, p1);
+#pragma unroll
+          for (int off = 0; off < E / 2; off += 32) { tc::prefetch_l2(p0 + off); tc::prefetch_l2(p1 + off); }
+          tc::prefetch_l2(p0 + E / 2 - 4);
+          tc::prefetch_l2(p1 + E / 2 - 4);
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < PB; ++ii) {
+        const int i = i0 + ii;
+        uint32_t v[32], hx[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int f = 32 * i + 4 * j;
+          const float4 ps = __ldg(reinterpret_cast<const float4*>(posrow + f));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.ble + f));
+          const float4 x = t[ii][j];
+          hx[2 * j] = pack_half2(x.x, x.y);
+          hx[2 * j + 1] = pack_half2(x.z, x.w);
+          v[4 * j + 0] = __float_as_uint(x.x + (ps.x + bb.x)); v[4 * j + 1] = __float_as_uint(x.y + (ps.y + bb.y));
+          v[4 * j + 2] = __float_as_uint(x.z + (ps.z + bb.z)); v[4 * j + 3] = __float_as_uint(x.w + (ps.w + bb.w));
+        }
+        tc::tmem_st32(lane_addr + 32 * i, v);
+        uint8_t* xline = xa + (i >> 1) * 16384 + roff;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(xline + ((((i & 1) * 4 + j) ^ sw) << 4)) =
+              make_uint4(hx[4 * j], hx[4 * j + 1], hx[4 * j + 2], hx[4 * j + 3]);
+      }
     }
     tc::tmem_st_wait();
     tc::tc_fence_before();

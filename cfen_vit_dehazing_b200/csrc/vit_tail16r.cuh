@@ -107,6 +107,9 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
     if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(x_full, KB * 16384);
       for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(xa + kb * 16384, &tmO, x_full, kb * 64, m0);
+      const int mp = m0 + 128 * C::MIN_CTAS * 148;   // the tile that runs one wave later: pull its O rows into L2
+      if (mp < a.M)
+        for (int kb = 0; kb < KB; ++kb) tc::tma_prefetch_2d(&tmO, kb * 64, mp);
     }
     __syncwarp();
     int slot = 0, par = 1;   // producer waits "empty" with the inverted parity: the first lap passes immediately
@@ -355,6 +358,11 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(t_ready);
+      if (m0 + row + 128 * C::MIN_CTAS * 148 < a.M) {   // ... and its residual rows
+        const float* pr = a.T + (size_t)(m0 + row + 128 * C::MIN_CTAS * 148) * E;
+#pragma unroll
+        for (int off = 0; off < E; off += 32) tc::prefetch_l2(pr + off);
+      }
       if (q == 0 && lane == 0) tl_stamp(2, tln, 302);
       // ---- epilogue 0: h = LN(t1) -> Xa
       tc::mbar_wait(&acc_full[0], 0);
