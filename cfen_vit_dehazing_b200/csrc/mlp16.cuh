@@ -22,9 +22,16 @@ namespace cfen {
 
 // Optional device-side trace (cfen_debug_set_buffer): CTA 0's MMA issuer logs clock64() around its waits.
 __device__ long long* g_dbg_buf = nullptr;
+// Only in the -DCFEN_TIMELINE build: in the product build even the disabled stamp cost a dependent global load of
+// g_dbg_buf plus a branch after EVERY tcgen05.mma of the issuer thread (r31: 8 k cycles per hidden chunk at E = 384
+// against 1.5 k cycles of tensor work).
+#ifdef CFEN_TIMELINE
 __device__ __forceinline__ void dbg_stamp(int& n, int tag) {
   if (g_dbg_buf && blockIdx.x == 0 && n < 4000) { g_dbg_buf[2 * n] = tag; g_dbg_buf[2 * n + 1] = clock64(); ++n; }
 }
+#else
+__device__ __forceinline__ void dbg_stamp(int&, int) {}
+#endif
 
 // Compile-time timeline (-DCFEN_TIMELINE, tools/timeline_tail16.py): one lane per role of CTA 0 logs
 // (tag, clock64) pairs into its own 1024-entry region of the debug buffer.  Compiled out otherwise.
