@@ -13,6 +13,7 @@
 //   * per 16x8x16 MMA the LSU issues ~1 instruction instead of ~5, and operand bytes are halved.
 // Reference geometry sources are listed in conv_igemm.cuh.
 #pragma once
+#include "tc_common.cuh"
 #include "attn16.cuh"
 #include "conv_igemm.cuh"
 
@@ -142,6 +143,41 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
 
   const int oy0 = S::TRANSPOSED ? ty0 - 1 : ty0 * S::STRIDE - S::PAD;
   const int ox0 = S::TRANSPOSED ? tx0 - 1 : tx0 * S::STRIDE - S::PAD;
+
+  // L2 prefetch for the CTA that runs one wave later (blocks are dispatched in linear order, x fastest): the
+  // loaders below are synchronous global loads and the kernels were long-scoreboard bound on their DRAM latency
+  // (profiles/r1_v4_c3_full.md); pulling the future tile's input rows (and residual rows) into L2 now turns those
+  // misses into L2 hits.  One 128-byte line per thread and item; nothing is waited on.
+  if constexpr (S::LOADER == LD_NHWC || S::LOADER == LD_SUM2 || S::LOADER == LD_CAT2) {
+    const int nblk = gridDim.x * gridDim.y * gridDim.z;
+    const int tgt = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 148 * C::MINB;
+    if (tgt < nblk) {
+      const int pbx = tgt % gridDim.x, pby = (tgt / gridDim.x) % gridDim.y, pbz = tgt / (gridDim.x * gridDim.y);
+      const int py0 = S::TRANSPOSED ? pby * C::TH - 1 : pby * C::TH * S::STRIDE - S::PAD;
+      const int px0 = max(S::TRANSPOSED ? pbx * C::TW - 1 : pbx * C::TW * S::STRIDE - S::PAD, 0);
+      constexpr int CSRC = S::LOADER == LD_CAT2 ? S::CIN / 2 : S::CIN;       // channels per source map
+      constexpr int LPR = (C::IN_W * CSRC * 4 + 127) / 128 + 1;             // lines per tile row (any alignment)
+      constexpr int NSRC = S::LOADER == LD_NHWC ? 1 : 2;
+      for (int i = tid; i < NSRC * C::IN_H * LPR; i += S::THREADS) {
+        const int ln = i % LPR, r = (i / LPR) % C::IN_H, which = i / (LPR * C::IN_H);
+        const int gy = py0 + r;
+        if ((unsigned)gy < (unsigned)Hin) {
+          const float* base = (which ? a.in1 : a.in0) + (((size_t)pbz * Hin + gy) * Win + px0) * CSRC;
+          const int len = min(C::IN_W, Win - px0) * CSRC;                   // floats of this row inside the image
+          tc::prefetch_l2(base + min(ln * 32, len - 1));
+        }
+      }
+      if (a.res && (a.flags & CF_RES)) {
+        constexpr int OTH = S::TRANSPOSED ? 2 * C::TH : C::TH, OTW = S::TRANSPOSED ? 2 * C::TW : C::TW;
+        constexpr int LPO = (OTW * S::COUT * 4 + 127) / 128 + 1;
+        for (int i = tid; i < OTH * LPO; i += S::THREADS) {
+          const int ln = i % LPO, r = i / LPO;
+          const float* base = a.res + (((size_t)pbz * Hout + pby * OTH + r) * Wout + pbx * OTW) * S::COUT;
+          tc::prefetch_l2(base + min(ln * 32, OTW * S::COUT - 1));
+        }
+      }
+    }
+  }
 
   if constexpr (S::LOADER == LD_LG) {
     // ------------------------------------------------------------------ local / global merge (1x1, no halo)

@@ -423,13 +423,17 @@ class dec_ipt(nn.Module):
                 plan.forward(b, x.data_ptr(), xr.data_ptr(), xs.data_ptr(), xd.data_ptr(), stream)
         return [xr, xs, xd]
 
-    def forward_host(self, input, out=None, device=None):
+    def forward_host(self, input, out=None, device=None, defer_sync=False):
         """Host-to-host forward for batches that start and end in (pinned) host memory - what
         DECHLGVIT.set_input (.to(device), model_iid_dehazing.py:126-136) + forward + tensor2im's .cpu()
         (util/util.py:12-24) do around the generator, restated as a three-stream pipeline: the H2D copy
         of pass i+1 and the D2H copy of pass i-1 overlap the kernels of pass i (one pass = the plan's
         images-per-pass chunk).  Returns [xr, xs, xd] as host tensors (`out` if given); they are
-        complete when the current stream of `device` has been synchronised.  No CPU compute path."""
+        complete when the current stream of `device` has been synchronised.  No CPU compute path.
+
+        defer_sync=True leaves the current stream independent of the trailing D2H copies, so the next
+        forward_host call's copies and kernels overlap them (streaming a sequence of batches); the
+        outputs of deferred calls are complete after host_sync()."""
         if not isinstance(input, torch.Tensor) or input.dim() != 4 or input.size(1) != 3:
             raise RuntimeError("dec_ipt.forward_host expects a [B, 3, H, W] tensor")
         if input.is_cuda:
@@ -454,39 +458,54 @@ class dec_ipt(nn.Module):
             if st is None:
                 st = {"in": [torch.empty((nb, 3, h, w), device=dev) for _ in range(2)],
                       "out": [[torch.empty((nb, c, h, w), device=dev) for c in (3, 1, 3)] for _ in range(2)],
-                      "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev)}
+                      "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                      # per device slot: the kernels that last read "in" / the D2H that last drained "out"; kept
+                      # across calls so that deferred calls chain without a stream-wide join
+                      "ev_comp": [None, None], "ev_out": [None, None], "next": 0, "dev": dev}
                 self._host_pipe = {key: st}
             cur = torch.cuda.current_stream(dev)
             s_in, s_out = st["s_in"], st["s_out"]
-            s_in.wait_stream(cur)
-            s_out.wait_stream(cur)
-            ev_comp, ev_out = {}, {}
+            ev_entry = torch.cuda.Event()
+            ev_entry.record(cur)                                 # the caller's earlier work on this stream
+            s_in.wait_event(ev_entry)
             n_pass = (b + nb - 1) // nb
             for i in range(n_pass):
-                slot, lo = i & 1, i * nb
+                slot, lo = st["next"], i * nb
+                st["next"] ^= 1
                 n = min(nb, b - lo)
                 with torch.cuda.stream(s_in):
-                    if i >= 2:
-                        s_in.wait_event(ev_comp[i - 2])          # the kernels of pass i-2 have consumed this slot
+                    if st["ev_comp"][slot] is not None:
+                        s_in.wait_event(st["ev_comp"][slot])     # the kernels that last read this slot are done
                     st["in"][slot][:n].copy_(input[lo:lo + n], non_blocking=True)
                     ev_in = torch.cuda.Event()
                     ev_in.record(s_in)
                 cur.wait_event(ev_in)
-                if i >= 2:
-                    cur.wait_event(ev_out[i - 2])                # the D2H of pass i-2 has drained this slot
+                if st["ev_out"][slot] is not None:
+                    cur.wait_event(st["ev_out"][slot])           # the D2H that last drained this slot is done
                 o = st["out"][slot]
                 plan.forward(n, st["in"][slot].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
                              cur.cuda_stream)
-                ev_comp[i] = torch.cuda.Event()
-                ev_comp[i].record(cur)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                st["ev_comp"][slot] = ev
                 with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_comp[i])
+                    s_out.wait_event(ev)
                     for dst, src in zip(out, o):
                         dst[lo:lo + n].copy_(src[:n], non_blocking=True)
-                    ev_out[i] = torch.cuda.Event()
-                    ev_out[i].record(s_out)
-            cur.wait_stream(s_out)
+                    ev2 = torch.cuda.Event()
+                    ev2.record(s_out)
+                    st["ev_out"][slot] = ev2
+            if not defer_sync:
+                cur.wait_stream(s_out)
         return out
+
+    def host_sync(self):
+        """Completes every forward_host(..., defer_sync=True) issued so far: the current stream of each pipeline's
+        device waits for the D2H copies, then the host waits for that stream."""
+        for st in getattr(self, "_host_pipe", {}).values():
+            cur = torch.cuda.current_stream(st["dev"])
+            cur.wait_stream(st["s_out"])
+            cur.synchronize()
 
 
 def _mark_dirty(module, _incompatible):

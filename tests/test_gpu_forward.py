@@ -175,3 +175,20 @@ def test_forward_host_pipeline_matches_forward(monkeypatch):
         assert a.device.type == "cpu" and torch.equal(a, b)
     with pytest.raises(RuntimeError):
         gnet.forward_host(x.cuda())
+
+
+def test_forward_host_streaming_defer_sync(monkeypatch):
+    """Three forward_host(defer_sync=True) calls on different batches chained without a stream join, then one
+    host_sync(): every output equals forward() bit for bit (device slots and their events persist across calls)."""
+    monkeypatch.setenv("CFEN_CHUNK_IMAGES", "4")
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    xs = [orc.make_inputs(128, [1, n])[1] for n in (6, 4, 9)]
+    xs[1] = xs[1] * 0.5
+    xs[2] = -xs[2]
+    with torch.no_grad():
+        refs = [[o.cpu() for o in gnet(x.cuda())] for x in xs]
+        outs = [gnet.forward_host(x.pin_memory(), defer_sync=True) for x in xs]
+        gnet.host_sync()
+    for out, ref in zip(outs, refs):
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b)
