@@ -312,6 +312,9 @@ struct cfen_plan {
   int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
   int conv_path = 1;  // 1: fp16 ldmatrix / m16n8k16 convolutions (conv16.cuh, default); 0: TF32 first generation
   int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
+  int fuse_min_tiles = 96;   // fused token kernels parallelise over 128-row tiles only: below this many tiles the unfused
+                             // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
+  int maps16 = 1;      // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
   int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
                        // as one kernel reading the NHWC map (vit_front16.cuh); tokenize_local is not launched
   int tail_variant = 1;  // 0: residual tile in shared memory (vit_tail16.cuh); 1: residual in TMEM for E = 96, two CTAs
@@ -493,6 +496,8 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
   p->tail_variant = default_tail_variant();
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
+  if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm) != 0;
+  if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
@@ -558,6 +563,8 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
   if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
+  if (strcmp(name, "maps16") == 0) { p->maps16 = value != 0; return 0; }
+  if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
   if (strcmp(name, "streams") == 0) { p->streams = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
@@ -909,7 +916,7 @@ static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, 
   return 0;
 }
 static bool front_fusable(const cfen_plan* p, int E, int M) {
-  return p->gemm_path == 2 && p->fuse_front && front16_supported(E) && (M + 127) / 128 >= 96;
+  return p->gemm_path == 2 && p->fuse_front && front16_supported(E) && (M + 127) / 128 >= p->fuse_min_tiles;
 }
 // `src` != nullptr: the tokens of this (local) call have NOT been materialised; the fused front kernel gathers them.
 static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* src = nullptr) {
@@ -924,11 +931,11 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
       RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
     }
     RET(run_attn16(r, w.qkv16, w.o16, nseq, v.L, E, v.heads));
-    if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= 96) return run_tail16(r, v, w.o16, w.t1, M);
+    if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= r.p->fuse_min_tiles) return run_tail16(r, v, w.o16, w.t1, M);
     RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0));
     RET(run_ln16(r, w.t1, w.h16, v.ln2g, v.ln2b, M, E));
     const int bm = 128 * mlp16_shape(E).MH;
-    if (r.p->fuse_mlp && mlp16_supported(E, hid) && (M + bm - 1) / bm >= 64) {
+    if (r.p->fuse_mlp && mlp16_supported(E, hid) && (M + bm - 1) / bm >= r.p->fuse_min_tiles * 2 / 3) {
       RET(run_mlp16(r, w.h16, v.h_1, v.b1, v.h_2, v.b2, w.t1, w.t1, w.x16, M, E, hid));
       RET(run_mlp16(r, w.x16, v.h_m0, v.bm0, v.h_m3, v.bm3, w.t1, w.t1, nullptr, M, E, hid));
       return 0;
@@ -975,13 +982,15 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   const double kelems = (double)conv_wpack_k(c.kind);           // contraction length per output pixel
   const double opix = (double)r.nb * H * W * (is_up ? 4 : 1);
   const double cflops = 2.0 * opix * kelems * cout_;
-  const double cbytes = 4.0 * (opix * cout_ * ((flags & CF_RES) ? 2 : 1) + (double)r.nb * H * W * conv_cin_bytes(c.kind));
+  const double out_b = (flags & CF_OUT16) ? 2.0 : 4.0, in_b = (flags & CF_IN16) ? 2.0 : 4.0;
+  const double res_b = (flags & CF_RES) ? ((flags & CF_RES16) ? 2.0 : 4.0) : 0.0;
+  const double cbytes = opix * cout_ * (out_b + res_b) + in_b * (double)r.nb * H * W * conv_cin_bytes(c.kind);
   const int pcls = is_lg ? PC_MERGE : PC_CONV;
   if (p->calibrating && !c.ankey.empty()) {
     // pass 1: conv + bias only, per-CTA statistics (models/actnorm.py:25-37)
     const int cout = conv_cout(c.kind);
     const int parts = p->conv_path ? conv16_parts(c.kind, H, W) : conv_parts(c.kind, H, W);
-    a.scale = p->ones; a.shift = c.bias_src; a.flags = 0; a.stats = r.ln->partials;
+    a.scale = p->ones; a.shift = c.bias_src; a.flags = flags & CF_FMT_MASK; a.stats = r.ln->partials;
     {
       Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str());
       CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
@@ -1000,9 +1009,9 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
 
 // conv + InstanceNorm2d + ReLU (v3.py:292-298, 301): conv emits partial stats, then normalise in place
 static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, float* out, int H, int W,
-                            int Hout, int Wout, int C) {
+                            int Hout, int Wout, int C, int fmt_flags = 0) {
   cfen_plan* p = r.p;
-  RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, 0, r.ln->partials));
+  RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, fmt_flags, r.ln->partials));
   const int parts = p->conv_path ? conv16_parts(p->conv[name].kind, H, W) : conv_parts(p->conv[name].kind, H, W);
   {
     Launch l(r, PC_NORM, 0.0, 8.0 * r.nb * parts * C);
@@ -1092,15 +1101,18 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
   p->lane[2].st = multi ? p->side[3] : st;
   p->lane[2].gst = multi ? p->side[4] : st;
   p->sync_used = 0;
+  // fp16 storage of the full-resolution 12-channel maps (conv16 generation only): f0 / f1 / f2 and the lanes' scratch
+  const bool m16 = p->conv_path && p->maps16;
+  const int I16 = m16 ? CF_IN16 : 0, O16 = m16 ? CF_OUT16 : 0, R16 = m16 ? CF_RES16 : 0;
   Run r0{p, st, nb, &p->lane[0]};
   {
     Run& r = r0;
     float *f0 = r.ln->f0, *f1 = r.ln->f1, *f2 = S("f2");
     // head: conv5x5 + ResBlock (v3.py:395)
-    RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, 0));
-    RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H, H, CF_RELU));
-    RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, f2, H, H, CF_RES));
-    RET(run_conv_in_relu(r, "ds_conv_e01", f2, S("xf"), H1, H1, H1, H1, 24));
+    RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, O16));
+    RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H, H, CF_RELU | I16 | O16));
+    RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, f2, H, H, CF_RES | I16 | O16 | R16));
+    RET(run_conv_in_relu(r, "ds_conv_e01", f2, S("xf"), H1, H1, H1, H1, 24, I16));
     // shared encoder (v3.py:403-539)
     RET(run_block(r, 0, S("xf"), S("e1")));
     RET(run_conv_in_relu(r, "ds_conv_e02", S("e1"), S("e1d"), H2, H2, H2, H2, 48));
@@ -1148,9 +1160,9 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
     RET(run_block(r, 3 + bi * 3 + 2, S("d1in" + b), S("d1" + b)));
     // us_conv_d01(block_out + xf) (v3.py:696,852,1008), then the tail (v3.py:348-383)
     float *f0 = r.ln->f0, *f1 = r.ln->f1;
-    RET(run_conv(r, "us_conv_d01" + b, S("d1" + b), S("xf"), nullptr, f0, H1, H1, CF_RELU));
-    RET(run_conv(r, std::string(tails[bi]) + ".c1", f0, nullptr, nullptr, f1, H, H, CF_RELU));
-    RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H, H, CF_TANH | CF_OUT_NCHW));
+    RET(run_conv(r, "us_conv_d01" + b, S("d1" + b), S("xf"), nullptr, f0, H1, H1, CF_RELU | O16));
+    RET(run_conv(r, std::string(tails[bi]) + ".c1", f0, nullptr, nullptr, f1, H, H, CF_RELU | I16 | O16));
+    RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H, H, CF_TANH | CF_OUT_NCHW | I16));
   }
   for (int bi = 1; bi < 3; ++bi) RET(stream_edge(p, rr[bi].st, st));   // join
   return 0;
@@ -1466,7 +1478,10 @@ extern "C" int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const flo
   if (k < 0 || k == K_LG1 || k == K_LG2 || k == K_LG3) return fail(1, "cfen_conv2d_nhwc: unknown kind '%s'", kind);
   // public flag bits: 0 relu, 1 tanh, 2 residual(extra), 3 out NCHW ; bit5: extra is a second input
   const bool extra_is_input = (flags & 32) != 0;
-  const int f = flags & (CF_RELU | CF_TANH | CF_RES | CF_OUT_NCHW);
+  // bits 8 / 9 / 10: `in` / `out` / the residual `extra` are fp16 NHWC maps (conv16 generation, plain NHWC loader)
+  const int f = (flags & (CF_RELU | CF_TANH | CF_RES | CF_OUT_NCHW)) | ((flags & 256) ? CF_IN16 : 0) |
+                ((flags & 512) ? CF_OUT16 : 0) | ((flags & 1024) ? CF_RES16 : 0);
+  if ((f & CF_FMT_MASK) && ((f & CF_OUT_NCHW) && (f & CF_OUT16))) return fail(1, "cfen_conv2d_nhwc: fp16 output is NHWC only");
   return conv_oneoff(k, in, extra_is_input ? extra : nullptr, (f & CF_RES) ? extra : nullptr, weight, bias,
                      an_weight, an_bias, out, B, H, W, f, 0, static_cast<cudaStream_t>(stream));
 }

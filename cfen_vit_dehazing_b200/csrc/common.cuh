@@ -41,6 +41,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(sz));
 }
+// 8-byte async copy (.ca: 16 bytes is the only size .cg takes); zero-fill when !pred.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, bool pred) {
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(sz));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -144,41 +144,6 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
   const int oy0 = S::TRANSPOSED ? ty0 - 1 : ty0 * S::STRIDE - S::PAD;
   const int ox0 = S::TRANSPOSED ? tx0 - 1 : tx0 * S::STRIDE - S::PAD;
 
-  // L2 prefetch for the CTA that runs one wave later (blocks are dispatched in linear order, x fastest): the
-  // loaders below are synchronous global loads and the kernels were long-scoreboard bound on their DRAM latency
-  // (profiles/r1_v4_c3_full.md); pulling the future tile's input rows (and residual rows) into L2 now turns those
-  // misses into L2 hits.  One 128-byte line per thread and item; nothing is waited on.
-  if constexpr (S::LOADER == LD_NHWC || S::LOADER == LD_SUM2 || S::LOADER == LD_CAT2) {
-    const int nblk = gridDim.x * gridDim.y * gridDim.z;
-    const int tgt = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + 148 * C::MINB;
-    if (tgt < nblk) {
-      const int pbx = tgt % gridDim.x, pby = (tgt / gridDim.x) % gridDim.y, pbz = tgt / (gridDim.x * gridDim.y);
-      const int py0 = S::TRANSPOSED ? pby * C::TH - 1 : pby * C::TH * S::STRIDE - S::PAD;
-      const int px0 = max(S::TRANSPOSED ? pbx * C::TW - 1 : pbx * C::TW * S::STRIDE - S::PAD, 0);
-      constexpr int CSRC = S::LOADER == LD_CAT2 ? S::CIN / 2 : S::CIN;       // channels per source map
-      constexpr int LPR = (C::IN_W * CSRC * 4 + 127) / 128 + 1;             // lines per tile row (any alignment)
-      constexpr int NSRC = S::LOADER == LD_NHWC ? 1 : 2;
-      for (int i = tid; i < NSRC * C::IN_H * LPR; i += S::THREADS) {
-        const int ln = i % LPR, r = (i / LPR) % C::IN_H, which = i / (LPR * C::IN_H);
-        const int gy = py0 + r;
-        if ((unsigned)gy < (unsigned)Hin) {
-          const float* base = (which ? a.in1 : a.in0) + (((size_t)pbz * Hin + gy) * Win + px0) * CSRC;
-          const int len = min(C::IN_W, Win - px0) * CSRC;                   // floats of this row inside the image
-          tc::prefetch_l2(base + min(ln * 32, len - 1));
-        }
-      }
-      if (a.res && (a.flags & CF_RES)) {
-        constexpr int OTH = S::TRANSPOSED ? 2 * C::TH : C::TH, OTW = S::TRANSPOSED ? 2 * C::TW : C::TW;
-        constexpr int LPO = (OTW * S::COUT * 4 + 127) / 128 + 1;
-        for (int i = tid; i < OTH * LPO; i += S::THREADS) {
-          const int ln = i % LPO, r = i / LPO;
-          const float* base = a.res + (((size_t)pbz * Hout + pby * OTH + r) * Wout + pbx * OTW) * S::COUT;
-          tc::prefetch_l2(base + min(ln * 32, OTW * S::COUT - 1));
-        }
-      }
-    }
-  }
-
   if constexpr (S::LOADER == LD_LG) {
     // ------------------------------------------------------------------ local / global merge (1x1, no halo)
     // channels [0,CC) = local ViT tokens, [CC,2CC) = bilinear x4 of the global ViT tokens
@@ -312,9 +277,34 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
       }
       return v;
     };
+    bool async_in = false;
+    if constexpr (S::LOADER == LD_NHWC) async_in = (a.flags & CF_IN16) != 0;
+    if (async_in) {
+      // fp16 map: the halo tile is copied global -> shared asynchronously (cp.async, zero-fill outside the image),
+      // no registers and no conversion; the copy group is waited for together with the first weight chunk
+      constexpr int CH = S::CIN % 8 == 0 ? 8 : 4;          // halves per copy
+      constexpr int CPP = S::CIN / CH, TOT16 = C::IN_H * C::IN_W * CPP;
+      const __half* in16 = reinterpret_cast<const __half*>(a.in0) + img * S::CIN;
+      for (int i = tid; i < TOT16; i += S::THREADS) {
+        const int cc = i % CPP, pix = i / CPP;
+        const int iy = pix / C::IN_W, ix = pix - iy * C::IN_W;
+        int gy = oy0 + iy, gx = ox0 + ix;
+        bool inside = true;
+        if (S::REFLECT) {
+          gy = gy < 0 ? -gy : (gy >= Hin ? 2 * (Hin - 1) - gy : gy);
+          gx = gx < 0 ? -gx : (gx >= Win ? 2 * (Win - 1) - gx : gx);
+        } else {
+          inside = (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win;
+        }
+        const __half* src = in16 + (inside ? (uint32_t)(gy * Win + gx) * S::CIN + cc * CH : 0u);
+        if (CH == 8) cp_async16(tile + pix * C::CPITCH + cc * CH, src, inside);
+        else cp_async8(tile + pix * C::CPITCH + cc * CH, src, inside);
+      }
+      cp_async_commit();
+    }
     // batches of U independent items per thread: all global loads of a batch are issued before the first
     // conversion / shared-memory store, so each thread keeps U requests in flight
-    for (int i0 = tid; i0 < TOTAL; i0 += S::THREADS * U) {
+    for (int i0 = async_in ? TOTAL : tid; i0 < TOTAL; i0 += S::THREADS * U) {
       float4 v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -497,8 +487,14 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
             const float2 rb = *reinterpret_cast<const float2*>(a.res + ib);
             v[0] += ra.x; v[1] += ra.y; v[2] += rb.x; v[3] += rb.y;
           }
-          *reinterpret_cast<float2*>(a.out + ia) = make_float2(v[0], v[1]);
-          *reinterpret_cast<float2*>(a.out + ib) = make_float2(v[2], v[3]);
+          if (flags & CF_OUT16) {
+            __half* o16 = reinterpret_cast<__half*>(a.out);
+            *reinterpret_cast<uint32_t*>(o16 + ia) = pack_half2(v[0], v[1]);
+            *reinterpret_cast<uint32_t*>(o16 + ib) = pack_half2(v[2], v[3]);
+          } else {
+            *reinterpret_cast<float2*>(a.out + ia) = make_float2(v[0], v[1]);
+            *reinterpret_cast<float2*>(a.out + ib) = make_float2(v[2], v[3]);
+          }
         }
       }
       if (want_stats) {
@@ -543,6 +539,39 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
           const int y = rowc % C::TH, c = rowc / C::TH;
           const float4 v = *reinterpret_cast<const float4*>(ost + i * 4);
           *reinterpret_cast<float4*>(obase + (size_t)c * plane + (uint32_t)(y * Wout + x4 * 4)) = v;
+        }
+      } else if (flags & CF_OUT16) {
+        // fp16 map out: 16-byte pieces = 8 channels-values; the residual is an fp16 (CF_RES16) or fp32 map
+        constexpr int RW8 = C::TW * S::COUT / 8, TOTAL8 = C::TH * RW8;
+        static_assert((C::TW * S::COUT) % 8 == 0, "fp16 copy-out moves 8 values per store");
+        const size_t obase = (((size_t)b * Hout + ty0) * Wout + tx0) * S::COUT;
+        const uint32_t rowpitch = (uint32_t)Wout * S::COUT;
+        const bool has_res = (flags & CF_RES) != 0, res16 = (flags & CF_RES16) != 0;
+        __half* o16 = reinterpret_cast<__half*>(a.out);
+        const __half* r16 = reinterpret_cast<const __half*>(a.res);
+        for (int i = tid; i < TOTAL8; i += S::THREADS) {
+          const int y = i / RW8, x8 = i - y * RW8;
+          const uint32_t off = y * rowpitch + x8 * 8;
+          float4 v0 = *reinterpret_cast<const float4*>(ost + i * 8);
+          float4 v1 = *reinterpret_cast<const float4*>(ost + i * 8 + 4);
+          if (has_res) {
+            if (res16) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(r16 + obase + off);
+              const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+              const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+              const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
+              const float2 p3 = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
+              v0.x += p0.x; v0.y += p0.y; v0.z += p1.x; v0.w += p1.y;
+              v1.x += p2.x; v1.y += p2.y; v1.z += p3.x; v1.w += p3.y;
+            } else {
+              const float4 q0 = *reinterpret_cast<const float4*>(a.res + obase + off);
+              const float4 q1 = *reinterpret_cast<const float4*>(a.res + obase + off + 4);
+              v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w;
+              v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w;
+            }
+          }
+          *reinterpret_cast<uint4*>(o16 + obase + off) =
+              make_uint4(pack_half2(v0.x, v0.y), pack_half2(v0.z, v0.w), pack_half2(v1.x, v1.y), pack_half2(v1.z, v1.w));
         }
       } else {
         constexpr int RW4 = C::TW * S::COUT / 4, TOTAL4 = C::TH * RW4;

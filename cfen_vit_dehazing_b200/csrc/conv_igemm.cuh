@@ -19,7 +19,11 @@
 namespace cfen {
 
 enum ConvLoader { LD_NHWC = 0, LD_NCHW3 = 1, LD_SUM2 = 2, LD_CAT2 = 3, LD_LG = 4 };
-enum ConvFlags { CF_RELU = 1, CF_TANH = 2, CF_RES = 4, CF_OUT_NCHW = 8 };
+enum ConvFlags {
+  CF_RELU = 1, CF_TANH = 2, CF_RES = 4, CF_OUT_NCHW = 8,
+  // fp16 map storage (conv16 generation only): in0 / out / res are __half NHWC maps
+  CF_IN16 = 16, CF_OUT16 = 32, CF_RES16 = 64, CF_FMT_MASK = 16 | 32 | 64
+};
 
 struct ConvArgs {
   const float* in0;    // primary input (layout per loader)

@@ -179,7 +179,9 @@ int32_t cfen_tokenize_global(const float* map_nhwc, float* tokens, void* tokens_
  * weight/bias in the reference layout (Conv2d [Cout,Cin,kh,kw]; ConvTranspose2d [Cin,Cout,4,4]);
  * scale/shift: optional per-channel affine applied to conv+bias (ActNorm), flags: bit0 relu,
  * bit1 tanh, bit2 add `extra` after activation (residual), bit3 output NCHW, bit4 input NCHW,
- * bit5 `extra` is a second input summed (SUM2) / concatenated (skip) before the conv. */
+ * bit5 `extra` is a second input summed (SUM2) / concatenated (skip) before the conv;
+ * bit8 `in` is an fp16 NHWC map (single-input NHWC kinds), bit9 `out` is an fp16 NHWC map, bit10 the residual
+ * `extra` is an fp16 NHWC map (the storage format of the full-resolution 12-channel maps inside cfen_forward). */
 int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const float* extra, const float* weight,
                          const float* bias, const float* an_weight, const float* an_bias,
                          float* out, int32_t B, int32_t H, int32_t W, int32_t flags, void* stream);

@@ -362,6 +362,56 @@ def test_conv_transposed(kind, cin, cout):
     assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
 
 
+IN16, OUT16, RES16 = 256, 512, 1024
+
+
+@pytest.mark.parametrize("fmt", [IN16, OUT16, IN16 | OUT16, IN16 | OUT16 | RES16, OUT16 | RES16])
+def test_conv3x3_fp16_maps(fmt):
+    """fp16 NHWC map storage around the 3x3 conv (cp.async halo loader, fp16 copy-out, fp16 / fp32 residual):
+    equals the fp64 conv of the fp16-rounded input up to the output's own fp16 rounding."""
+    B, H = 2, 64
+    x, w, b = dev(B, 12, H, H, seed=1), dev(12, 12, 3, 3, seed=2, scale=0.1), dev(12, seed=3)
+    res = dev(B, 12, H, H, seed=4)
+    xin = U.to_nhwc(x).half() if fmt & IN16 else U.to_nhwc(x)
+    rin = U.to_nhwc(res).half() if fmt & RES16 else U.to_nhwc(res)
+    out = torch.empty(B, H, H, 12, device="cuda", dtype=torch.float16 if fmt & OUT16 else torch.float32)
+    _conv("conv3x3_12_12", xin, rin, w, b, None, None, out, B, H, H, RELU | RES | fmt)
+    xr = U.to_nchw(xin.float()).double()
+    ref = torch.relu(F.conv2d(xr, w.double(), b.double(), padding=1)) + U.to_nchw(rin.float()).double()
+    assert U.rel_err(U.to_nchw(out.float()), ref) <= TF32_TOL
+
+
+def test_conv_fp16_map_chain_up_tail():
+    """The full-resolution decoder tail as cfen_forward stores it: up_24_12 -> fp16 map -> 3x3 -> fp16 map -> reflect
+    7x7 + tanh -> fp32 NCHW; ds_12_24 reading an fp16 map."""
+    B, Hi = 2, 16
+    x, x2 = dev(B, 24, Hi, Hi, seed=1), dev(B, 24, Hi, Hi, seed=2)
+    wu, bu = dev(24, 12, 4, 4, seed=3, scale=0.1), dev(12, seed=4)
+    w1, b1 = dev(12, 12, 3, 3, seed=5, scale=0.1), dev(12, seed=6)
+    w2, b2 = dev(3, 12, 7, 7, seed=7, scale=0.05), dev(3, seed=8, scale=0.1)
+    wd, bd = dev(24, 12, 3, 3, seed=9, scale=0.1), dev(24, seed=10)
+    H = 2 * Hi
+    u16 = torch.empty(B, H, H, 12, device="cuda", dtype=torch.float16)
+    c16 = torch.empty(B, H, H, 12, device="cuda", dtype=torch.float16)
+    y = torch.empty(B, 3, H, H, device="cuda")
+    d = torch.empty(B, H // 2, H // 2, 24, device="cuda")
+    _conv("up_24_12", U.to_nhwc(x), U.to_nhwc(x2), wu, bu, None, None, u16, B, Hi, Hi, RELU | EXTRA_IN | OUT16)
+    _conv("conv3x3_12_12", u16, None, w1, b1, None, None, c16, B, H, H, RELU | IN16 | OUT16)
+    _conv("tail7x7_3", c16, None, w2, b2, None, None, y, B, H, H, TANH | ONCHW | IN16)
+    _conv("ds_12_24", c16, None, wd, bd, None, None, d, B, H // 2, H // 2, IN16)
+    r16 = lambda z: z.float().half().double()
+    ru = r16(torch.relu(F.conv_transpose2d((x + x2).double(), wu.double(), bu.double(), stride=2, padding=1)))
+    assert U.rel_err(U.to_nchw(u16.float()), ru) <= TF32_TOL
+    ru_got = U.to_nchw(u16.float()).double()
+    rc = torch.relu(F.conv2d(ru_got, w1.double(), b1.double(), padding=1))
+    assert U.rel_err(U.to_nchw(c16.float()), rc) <= TF32_TOL
+    rc_got = U.to_nchw(c16.float()).double()
+    ry = torch.tanh(F.conv2d(F.pad(rc_got, (3, 3, 3, 3), mode="reflect"), w2.double(), b2.double()))
+    assert (y.double() - ry).abs().max().item() <= TF32_TOL
+    rd = F.conv2d(rc_got, wd.double(), bd.double(), stride=2, padding=1)
+    assert U.rel_err(U.to_nchw(d), rd) <= TF32_TOL
+
+
 @pytest.mark.parametrize("kind,c", [("skip_96_48", 48), ("skip_48_24", 24)])
 def test_conv_skip_concat(kind, c):
     B, H = 2, 32
