@@ -188,6 +188,34 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def kernels_from_trace(path):
+    """Per-launch CSV (class, tag, us, gflop, mbytes) -> {kernel-at-shape: totals}.  The three decoder branches run
+    the same kernels at the same shapes under different layer names: those are one kernel here."""
+    import csv
+    import re
+    out = {}
+    for r in csv.DictReader(open(path)):
+        tag = re.sub(r"(tail_|_d0\d)[RSDrsd]\b", r"\1*", r["tag"]) or r["class"]
+        k = out.setdefault(tag, {"class": r["class"], "us": 0.0, "gflop": 0.0, "mbytes": 0.0, "launches": 0})
+        k["us"] += float(r["us"]); k["gflop"] += float(r["gflop"]); k["mbytes"] += float(r["mbytes"]); k["launches"] += 1
+    return out
+
+
+def ncu_traffic(table, name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `name`, from one ncu --set full capture of the same
+    kernel (bytes per row / pixel recorded in profiles/ncu_traffic.json) scaled to this launch's row count."""
+    import re
+    for key, ent in table.items():
+        if name.startswith(key.split(" ")[0]) and all(tok in name for tok in key.split(" ")[1:]):
+            m = re.search(r"\bM(\d+)", name)
+            px = re.search(r"(\d+)x(\d+)$", name)
+            units = int(m.group(1)) if m else (int(px.group(1)) * int(px.group(2)) * ent.get("images", 1) if px else None)
+            if units is None:
+                return None
+            return ent["bytes_per_unit"] * units
+    return None
+
+
 def workload_name(args):
     return ("v3 generator (iid_hlgvit_crs_gd4_cfs_v3) n_feats=24 hidden_dim_ratio=%d, %dx%d, per-GPU batch %d "
             "(BASELINE configs[3]: image-sharded, replicated weights)" % (args.hr, args.size, args.size, args.batch))
@@ -253,8 +281,12 @@ def run_ours(args):
         barrier()
         ms_instrumented = p0.elapsed_time(p1)
         prof = plan.profile()
-        if os.environ.get("CFEN_BENCH_TRACE") and rank == 0:
-            plan.profile_trace(os.environ["CFEN_BENCH_TRACE"])
+        kernels = {}
+        if rank == 0:
+            import tempfile
+            trace_path = os.environ.get("CFEN_BENCH_TRACE") or os.path.join(tempfile.gettempdir(), "cfen_trace_%d.csv" % os.getpid())
+            plan.profile_trace(trace_path)
+            kernels = kernels_from_trace(trace_path)
         plan.set_option("timing", 0)
         chunks = (B + plan.max_batch - 1) // plan.max_batch
         launches_per_step = plan.launches_per_forward * chunks
@@ -322,25 +354,27 @@ def run_ours(args):
         peaks = measured_peaks()
         images = B * world * args.steps
         value = images / (ms_total / 1e3)
-        # dominant kernel class -> roofline
-        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
-        name, d = dom
+        # dominant kernel (one kernel at one shape, summed over its launches of the timed region) -> roofline
+        name, d = max(kernels.items(), key=lambda kv: kv[1]["us"])
         nl = max(1, d["launches"])
-        t_s = d["ms"] / 1e3
-        tf = d["flops"] / t_s / 1e12 if t_s > 0 else 0.0
-        gbs = d["bytes"] / t_s / 1e9 if t_s > 0 else 0.0
-        tensor_bound = d["flops"] / (peaks["tf_sustained"] * 1e12) >= d["bytes"] / (peaks["hbm_gbs"] * 1e9)
+        t_s = d["us"] / 1e6
+        tf = d["gflop"] * 1e9 / t_s / 1e12 if t_s > 0 else 0.0
+        gbs = d["mbytes"] * 1e6 / t_s / 1e9 if t_s > 0 else 0.0
+        tensor_bound = d["gflop"] * 1e9 / (peaks["tf_sustained"] * 1e12) >= d["mbytes"] * 1e6 / (peaks["hbm_gbs"] * 1e9)
         roof = ({"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                  "frac": tf / peaks["tf_sustained"]} if tensor_bound else
                 {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                  "frac": gbs / peaks["hbm_gbs"]})
         roof.update({"kernel": name, "traffic": None, "launches": d["launches"],
-                     "avg_launch_us": 1e3 * d["ms"] / nl, "peak_source": peaks["source"],
+                     "avg_launch_us": d["us"] / nl, "share_of_step": d["us"] / max(1e-9, sum(k["us"] for k in kernels.values())),
+                     "algorithmic_gflop_per_launch": d["gflop"] / nl, "algorithmic_mbytes_per_launch": d["mbytes"] / nl,
+                     "peak_source": peaks["source"],
                      "note": "algorithmic flops/bytes per launch over CUDA-event launch time (second, instrumented "
-                             "pass of the same K steps); tensor peak = measured dense bf16 (sustained)"})
+                             "pass of the same K steps); tensor peak = measured dense bf16 (sustained); traffic = ncu "
+                             "dram bytes per launch scaled to this launch's rows (profiles/ncu_traffic.json)"})
         traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(traffic_file):
-            roof["traffic"] = json.load(open(traffic_file)).get(name)
+            roof["traffic"] = ncu_traffic(json.load(open(traffic_file)), name)
         tprof = sum(v["ms"] for v in prof.values())
         breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / tprof if tprof else 0,
                          "launches_per_step": v["launches"] / args.steps,

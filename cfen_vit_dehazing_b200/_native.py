@@ -95,9 +95,10 @@ def check(status):
 
 
 def chunk_images(height, batch):
-    """Images processed per internal pass: bounds the workspace (~90 MB/image at 512x512).  32 images fill the
-    148 SMs on every level (measured: 16 -> 32 images per pass is +16 % throughput)."""
-    per = 32 if height <= 512 else 8
+    """Images processed per internal pass: bounds the workspace (~90 MB/image at 512x512, 5.8 GB of the 180 GB at
+    64 images).  Measured: 16 -> 32 images per pass +16 % throughput, 32 -> 64 another +3.5 % (the small-M
+    GEMMs of the global branch and the level-3 kernels fill more of a wave)."""
+    per = 64 if height <= 512 else 16
     env = os.environ.get("CFEN_CHUNK_IMAGES")
     if env:
         per = max(1, int(env))

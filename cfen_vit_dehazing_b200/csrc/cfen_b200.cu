@@ -312,7 +312,7 @@ struct cfen_plan {
   int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
   int conv_path = 1;  // 1: fp16 ldmatrix / m16n8k16 convolutions (conv16.cuh, default); 0: TF32 first generation
   int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
-  int fuse_min_tiles = 96;   // fused token kernels parallelise over 128-row tiles only: below this many tiles the unfused
+  int fuse_min_tiles = 32;   // fused token kernels parallelise over 128-row tiles only: below this many tiles the unfused
                              // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
   int maps16 = 1;      // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
   int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
