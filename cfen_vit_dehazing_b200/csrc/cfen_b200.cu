@@ -260,7 +260,9 @@ struct VitW {
   __half *h_le, *h_in, *h_out, *h_1, *h_2, *h_m0, *h_m3;  // fp16 operand copies (gemm_path 2)
 };
 
-struct TokWs { float *t0, *t1, *h, *qkv, *o, *f; __half *x16, *h16, *qkv16, *o16, *f16; };
+struct TokWs { float *t0, *t1, *h, *qkv, *o, *f, *part; __half *x16, *h16, *qkv16, *o16, *f16; };
+// split-K partial tiles of one Linear: slices x padded rows x N <= ~148 CTAs x 128 x 192 floats (gemm16_pick_split)
+static const size_t kSplitPartFloats = (size_t)4 << 20;
 
 struct Arena {
   char* base = nullptr;
@@ -312,6 +314,7 @@ struct cfen_plan {
   int fuse_mlp = 1;   // FFN / MLP-head pairs run as one tcgen05 kernel (mlp16.cuh / mlp_tc.cuh)
   int conv_path = 1;  // 1: fp16 ldmatrix / m16n8k16 convolutions (conv16.cuh, default); 0: TF32 first generation
   int fuse_tail = 1;  // gemm_path 2, E <= 192: out-proj + LN + FFN + MLP head as one kernel (vit_tail16.cuh)
+  int split_k = 1;           // small-M Linears: split the contraction over ~one wave of CTAs + a reduce pass
   int fuse_min_tiles = 32;   // fused token kernels parallelise over 128-row tiles only: below this many tiles the unfused
                              // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
   int maps16 = 1;      // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
@@ -393,6 +396,7 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
       L.lws.qkv = a.take(3 * lt); L.lws.f = a.take(lt * hr);
       L.lws.x16 = a.take16(lt); L.lws.h16 = a.take16(lt); L.lws.o16 = a.take16(lt);
       L.lws.qkv16 = a.take16(3 * lt); L.lws.f16 = a.take16(lt * hr);
+      L.lws.part = a.take(kSplitPartFloats); L.gws.part = a.take(kSplitPartFloats);
       L.gws.t0 = a.take(gt); L.gws.t1 = a.take(gt); L.gws.h = a.take(gt); L.gws.o = a.take(gt);
       L.gws.qkv = a.take(3 * gt); L.gws.f = a.take(gt * hr);
       L.gws.x16 = a.take16(gt); L.gws.h16 = a.take16(gt); L.gws.o16 = a.take16(gt);
@@ -498,6 +502,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
   if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm) != 0;
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
+  if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
   if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
   for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
   plan_declare_convs(p);
@@ -565,6 +570,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
   if (strcmp(name, "maps16") == 0) { p->maps16 = value != 0; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
+  if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
   if (strcmp(name, "streams") == 0) { p->streams = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
@@ -787,11 +793,32 @@ static int get_tmap2(cfen_plan* p, const void* ptr, int esize, uint64_t rows, ui
 
 // fp16-operand Linear: C32 and / or C16 = epi(A16 * W16^T)
 static int run_gemm16(Run& r, const __half* A, const __half* W, float* C32, __half* C16, int M, int N, int K,
-                      const float* bias, const float* res, const float* pos, int period, int relu) {
+                      const float* bias, const float* res, const float* pos, int period, int relu,
+                      float* part = nullptr) {
   const int BN = gemm16_pick_bn(M, N);
   const CUtensorMap *ta, *tw, *tc32, *tr, *tc16;
   RET(get_tmap2(r.p, A, 2, M, K, 64, 128, &ta));
   RET(get_tmap2(r.p, W, 2, N, K, 64, BN, &tw));
+  const int split = (part && r.p->split_k) ? gemm16_pick_split(M, N, K, BN) : 1;
+  const int Mpad = (M + 127) / 128 * 128;
+  if (split > 1 && (size_t)split * Mpad * N <= kSplitPartFloats) {
+    // split-K: fp32 partial tiles into `part`, then one reduce + epilogue pass (deterministic summation order)
+    const CUtensorMap* tp;
+    RET(get_tmap2(r.p, part, 4, (uint64_t)split * Mpad, N, 32, 128, &tp));
+    Gemm16Epilogue ep0{nullptr, nullptr, 1, 0, 0, 1, 0};
+    {
+      Launch l(r, PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + 4.0 * split * (double)Mpad * N,
+               "gemm16 M%d N%d K%d split%d", M, N, K, split);
+      CU(launch_gemm16(*ta, *tw, *tp, *ta, *ta, BN, M, N, K, ep0, r.st, split));
+    }
+    Launch l(r, PC_GEMM, 0.0, 4.0 * split * (double)M * N + (double)M * N * ((C32 ? 4 : 0) + (C16 ? 2 : 0) + (res ? 4 : 0)),
+             "splitk_reduce M%d N%d S%d", M, N, split);
+    const long long n4 = (long long)M * N / 4;
+    splitk_reduce_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(part, split, Mpad, M, N, bias, res, pos, period > 0 ? period : 1,
+                                                         relu, C32, C16);
+    CU(cudaGetLastError());
+    return 0;
+  }
   tc32 = tr = tc16 = ta;  // unused maps still need a valid object
   if (C32) RET(get_tmap2(r.p, C32, 4, M, N, 32, 128, &tc32));
   if (res) RET(get_tmap2(r.p, res, 4, M, N, 32, 128, &tr));
@@ -926,13 +953,13 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
     if (src) {
       RET(run_front16(r, v, src, nullptr, w.t1, w.qkv16, M));
     } else {
-      RET(run_gemm16(r, w.x16, v.h_le, w.t1, nullptr, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
+      RET(run_gemm16(r, w.x16, v.h_le, w.t1, nullptr, M, E, E, v.b_le, w.t0, v.pos, v.L, 0, w.part));
       RET(run_ln16(r, w.t1, w.h16, v.ln1g, v.ln1b, M, E));
-      RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0));
+      RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0, w.part));
     }
     RET(run_attn16(r, w.qkv16, w.o16, nseq, v.L, E, v.heads));
     if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= r.p->fuse_min_tiles) return run_tail16(r, v, w.o16, w.t1, M);
-    RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0));
+    RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0, w.part));
     RET(run_ln16(r, w.t1, w.h16, v.ln2g, v.ln2b, M, E));
     const int bm = 128 * mlp16_shape(E).MH;
     if (r.p->fuse_mlp && mlp16_supported(E, hid) && (M + bm - 1) / bm >= r.p->fuse_min_tiles * 2 / 3) {
@@ -940,10 +967,10 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
       RET(run_mlp16(r, w.x16, v.h_m0, v.bm0, v.h_m3, v.bm3, w.t1, w.t1, nullptr, M, E, hid));
       return 0;
     }
-    RET(run_gemm16(r, w.h16, v.h_1, nullptr, w.f16, M, hid, E, v.b1, nullptr, nullptr, 0, 1));
-    RET(run_gemm16(r, w.f16, v.h_2, w.t1, w.x16, M, E, hid, v.b2, w.t1, nullptr, 0, 0));
-    RET(run_gemm16(r, w.x16, v.h_m0, nullptr, w.f16, M, hid, E, v.bm0, nullptr, nullptr, 0, 1));
-    RET(run_gemm16(r, w.f16, v.h_m3, w.t1, nullptr, M, E, hid, v.bm3, w.t1, nullptr, 0, 0));
+    RET(run_gemm16(r, w.h16, v.h_1, nullptr, w.f16, M, hid, E, v.b1, nullptr, nullptr, 0, 1, w.part));
+    RET(run_gemm16(r, w.f16, v.h_2, w.t1, w.x16, M, E, hid, v.b2, w.t1, nullptr, 0, 0, w.part));
+    RET(run_gemm16(r, w.x16, v.h_m0, nullptr, w.f16, M, hid, E, v.bm0, nullptr, nullptr, 0, 1, w.part));
+    RET(run_gemm16(r, w.f16, v.h_m3, w.t1, nullptr, M, E, hid, v.bm3, w.t1, nullptr, 0, 0, w.part));
     return 0;
   }
   RET(run_gemm(r, w.t0, v.w_le, w.t1, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
@@ -1315,6 +1342,31 @@ extern "C" int32_t cfen_gemm_f16(const void* A16, const void* W16, float* C32, v
   if (ok && residual) ok = make_tmap_2d(&tr, residual, 4, M, N, 32, 128);
   if (ok && C16) ok = make_tmap_2d(&tc16, C16, 2, M, N, 32, 128);
   if (!ok) return fail(11, "cfen_gemm_f16: cuTensorMapEncodeTiled failed");
+  // same split-K policy as the plan (run_gemm16); the partial buffer is a temporary here (test-only convenience)
+  const char* ske = getenv("CFEN_SPLIT_K");
+  const int split = (!ske || atoi(ske) != 0) ? gemm16_pick_split(M, N, K, BN) : 1;
+  const int Mpad = (M + 127) / 128 * 128;
+  if (split > 1 && (size_t)split * Mpad * N <= kSplitPartFloats) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* part = nullptr;
+    CU(cudaMalloc(&part, (size_t)split * Mpad * N * sizeof(float)));
+    CUtensorMap tp;
+    cudaError_t e = make_tmap_2d(&tp, part, 4, (uint64_t)split * Mpad, N, 32, 128) ? cudaSuccess : cudaErrorInvalidValue;
+    if (e == cudaSuccess) {
+      Gemm16Epilogue ep0{nullptr, nullptr, 1, 0, 0, 1, 0};
+      e = launch_gemm16(ta, tw, tp, ta, ta, BN, M, N, K, ep0, st, split);
+    }
+    if (e == cudaSuccess) {
+      splitk_reduce_kernel<<<ew_blocks((long long)M * N / 4), 256, 0, st>>>(part, split, Mpad, M, N, bias, residual, pos,
+                                                                          pos_period > 0 ? pos_period : 1, relu, C32,
+                                                                          static_cast<__half*>(C16));
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(part);
+    if (e != cudaSuccess) return fail(2, "cfen_gemm_f16 (split-K) failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   Gemm16Epilogue ep{bias, pos, pos_period > 0 ? pos_period : 1, relu, residual != nullptr, C32 != nullptr, C16 != nullptr};
   CU(launch_gemm16(ta, tw, tc32, tr, tc16, BN, M, N, K, ep, static_cast<cudaStream_t>(stream)));
   return 0;

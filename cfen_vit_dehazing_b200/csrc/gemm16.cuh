@@ -63,7 +63,15 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   // single-lane roles in an ELECT + BRA.U.ANY uniformisation loop (~130 cycles per MMA issue, profiles/r1_v2_*)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * Cfg::BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + Cfg::BK - 1) / Cfg::BK;
+  // split-K (gridDim.z > 1): this CTA contracts k-boxes [kb0, kb0 + nkb) and stores its fp32 partial tile at row
+  // blockIdx.z * gridDim.y * BM of the partial buffer tmC32 maps; splitk_reduce_kernel sums the slices in a fixed
+  // order and applies the epilogue.  Small-M Linears (global branch, batch-1) otherwise stream their weights
+  // through a handful of CTAs.
+  const int nkb_all = (K + Cfg::BK - 1) / Cfg::BK;
+  const int kb_per = (nkb_all + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * kb_per;
+  const int nkb = min(kb_per, nkb_all - kb0);   // >= 1: the host sizes the split so that no slice is empty
+  const int m0_out = m0 + blockIdx.z * gridDim.y * Cfg::BM;
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -100,8 +108,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (tc::elect_one()) {
         uint8_t* a = smem + s * Cfg::STAGE_BYTES;
         tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        tc::tma_load_2d(a, &tmA, &full_bar[s], kb * Cfg::BK, m0);
-        tc::tma_load_2d(a + Cfg::A_BYTES, &tmW, &full_bar[s], kb * Cfg::BK, n0);
+        tc::tma_load_2d(a, &tmA, &full_bar[s], (kb0 + kb) * Cfg::BK, m0);
+        tc::tma_load_2d(a + Cfg::A_BYTES, &tmW, &full_bar[s], (kb0 + kb) * Cfg::BK, n0);
       }
       __syncwarp();
     }
@@ -125,7 +133,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint64_t adesc = tc::umma_desc_sw128(a_addr);
         const uint64_t bdesc = tc::umma_desc_sw128(a_addr + Cfg::A_BYTES);
-        const int krem = K - kb * Cfg::BK;
+        const int krem = K - (kb0 + kb) * Cfg::BK;
         const int nks = krem >= Cfg::BK ? Cfg::BK / 16 : (krem + 15) / 16;
         for (int k = 0; k < nks; ++k)  // +32 bytes per K=16 step inside the swizzle atom
           tc::umma_f16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -189,7 +197,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (warp == 2 && tc::elect_one()) {
       if (ep.out32) {
 #pragma unroll
-        for (int i = 0; i < Cfg::NP; ++i) tc::tma_store_2d(&tmC32, smem + i * Cfg::P32_BYTES, n0 + 32 * i, m0);
+        for (int i = 0; i < Cfg::NP; ++i) tc::tma_store_2d(&tmC32, smem + i * Cfg::P32_BYTES, n0 + 32 * i, m0_out);
       }
       if (ep.out16) {
 #pragma unroll
@@ -241,12 +249,51 @@ inline int gemm16_smem_bytes(int nst, const Gemm16Epilogue& ep) {
   const int staging = ((ep.out32 || ep.has_res) ? Cfg::NP * Cfg::P32_BYTES : 0) + (ep.out16 ? Cfg::NP * Cfg::P16_BYTES : 0);
   return (ring > staging ? ring : staging) + 1024;
 }
+// Split-K slices for a small-M Linear: enough CTAs for about one wave, at least two k-boxes per slice, no empty slice.
+inline int gemm16_pick_split(int M, int N, int K, int BN) {
+  const int tiles = (N / BN) * ((M + 127) / 128), nkb = (K + 63) / 64;
+  if (tiles >= 74 || nkb < 4) return 1;
+  int s = (148 + tiles - 1) / tiles;
+  if (s > nkb / 2) s = nkb / 2;
+  if (s > 16) s = 16;
+  if (s < 2) return 1;
+  const int per = (nkb + s - 1) / s;
+  return (nkb + per - 1) / per;   // slices actually used by ceil(nkb / s) boxes each
+}
+// out = epi(sum_s part[s]) for the split-K partial buffer part[S][Mpad][N] (fp32): bias, ReLU, residual, position
+// rows as in the fused epilogue, fp32 and / or fp16 outputs.  One thread per 4 columns.
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, int Mpad, int M, int N,
+                                     const float* __restrict__ bias, const float* res,   // res may alias c32
+                                     const float* __restrict__ pos, int pos_period, int relu,
+                                     float* c32, __half* __restrict__ c16) {
+  const int n4 = N >> 2;
+  const long long total = (long long)M * n4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % n4) * 4, r = (int)(i / n4);
+    float4 v = *reinterpret_cast<const float4*>(part + (size_t)r * N + c);
+    for (int s = 1; s < S; ++s) {
+      const float4 p = *reinterpret_cast<const float4*>(part + ((size_t)s * Mpad + r) * N + c);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + c); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (res) { const float4 b = *reinterpret_cast<const float4*>(res + (size_t)r * N + c); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+    if (pos) {
+      const float4 b = *reinterpret_cast<const float4*>(pos + (size_t)(r % pos_period) * N + c);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (c32) *reinterpret_cast<float4*>(c32 + (size_t)r * N + c) = v;
+    if (c16) *reinterpret_cast<uint2*>(c16 + (size_t)r * N + c) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+  }
+}
+
 inline cudaError_t launch_gemm16(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC32,
                                  const CUtensorMap& tmR, const CUtensorMap& tmC16, int BN, int M, int N, int K,
-                                 const Gemm16Epilogue& ep, cudaStream_t st) {
+                                 const Gemm16Epilogue& ep, cudaStream_t st, int split = 1) {
   if (M <= 0) return cudaSuccess;
   if (N % BN != 0 || K % 16 != 0) return cudaErrorInvalidValue;
-  dim3 grid(N / BN, (M + 127) / 128);
+  if (split > 1 && (ep.bias || ep.pos || ep.relu || ep.has_res || ep.out16 || !ep.out32)) return cudaErrorInvalidValue;
+  dim3 grid(N / BN, (M + 127) / 128, split);
   const int nst = (K + 63) / 64 <= 6 ? 2 : 4;
   if (BN == 96)
     gemm16_kernel<96><<<grid, 192, gemm16_smem_bytes<96>(nst, ep), st>>>(tmA, tmW, tmC32, tmR, tmC16, M, N, K, nst, ep);
