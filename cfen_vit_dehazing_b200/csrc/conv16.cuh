@@ -283,10 +283,9 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
       // fp16 map: the halo tile is copied global -> shared asynchronously (cp.async, zero-fill outside the image),
       // no registers and no conversion; the copy group is waited for together with the first weight chunk
       constexpr int CH = S::CIN % 8 == 0 ? 8 : 4;          // halves per copy
-      constexpr int CPP = S::CIN / CH, TOT16 = C::IN_H * C::IN_W * CPP;
+      constexpr int CPP = S::CIN / CH;
       const __half* in16 = reinterpret_cast<const __half*>(a.in0) + img * S::CIN;
-      for (int i = tid; i < TOT16; i += S::THREADS) {
-        const int cc = i % CPP, pix = i / CPP;
+      for (int pix = tid; pix < C::IN_H * C::IN_W; pix += S::THREADS) {   // one pixel (all its chunks) per item
         const int iy = pix / C::IN_W, ix = pix - iy * C::IN_W;
         int gy = oy0 + iy, gx = ox0 + ix;
         bool inside = true;
@@ -296,9 +295,13 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
         } else {
           inside = (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win;
         }
-        const __half* src = in16 + (inside ? (uint32_t)(gy * Win + gx) * S::CIN + cc * CH : 0u);
-        if (CH == 8) cp_async16(tile + pix * C::CPITCH + cc * CH, src, inside);
-        else cp_async8(tile + pix * C::CPITCH + cc * CH, src, inside);
+        const __half* src = in16 + (inside ? (uint32_t)(gy * Win + gx) * S::CIN : 0u);
+        __half* dst = tile + pix * C::CPITCH;
+#pragma unroll
+        for (int cc = 0; cc < CPP; ++cc) {
+          if (CH == 8) cp_async16(dst + cc * CH, src + (inside ? cc * CH : 0), inside);
+          else cp_async8(dst + cc * CH, src + (inside ? cc * CH : 0), inside);
+        }
       }
       cp_async_commit();
     }
