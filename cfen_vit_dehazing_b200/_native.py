@@ -17,7 +17,7 @@ _lib = None
 EXPORTED_SYMBOLS = (
     "cfen_abi_version", "cfen_last_error",
     "cfen_plan_create", "cfen_plan_destroy", "cfen_plan_set_weight", "cfen_plan_pack_weights",
-    "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option",
+    "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option", "cfen_plan_get_option",
     "cfen_plan_profile_json", "cfen_plan_profile_trace",
     "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
     "cfen_plan_stage_ptr",
@@ -56,6 +56,7 @@ def lib():
         L.cfen_plan_launches_per_forward.argtypes = [vp]
         L.cfen_plan_launches_per_forward.restype = i64
         L.cfen_plan_set_option.argtypes = [vp, cp, i64]
+        L.cfen_plan_get_option.argtypes = [vp, cp, ctypes.POINTER(ctypes.c_int64)]
         L.cfen_plan_profile_json.argtypes = [vp, cp, i64]
         L.cfen_plan_profile_trace.argtypes = [vp, cp]
         L.cfen_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -149,6 +150,11 @@ class Plan:
 
     def set_option(self, name, value):
         check(lib().cfen_plan_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = ctypes.c_int64()
+        check(lib().cfen_plan_get_option(self._h, name.encode(), ctypes.byref(v)))
+        return v.value
 
     def profile(self):
         """Per-kernel-class timing of the last forward (needs set_option("timing", 1))."""

@@ -73,6 +73,9 @@ static int default_tail_variant() {
 }
 static bool tail_in_tmem(int variant, int E) { return (variant == 1 && E == 96) || variant == 2; }
 
+struct cfen_plan;
+static bool all_maps16(const cfen_plan* p);
+
 static cudaError_t set_kernel_attributes() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<128, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -317,7 +320,8 @@ struct cfen_plan {
   int split_k = 1;           // small-M Linears: split the contraction over ~one wave of CTAs + a reduce pass
   int fuse_min_tiles = 32;   // fused token kernels parallelise over 128-row tiles only: below this many tiles the unfused
                              // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
-  int maps16 = 1;      // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
+  int maps16 = 2;      // 0: fp32 maps; 1: fp16 full-resolution maps only; 2: every stage map is fp16
+  //     // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
   int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
                        // as one kernel reading the NHWC map (vit_front16.cuh); tokenize_local is not launched
   int tail_variant = 1;  // 0: residual tile in shared memory (vit_tail16.cuh); 1: residual in TMEM for E = 96, two CTAs
@@ -500,7 +504,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
   p->tail_variant = default_tail_variant();
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
-  if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm) != 0;
+  if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm);
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
   if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
@@ -551,6 +555,16 @@ extern "C" int32_t cfen_plan_set_weight(cfen_plan* p, const char* key, const voi
 
 extern "C" int64_t cfen_plan_workspace_bytes(const cfen_plan* p) { return p ? (int64_t)(p->wa.cap + p->ws.cap) : 0; }
 extern "C" int64_t cfen_plan_launches_per_forward(const cfen_plan* p) { return p ? p->launches_last : 0; }
+extern "C" int32_t cfen_plan_get_option(const cfen_plan* p, const char* name, int64_t* value) {
+  if (!p || !name || !value) return fail(1, "cfen_plan_get_option: null argument");
+  if (strcmp(name, "maps16") == 0) { *value = p->conv_path ? p->maps16 : 0; return 0; }
+  if (strcmp(name, "gemm_path") == 0) { *value = p->gemm_path; return 0; }
+  if (strcmp(name, "conv_path") == 0) { *value = p->conv_path; return 0; }
+  if (strcmp(name, "fuse_front") == 0) { *value = p->fuse_front; return 0; }
+  if (strcmp(name, "fuse_tail") == 0) { *value = p->fuse_tail; return 0; }
+  if (strcmp(name, "split_k") == 0) { *value = p->split_k; return 0; }
+  return fail(5, "unknown option '%s'", name);
+}
 extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t value) {
   if (!p || !name) return fail(1, "cfen_plan_set_option: null argument");
   // "timing": records accumulate over forwards until "timing_reset" (or re-enabling) clears them
@@ -568,7 +582,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
   if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
-  if (strcmp(name, "maps16") == 0) { p->maps16 = value != 0; return 0; }
+  if (strcmp(name, "maps16") == 0) { p->maps16 = (int)value; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
@@ -791,6 +805,8 @@ static int get_tmap2(cfen_plan* p, const void* ptr, int esize, uint64_t rows, ui
   return 0;
 }
 
+static bool all_maps16(const cfen_plan* p) { return p->conv_path && p->maps16 >= 2; }
+
 // fp16-operand Linear: C32 and / or C16 = epi(A16 * W16^T)
 static int run_gemm16(Run& r, const __half* A, const __half* W, float* C32, __half* C16, int M, int N, int K,
                       const float* bias, const float* res, const float* pos, int period, int relu,
@@ -871,7 +887,7 @@ static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
   return 0;
 }
 // Window gather (or token matrix) -> t1 (fp32) and qkv16 of one local ViT call as one kernel (vit_front16.cuh)
-struct FrontSrc { const float* map; int H, W, C, win; };
+struct FrontSrc { const float* map; int H, W, C, win; bool h16; };
 static int run_front16(Run& r, const VitW& v, const FrontSrc* src, const float* T0, float* T1, __half* QKV16, int M) {
   const int E = v.E;
   const CUtensorMap *twle, *twin, *tt1, *tq;
@@ -879,7 +895,7 @@ static int run_front16(Run& r, const VitW& v, const FrontSrc* src, const float* 
   RET(get_tmap2(r.p, v.h_in, 2, 3 * E, E, 64, 96, &twin));
   RET(get_tmap2(r.p, T1, 4, M, E, 32, 128, &tt1));
   RET(get_tmap2(r.p, QKV16, 2, M, 3 * E, 32, 128, &tq));
-  Front16Args a{src ? src->map : T0, src != nullptr, src ? src->H : 0, src ? src->W : 0, src ? src->C : 0,
+  Front16Args a{src ? src->map : T0, src ? (src->h16 ? 2 : 1) : 0, src ? src->H : 0, src ? src->W : 0, src ? src->C : 0,
                 src ? src->win : 0, v.b_le, v.pos, v.L, v.ln1g, v.ln1b, M};
   Launch l(r, PC_GEMM, 8.0 * M * E * E, (double)M * E * (4 + 4 + 6) + 8.0 * E * E, "front16 M%d E%d", M, E);
   CU(launch_front16(E, *twle, *twin, *tt1, *tq, a, r.st));
@@ -1004,6 +1020,9 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = c.wpack; a.out = out;
   a.B = r.nb; a.H = H; a.W = W; a.win = p->win;
   const bool is_lg = c.kind == K_LG1 || c.kind == K_LG2 || c.kind == K_LG3;
+  // every stage map is fp16 (maps16 level 2): the map operands of every conv-family layer; loaders / epilogues that
+  // do not touch a map of that role ignore the bit (token-matrix inputs of the merges, NCHW network input / outputs)
+  if (all_maps16(p)) flags |= CF_IN16 | CF_OUT16 | ((flags & CF_RES) ? CF_RES16 : 0);
   const bool is_up = c.kind == K_UP3 || c.kind == K_UP2 || c.kind == K_UP1;
   const int cout_ = conv_cout(c.kind);
   const double kelems = (double)conv_wpack_k(c.kind);           // contraction length per output pixel
@@ -1047,7 +1066,8 @@ static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, f
   }
   const long long total4 = (long long)r.nb * Hout * Wout * C / 4;
   Launch l(r, PC_NORM, 0.0, 32.0 * total4);
-  instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, r.ln->mean_rstd, Hout * Wout, C, total4);
+  instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, r.ln->mean_rstd, Hout * Wout, C, total4,
+                                                               all_maps16(p));
   CU(cudaGetLastError());
   return 0;
 }
@@ -1059,8 +1079,8 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
   const long long total4 = (long long)r.nb * HW * C / 4;
   {
     Launch l(r, PC_CFSM, 0.0, 48.0 * total4);
-    if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW);
-    else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW);
+    if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW, all_maps16(p));
+    else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW, all_maps16(p));
     CU(cudaGetLastError());
   }
   {
@@ -1070,7 +1090,7 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
     CU(cudaGetLastError());
   }
   Launch l(r, PC_CFSM, 0.0, 64.0 * total4);
-  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, r.ln->gates, out, HW, C, total4);
+  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, r.ln->gates, out, HW, C, total4, all_maps16(p));
   CU(cudaGetLastError());
   return 0;
 }
@@ -1090,7 +1110,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17, "tok_global H%d C%d", Hl, C);
-      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.gws.t0, L.gws.x16, r.nb, Hl, Hl, C);
+      tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.gws.t0, L.gws.x16, r.nb, Hl, Hl, C, all_maps16(p));
       CU(cudaGetLastError());
     }
     const int rc = run_vit(r, p->gvit[si], L.gws, r.nb);
@@ -1098,13 +1118,13 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     RET(rc);
   }
   if (front_fusable(p, p->lvit[si].E, r.nb * nwin * p->lvit[si].L)) {
-    const FrontSrc src{x, Hl, Hl, C, p->win};
+    const FrontSrc src{x, Hl, Hl, C, p->win, all_maps16(p)};
     RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin, &src));
   } else {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4, "tok_local H%d C%d", Hl, C);
-      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.lws.t0, L.lws.x16, r.nb, Hl, Hl, C, p->win);
+      tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.lws.t0, L.lws.x16, r.nb, Hl, Hl, C, p->win, all_maps16(p));
       CU(cudaGetLastError());
     }
     RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin));
@@ -1129,7 +1149,7 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
   p->lane[2].gst = multi ? p->side[4] : st;
   p->sync_used = 0;
   // fp16 storage of the full-resolution 12-channel maps (conv16 generation only): f0 / f1 / f2 and the lanes' scratch
-  const bool m16 = p->conv_path && p->maps16;
+  const bool m16 = p->conv_path && p->maps16 >= 1;
   const int I16 = m16 ? CF_IN16 : 0, O16 = m16 ? CF_OUT16 : 0, R16 = m16 ? CF_RES16 : 0;
   Run r0{p, st, nb, &p->lane[0]};
   {
@@ -1559,13 +1579,13 @@ extern "C" int32_t cfen_cfsm(const float* x0, const float* x1, const float* x2, 
   float* gates = scratch + (size_t)B * parts * 2 * C;  // [B][2][C]
   const long long total4 = (long long)B * HW * C / 4;
   if (C == 48) {
-    cfsm_reduce_kernel<48><<<dim3(parts, B), 192, 0, st>>>(x0, x1, x2, part, HW);
+    cfsm_reduce_kernel<48><<<dim3(parts, B), 192, 0, st>>>(x0, x1, x2, part, HW, false);
     cfsm_gate_kernel<48><<<B, 128, 0, st>>>(part, w, gates, parts, HW);
   } else {
-    cfsm_reduce_kernel<24><<<dim3(parts, B), 192, 0, st>>>(x0, x1, x2, part, HW);
+    cfsm_reduce_kernel<24><<<dim3(parts, B), 192, 0, st>>>(x0, x1, x2, part, HW, false);
     cfsm_gate_kernel<24><<<B, 128, 0, st>>>(part, w, gates, parts, HW);
   }
-  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(x0, x1, x2, gates, out, HW, C, total4);
+  cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(x0, x1, x2, gates, out, HW, C, total4, false);
   CU(cudaGetLastError());
   return 0;
 }

@@ -31,6 +31,23 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return r;
 }
 
+// ---------------------------------------------------------------- NHWC maps stored as fp32 or fp16
+// Four consecutive channels of a map: `i4` counts 4-element groups from the map base, whatever the storage width
+// (fp16 maps are addressed through the same float* the plan hands out).
+__device__ __forceinline__ float4 ld_map4(const float* base, size_t i4, bool h16) {
+  if (h16) {
+    const uint2 u = reinterpret_cast<const uint2*>(base)[i4];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return reinterpret_cast<const float4*>(base)[i4];
+}
+__device__ __forceinline__ void st_map4(float* base, size_t i4, float4 v, bool h16) {
+  if (h16) reinterpret_cast<uint2*>(base)[i4] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+  else reinterpret_cast<float4*>(base)[i4] = v;
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

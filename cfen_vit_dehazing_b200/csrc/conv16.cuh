@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
     constexpr int C4R = S::LOADER == LD_NCHW3 ? 1 : S::CIN / 4;
     constexpr int U = S::LOADER == LD_SUM2 ? 4 : 8, TOTAL = C::IN_H * C::IN_W * C4R;
     const size_t img = (size_t)b * Hin * Win;   // first pixel of this image
+    const bool in16 = (a.flags & CF_IN16) != 0;   // fp16 source maps (both inputs of SUM2 / CAT2)
     auto fetch = [&](int i) -> float4 {
       const int c4 = i % C4R, pix = i / C4R;
       const int iy = pix / C::IN_W, ix = pix - iy * C::IN_W;
@@ -259,16 +260,17 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
       if (inside) {
         const uint32_t pidx = (uint32_t)(gy * Win + gx);   // pixel inside the image
         if (S::LOADER == LD_NHWC) {
-          v = *reinterpret_cast<const float4*>(a.in0 + img * S::CIN + (pidx * S::CIN + c4 * 4));
+          v = ld_map4(a.in0, (img * S::CIN + (pidx * S::CIN + c4 * 4)) >> 2, in16);
         } else if (S::LOADER == LD_SUM2) {
-          const float4 p = *reinterpret_cast<const float4*>(a.in0 + img * S::CIN + (pidx * S::CIN + c4 * 4));
-          const float4 q = *reinterpret_cast<const float4*>(a.in1 + img * S::CIN + (pidx * S::CIN + c4 * 4));
+          const size_t i4 = (img * S::CIN + (pidx * S::CIN + c4 * 4)) >> 2;
+          const float4 p = ld_map4(a.in0, i4, in16);
+          const float4 q = ld_map4(a.in1, i4, in16);
           v = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
         } else if (S::LOADER == LD_CAT2) {
           constexpr int C1 = S::CIN / 2;
           const int c = c4 * 4;
-          v = c < C1 ? *reinterpret_cast<const float4*>(a.in0 + img * C1 + (pidx * C1 + c))
-                     : *reinterpret_cast<const float4*>(a.in1 + img * C1 + (pidx * C1 + (c - C1)));
+          v = c < C1 ? ld_map4(a.in0, (img * C1 + (pidx * C1 + c)) >> 2, in16)
+                     : ld_map4(a.in1, (img * C1 + (pidx * C1 + (c - C1))) >> 2, in16);
         } else {  // LD_NCHW3
           const size_t plane = (size_t)Hin * Win;
           const float* p = a.in0 + img * 3 + pidx;
@@ -486,8 +488,15 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
           const size_t ia = (((size_t)b * Hout + oy) * Wout + oxa) * S::COUT + c;
           const size_t ib = (((size_t)b * Hout + oy) * Wout + oxb) * S::COUT + c;
           if (flags & CF_RES) {
-            const float2 ra = *reinterpret_cast<const float2*>(a.res + ia);
-            const float2 rb = *reinterpret_cast<const float2*>(a.res + ib);
+            float2 ra, rb;
+            if (flags & CF_RES16) {
+              const __half* r16 = reinterpret_cast<const __half*>(a.res);
+              ra = __half22float2(*reinterpret_cast<const __half2*>(r16 + ia));
+              rb = __half22float2(*reinterpret_cast<const __half2*>(r16 + ib));
+            } else {
+              ra = *reinterpret_cast<const float2*>(a.res + ia);
+              rb = *reinterpret_cast<const float2*>(a.res + ib);
+            }
             v[0] += ra.x; v[1] += ra.y; v[2] += rb.x; v[3] += rb.y;
           }
           if (flags & CF_OUT16) {

@@ -27,7 +27,7 @@ __global__ void instnorm_finalize_kernel(const float* __restrict__ partials, flo
 
 // x <- relu((x - mean) * rstd), in place
 __global__ void instnorm_relu_apply_kernel(float* __restrict__ x, const float* __restrict__ mean_rstd,
-                                           int HW, int C, long long total4) {
+                                           int HW, int C, long long total4, bool h16) {
   const int C4 = C >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -35,12 +35,12 @@ __global__ void instnorm_relu_apply_kernel(float* __restrict__ x, const float* _
     const int b = (int)(i / ((long long)HW * C4));
     const float4 m = *reinterpret_cast<const float4*>(mean_rstd + ((size_t)b * 2 + 0) * C + c);
     const float4 r = *reinterpret_cast<const float4*>(mean_rstd + ((size_t)b * 2 + 1) * C + c);
-    float4 v = reinterpret_cast<float4*>(x)[i];
+    float4 v = ld_map4(x, i, h16);
     v.x = fmaxf((v.x - m.x) * r.x, 0.f);
     v.y = fmaxf((v.y - m.y) * r.y, 0.f);
     v.z = fmaxf((v.z - m.z) * r.z, 0.f);
     v.w = fmaxf((v.w - m.w) * r.w, 0.f);
-    reinterpret_cast<float4*>(x)[i] = v;
+    st_map4(x, i, v, h16);
   }
 }
 
@@ -76,7 +76,7 @@ __global__ void actnorm_calibrate_kernel(const float* __restrict__ partials, int
 template <int C>
 __global__ void __launch_bounds__(192)
 cfsm_reduce_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
-                   const float* __restrict__ x2, float* __restrict__ partials, int HW) {
+                   const float* __restrict__ x2, float* __restrict__ partials, int HW, bool h16) {
   constexpr int C4 = C / 4;
   constexpr int PIX_PER_ITER = 192 / C4;  // threads are (pixel lane, c4); block = 192
   static_assert(192 % C4 == 0, "channel vectors must tile the block");
@@ -90,10 +90,10 @@ cfsm_reduce_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   const size_t base = (size_t)b * HW * C;
   for (int p = p0 + pl; p < p1; p += PIX_PER_ITER) {
-    const size_t off = base + (size_t)p * C + c4 * 4;
-    const float4 a = *reinterpret_cast<const float4*>(x0 + off);
-    const float4 bb = *reinterpret_cast<const float4*>(x1 + off);
-    const float4 cc = *reinterpret_cast<const float4*>(x2 + off);
+    const size_t off4 = (base + (size_t)p * C) / 4 + c4;
+    const float4 a = ld_map4(x0, off4, h16);
+    const float4 bb = ld_map4(x1, off4, h16);
+    const float4 cc = ld_map4(x2, off4, h16);
     const float4 v = make_float4(a.x + bb.x + cc.x, a.y + bb.y + cc.y, a.z + bb.z + cc.z, a.w + bb.w + cc.w);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
@@ -159,7 +159,7 @@ __global__ void cfsm_gate_kernel(const float* __restrict__ partials, const float
 // (3) out = x0 + x1*sig1 + x2*sig2
 __global__ void cfsm_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1,
                                   const float* __restrict__ x2, const float* __restrict__ gates,
-                                  float* __restrict__ out, int HW, int C, long long total4) {
+                                  float* __restrict__ out, int HW, int C, long long total4, bool h16) {
   const int C4 = C >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -167,15 +167,15 @@ __global__ void cfsm_apply_kernel(const float* __restrict__ x0, const float* __r
     const int b = (int)(i / ((long long)HW * C4));
     const float4 g1 = *reinterpret_cast<const float4*>(gates + ((size_t)b * 2 + 0) * C + c);
     const float4 g2 = *reinterpret_cast<const float4*>(gates + ((size_t)b * 2 + 1) * C + c);
-    const float4 a = reinterpret_cast<const float4*>(x0)[i];
-    const float4 p = reinterpret_cast<const float4*>(x1)[i];
-    const float4 q = reinterpret_cast<const float4*>(x2)[i];
+    const float4 a = ld_map4(x0, i, h16);
+    const float4 p = ld_map4(x1, i, h16);
+    const float4 q = ld_map4(x2, i, h16);
     float4 o;
     o.x = a.x + p.x * g1.x + q.x * g2.x;
     o.y = a.y + p.y * g1.y + q.y * g2.y;
     o.z = a.z + p.z * g1.z + q.z * g2.z;
     o.w = a.w + p.w * g1.w + q.w * g2.w;
-    reinterpret_cast<float4*>(out)[i] = o;
+    st_map4(out, i, o, h16);
   }
 }
 

@@ -39,7 +39,7 @@ struct Front16 {
 };
 
 struct Front16Args {
-  const float* src;            // NHWC map [B,H,W,C] (is_map) or token matrix [M,E]
+  const float* src;            // NHWC map [B,H,W,C] (is_map: 1 = fp32 storage, 2 = fp16 storage) or token matrix [M,E]
   int is_map, H, W, C, win;    // map geometry; a token is a 2x2 patch, a window win x win pixels
   const float* ble;            // linear_encoding bias [E]
   const float* pos;            // position rows [L,E]
@@ -176,20 +176,22 @@ vit_front16_kernel(const __grid_constant__ CUtensorMap tmWle, const __grid_const
     const int m = m0 + row;
     const bool valid = m < a.M;
     // ---- token row source: two contiguous segments of E/2 floats (ky = 0, 1)
-    auto row_segments = [&](int mm, const float*& s0, const float*& s1) {
+    // (element offsets from a.src: the map may be stored as fp32 or fp16)
+    const bool h16 = a.is_map == 2;
+    auto row_segments = [&](int mm, size_t& s0, size_t& s1) {
       if (a.is_map) {
         const int l = mm % a.L, widx = mm / a.L;
         const int half = a.win >> 1, nx = a.W / a.win, ny = a.H / a.win;
         const int wx = widx % nx, wy = (widx / nx) % ny, b = widx / (nx * ny);
         const int ty = l / half, tx = l - ty * half;
-        s0 = a.src + (((size_t)b * a.H + wy * a.win + 2 * ty) * a.W + wx * a.win + 2 * tx) * a.C;
+        s0 = (((size_t)b * a.H + wy * a.win + 2 * ty) * a.W + wx * a.win + 2 * tx) * a.C;
         s1 = s0 + (size_t)a.W * a.C;
       } else {
-        s0 = a.src + (size_t)mm * E;
+        s0 = (size_t)mm * E;
         s1 = s0 + E / 2;
       }
     };
-    const float *seg0, *seg1;
+    size_t seg0, seg1;
     row_segments(valid ? m : 0, seg0, seg1);
     const float* posrow = a.pos + (size_t)(m % a.L) * E;
     // ---- prologue: ACC <- x + b_le + pos ; Xa <- fp16(x).  Three panels (24 x 16 B per thread) are requested before
@@ -203,18 +205,22 @@ vit_front16_kernel(const __grid_constant__ CUtensorMap tmWle, const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int f = 32 * (i0 + ii) + 4 * j;
-          const float* p = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
-          t[ii][j] = valid ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t off = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
+          t[ii][j] = valid ? ld_map4(a.src, off >> 2, h16) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       if (i0 == 0) {   // pull the same rows of the tile that runs one wave later into L2
         const int mp = m + 128 * C::MIN_CTAS * 148;
         if (mp < a.M) {
-          const float *p0, *p1;
-          row_segments(mp, p0, p1);
-#pragma unroll
-          for (int off = 0; off < E / 2; off += 32) { tc::prefetch_l2(p0 + off); tc::prefetch_l2(p1 + off); }
-          tc::prefetch_l2(p0 + E / 2 - 4);
-          tc::prefetch_l2(p1 + E / 2 - 4);
+          size_t o0, o1;
+          row_segments(mp, o0, o1);
+          const int esz = h16 ? 2 : 4, step = 128 / esz;    // elements per 128-byte line
+          const char* base = reinterpret_cast<const char*>(a.src);
+          for (int off = 0; off < E / 2; off += step) {
+            tc::prefetch_l2(base + (o0 + off) * esz);
+            tc::prefetch_l2(base + (o1 + off) * esz);
+          }
+          tc::prefetch_l2(base + (o0 + E / 2 - 4) * esz);
+          tc::prefetch_l2(base + (o1 + E / 2 - 4) * esz);
         }
       }
 #pragma unroll

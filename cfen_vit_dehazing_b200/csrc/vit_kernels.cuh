@@ -12,7 +12,8 @@ namespace cfen {
 // One thread moves one float4.
 // =====================================================================================
 __global__ void tokenize_local_kernel(const float* __restrict__ map, float* __restrict__ tok,
-                                      __half* __restrict__ tok16, int B, int H, int W, int C, int win) {
+                                      __half* __restrict__ tok16, int B, int H, int W, int C, int win,
+                                      bool h16 = false) {
   const int E4 = C;  // 4C floats per token = C float4
   const int half = win >> 1, L = half * half;
   const int ny = H / win, nx = W / win;
@@ -29,7 +30,7 @@ __global__ void tokenize_local_kernel(const float* __restrict__ map, float* __re
     const int f = f4 * 4;
     const int ky = f / (2 * C), rem = f - ky * 2 * C;  // rem = kx*C + c, contiguous in NHWC too
     const int y = wy * win + 2 * ty + ky, x = wx * win + 2 * tx;
-    const float4 v = *reinterpret_cast<const float4*>(map + (((size_t)b * H + y) * W + x) * C + rem);
+    const float4 v = ld_map4(map, ((((size_t)b * H + y) * W + x) * C + rem) >> 2, h16);
     reinterpret_cast<float4*>(tok)[i] = v;
     if (tok16) reinterpret_cast<uint2*>(tok16)[i] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
   }
@@ -41,7 +42,7 @@ __global__ void tokenize_local_kernel(const float* __restrict__ map, float* __re
 // 4x4 block at (16ty+4ky, 16tx+4kx).  The two 2x2 means are taken in the reference's order.
 // =====================================================================================
 __global__ void tokenize_global_kernel(const float* __restrict__ map, float* __restrict__ tok,
-                                       __half* __restrict__ tok16, int B, int H, int W, int C) {
+                                       __half* __restrict__ tok16, int B, int H, int W, int C, bool h16 = false) {
   const int C4 = C >> 2;
   const int gy = H >> 4, gx = W >> 4;
   const long long total = (long long)B * gy * gx * 16 * C4;
@@ -54,7 +55,7 @@ __global__ void tokenize_global_kernel(const float* __restrict__ map, float* __r
     const int ty = (int)(r % gy);
     const int b = (int)(r / gy);
     const int y0 = ty * 16 + (kk >> 2) * 4, x0 = tx * 16 + (kk & 3) * 4;
-    const float* base = map + (((size_t)b * H + y0) * W + x0) * C + c4 * 4;
+    const size_t base4 = ((((size_t)b * H + y0) * W + x0) * C + c4 * 4) >> 2;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int qy = 0; qy < 2; ++qy)
@@ -65,8 +66,7 @@ __global__ void tokenize_global_kernel(const float* __restrict__ map, float* __r
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 2; ++dx) {
-            const float4 v = *reinterpret_cast<const float4*>(
-                base + ((size_t)(qy * 2 + dy) * W + (qx * 2 + dx)) * C);
+            const float4 v = ld_map4(map, base4 + ((((size_t)(qy * 2 + dy) * W + (qx * 2 + dx)) * C) >> 2), h16);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
           }
         acc.x += s.x * 0.25f; acc.y += s.y * 0.25f; acc.z += s.z * 0.25f; acc.w += s.w * 0.25f;

@@ -72,6 +72,9 @@ int64_t cfen_plan_launches_per_forward(const cfen_plan* plan); /* kernels per ma
 /* options: "timing" (0/1): bracket every kernel launch with CUDA events on the launching stream;
  * "timing_reset"; "gemm_path" 2 = fp16 tcgen05+TMA (default), 1 = TF32 tcgen05, 0 = TF32 mma.sync (env CFEN_GEMM_PATH) */
 int32_t cfen_plan_set_option(cfen_plan* plan, const char* name, int64_t value);
+/* Reads back an option; "maps16" (0 fp32 stage maps, 1 fp16 full-resolution maps, 2 every stage map fp16 - the
+ * element type behind cfen_plan_stage_ptr), "gemm_path", "conv_path", "fuse_front", "fuse_tail", "split_k". */
+int32_t cfen_plan_get_option(const cfen_plan* plan, const char* name, int64_t* value);
 /* JSON text with per-kernel-class {launches, ms, flops, bytes} of the last forward run with
  * "timing" on (algorithmic flops/bytes; used by bench.py's roofline).  Synchronises the device. */
 int32_t cfen_plan_profile_json(cfen_plan* plan, char* buf, int64_t cap);
@@ -96,7 +99,7 @@ int32_t cfen_forward_u8(cfen_plan* plan, int32_t batch, const uint8_t* in_hwc,
                         uint8_t* xr_hwc, uint8_t* xs_hwc, uint8_t* xd_hwc, void* stream);
 
 /* Debug/testing: device pointer + element count of a named internal NHWC stage buffer of the
- * last pass ("xf", "e1", "e2", "e3", "u3r", ...). */
+ * last pass ("xf", "e1", "e2", "e3", "u3r", ...); elements are fp16 when option "maps16" is 2, else fp32. */
 int32_t cfen_plan_stage_ptr(cfen_plan* plan, const char* name, void** dev_ptr, int64_t* numel);
 
 /* ---- per-kernel entry points (unit parity tests; same kernels the plan launches) ---- */

@@ -18,13 +18,17 @@ def ptr(t):
 
 
 class _RawCuda:
-    def __init__(self, p, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (p, False), "version": 2}
+    def __init__(self, p, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (p, False), "version": 2}
 
 
 def view_f32(p, n):
     """torch view over a raw device pointer owned by a plan (valid while the plan lives)."""
     return torch.as_tensor(_RawCuda(p, n), device="cuda")
+
+
+def view_f16(p, n):
+    return torch.as_tensor(_RawCuda(p, n, "<f2"), device="cuda")
 
 
 def local_tokens_ref(x, win):

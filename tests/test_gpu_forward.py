@@ -43,7 +43,8 @@ def _stage_report(gnet, size, taps, batch):
     for name in STAGE_ORDER:
         ref = taps[STAGE_TAPS[name]]
         p, per = plan.stage_ptr(name)
-        got = G.view_f32(p, per * batch).view(batch, ref.shape[2], ref.shape[3], ref.shape[1]).permute(0, 3, 1, 2)
+        view = G.view_f16 if plan.get_option("maps16") >= 2 else G.view_f32     # stage maps' storage type
+        got = view(p, per * batch).float().view(batch, ref.shape[2], ref.shape[3], ref.shape[1]).permute(0, 3, 1, 2)
         d = (got.cpu().double() - ref.double()).abs()
         rep[name] = {"max_abs": d.max().item(), "ref_absmax": ref.abs().max().item(),
                      "rel": d.max().item() / max(ref.abs().max().item(), 1e-30)}
