@@ -280,13 +280,16 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
       return v;
     };
     bool async_in = false;
-    if constexpr (S::LOADER == LD_NHWC) async_in = (a.flags & CF_IN16) != 0;
+    if constexpr (S::LOADER == LD_NHWC || S::LOADER == LD_CAT2) async_in = (a.flags & CF_IN16) != 0;
     if (async_in) {
       // fp16 map: the halo tile is copied global -> shared asynchronously (cp.async, zero-fill outside the image),
       // no registers and no conversion; the copy group is waited for together with the first weight chunk
-      constexpr int CH = S::CIN % 8 == 0 ? 8 : 4;          // halves per copy
-      constexpr int CPP = S::CIN / CH;
-      const __half* in16 = reinterpret_cast<const __half*>(a.in0) + img * S::CIN;
+      // (LD_CAT2: channel halves [0, CIN/2) / [CIN/2, CIN) come from the two source maps)
+      constexpr int CSRC = S::LOADER == LD_CAT2 ? S::CIN / 2 : S::CIN;   // channels per source map
+      constexpr int CH = CSRC % 8 == 0 ? 8 : 4;            // halves per copy
+      constexpr int CPP = CSRC / CH;
+      const __half* in16 = reinterpret_cast<const __half*>(a.in0) + img * CSRC;
+      const __half* in16b = S::LOADER == LD_CAT2 ? reinterpret_cast<const __half*>(a.in1) + img * CSRC : nullptr;
       for (int pix = tid; pix < C::IN_H * C::IN_W; pix += S::THREADS) {   // one pixel (all its chunks) per item
         const int iy = pix / C::IN_W, ix = pix - iy * C::IN_W;
         int gy = oy0 + iy, gx = ox0 + ix;
@@ -297,12 +300,19 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
         } else {
           inside = (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win;
         }
-        const __half* src = in16 + (inside ? (uint32_t)(gy * Win + gx) * S::CIN : 0u);
+        const uint32_t poff = inside ? (uint32_t)(gy * Win + gx) * CSRC : 0u;
         __half* dst = tile + pix * C::CPITCH;
 #pragma unroll
         for (int cc = 0; cc < CPP; ++cc) {
-          if (CH == 8) cp_async16(dst + cc * CH, src + (inside ? cc * CH : 0), inside);
-          else cp_async8(dst + cc * CH, src + (inside ? cc * CH : 0), inside);
+          if (CH == 8) cp_async16(dst + cc * CH, in16 + poff + (inside ? cc * CH : 0), inside);
+          else cp_async8(dst + cc * CH, in16 + poff + (inside ? cc * CH : 0), inside);
+        }
+        if constexpr (S::LOADER == LD_CAT2) {
+#pragma unroll
+          for (int cc = 0; cc < CPP; ++cc) {
+            if (CH == 8) cp_async16(dst + CSRC + cc * CH, in16b + poff + (inside ? cc * CH : 0), inside);
+            else cp_async8(dst + CSRC + cc * CH, in16b + poff + (inside ? cc * CH : 0), inside);
+          }
         }
       }
       cp_async_commit();
@@ -481,6 +491,19 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
           } else if (ok0) {            // [TH][TW][COUT]; COUT is even on every NHWC-output geometry
             *reinterpret_cast<float2*>(ost + (py * C::TW + pxa) * S::COUT + c) = make_float2(v[0], v[1]);
             *reinterpret_cast<float2*>(ost + (py * C::TW + pxb) * S::COUT + c) = make_float2(v[2], v[3]);
+          }
+        } else if ((flags & CF_OUT16) && !(flags & CF_RES)) {
+          // transposed phases, fp16 map out: lanes t and t^1 swap halves so that each stores 4 consecutive
+          // channels (8 bytes) of ONE pixel instead of 2 channels of two pixels (COUT is a multiple of 4)
+          const bool odd = (t & 1) != 0;
+          const float r0 = __shfl_xor_sync(0xffffffffu, odd ? v[0] : v[2], 1);
+          const float r1 = __shfl_xor_sync(0xffffffffu, odd ? v[1] : v[3], 1);
+          if (ok0) {
+            const int oy = 2 * (ty0 + py) + ry;
+            const int ox = 2 * (tx0 + (odd ? pxb : pxa)) + rx;
+            __half* o16 = reinterpret_cast<__half*>(a.out) + (((size_t)b * Hout + oy) * Wout + ox) * S::COUT + (odd ? c - 2 : c);
+            *reinterpret_cast<uint2*>(o16) = odd ? make_uint2(pack_half2(r0, r1), pack_half2(v[2], v[3]))
+                                                 : make_uint2(pack_half2(v[0], v[1]), pack_half2(r0, r1));
           }
         } else if (ok0) {              // transposed phases: NHWC, pixels (2y + ry, 2x + rx)
           const int oy = 2 * (ty0 + py) + ry;

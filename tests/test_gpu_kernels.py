@@ -348,18 +348,24 @@ def test_conv_strided(kind, cin, cout):
 
 
 @pytest.mark.parametrize("kind,cin,cout", [("up_96_48", 96, 48), ("up_48_24", 48, 24), ("up_24_12", 24, 12)])
-def test_conv_transposed(kind, cin, cout):
+@pytest.mark.parametrize("f16", [False, True])
+def test_conv_transposed(kind, cin, cout, f16):
+    """f16: fp16 NHWC maps in and out (cp.async loader / the SUM2 register loader, paired 8-byte stores)."""
     B, Hi = 2, 16
     x, w, b = dev(B, cin, Hi, 2 * Hi, seed=1), dev(cin, cout, 4, 4, seed=2, scale=0.1), dev(cout, seed=3)
     x2 = dev(B, cin, Hi, 2 * Hi, seed=7)
-    out = torch.empty(B, 2 * Hi, 4 * Hi, cout, device="cuda")
+    fmt = (256 | 512) if f16 else 0
+    cast = (lambda z: U.to_nhwc(z).half()) if f16 else U.to_nhwc
+    back = (lambda z: U.to_nchw(z.float()).double()) if f16 else (lambda z: U.to_nchw(z).double())
+    xi, x2i = cast(x), cast(x2)
+    out = torch.empty(B, 2 * Hi, 4 * Hi, cout, device="cuda", dtype=torch.float16 if f16 else torch.float32)
     if kind == "up_24_12":   # consumes block_out + xf (v3.py:696)
-        _conv(kind, U.to_nhwc(x), U.to_nhwc(x2), w, b, None, None, out, B, Hi, 2 * Hi, RELU | EXTRA_IN)
-        ref = torch.relu(F.conv_transpose2d((x + x2).double(), w.double(), b.double(), stride=2, padding=1))
+        _conv(kind, xi, x2i, w, b, None, None, out, B, Hi, 2 * Hi, RELU | EXTRA_IN | fmt)
+        ref = torch.relu(F.conv_transpose2d(back(xi) + back(x2i), w.double(), b.double(), stride=2, padding=1))
     else:
-        _conv(kind, U.to_nhwc(x), None, w, b, None, None, out, B, Hi, 2 * Hi, 0)
-        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2, padding=1)
-    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+        _conv(kind, xi, None, w, b, None, None, out, B, Hi, 2 * Hi, fmt)
+        ref = F.conv_transpose2d(back(xi), w.double(), b.double(), stride=2, padding=1)
+    assert U.rel_err(U.to_nchw(out.float()), ref) <= TF32_TOL
 
 
 IN16, OUT16, RES16 = 256, 512, 1024
@@ -410,6 +416,22 @@ def test_conv_fp16_map_chain_up_tail():
     assert (y.double() - ry).abs().max().item() <= TF32_TOL
     rd = F.conv2d(rc_got, wd.double(), bd.double(), stride=2, padding=1)
     assert U.rel_err(U.to_nchw(d), rd) <= TF32_TOL
+
+
+@pytest.mark.parametrize("kind,c", [("skip_96_48", 48), ("skip_48_24", 24)])
+def test_conv_skip_concat_fp16_maps(kind, c):
+    """CAT2 1x1 merge on fp16 maps: both halves arrive through cp.async, fp16 copy-out."""
+    B, H = 2, 32
+    a, s = dev(B, c, H, H, seed=1), dev(B, c, H, H, seed=2)
+    w, b = dev(c, 2 * c, 1, 1, seed=3, scale=0.1), dev(c, seed=4)
+    anw, anb = dev(c, seed=5, scale=0.3), dev(c, seed=6)
+    a16, s16 = U.to_nhwc(a).half(), U.to_nhwc(s).half()
+    out = torch.empty(B, H, H, c, device="cuda", dtype=torch.float16)
+    _conv(kind, a16, s16, w, b, anw, anb, out, B, H, H, RELU | EXTRA_IN | 256 | 512)
+    cat = torch.cat((U.to_nchw(a16.float()), U.to_nchw(s16.float())), 1).double()
+    ref = torch.relu((F.conv2d(cat, w.double(), b.double()) + anb.double().view(1, -1, 1, 1)) *
+                     torch.exp(anw.double()).view(1, -1, 1, 1))
+    assert U.rel_err(U.to_nchw(out.float()), ref) <= TF32_TOL
 
 
 @pytest.mark.parametrize("kind,c", [("skip_96_48", 48), ("skip_48_24", 24)])
