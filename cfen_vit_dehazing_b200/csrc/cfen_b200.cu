@@ -897,7 +897,7 @@ static int run_front16(Run& r, const VitW& v, const FrontSrc* src, const float* 
   RET(get_tmap2(r.p, QKV16, 2, M, 3 * E, 32, 128, &tq));
   Front16Args a{src ? src->map : T0, src ? (src->h16 ? 2 : 1) : 0, src ? src->H : 0, src ? src->W : 0, src ? src->C : 0,
                 src ? src->win : 0, v.b_le, v.pos, v.L, v.ln1g, v.ln1b, M};
-  Launch l(r, PC_GEMM, 8.0 * M * E * E, (double)M * E * (4 + 4 + 6) + 8.0 * E * E, "front16 M%d E%d", M, E);
+  Launch l(r, PC_GEMM, 8.0 * M * E * E, (double)M * E * ((src && src->h16 ? 2 : 4) + 4 + 6) + 8.0 * E * E, "front16 M%d E%d", M, E);
   CU(launch_front16(E, *twle, *twin, *tt1, *tq, a, r.st));
   return 0;
 }
@@ -1065,7 +1065,7 @@ static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, f
     CU(cudaGetLastError());
   }
   const long long total4 = (long long)r.nb * Hout * Wout * C / 4;
-  Launch l(r, PC_NORM, 0.0, 32.0 * total4);
+  Launch l(r, PC_NORM, 0.0, (all_maps16(p) ? 16.0 : 32.0) * total4);
   instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, r.ln->mean_rstd, Hout * Wout, C, total4,
                                                                all_maps16(p));
   CU(cudaGetLastError());
@@ -1078,7 +1078,7 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
   const int C = which == 0 ? 48 : 24, HW = H * W, parts = 64;
   const long long total4 = (long long)r.nb * HW * C / 4;
   {
-    Launch l(r, PC_CFSM, 0.0, 48.0 * total4);
+    Launch l(r, PC_CFSM, 0.0, (all_maps16(p) ? 24.0 : 48.0) * total4);
     if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW, all_maps16(p));
     else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW, all_maps16(p));
     CU(cudaGetLastError());
@@ -1089,7 +1089,7 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
     else cfsm_gate_kernel<24><<<r.nb, 128, 0, r.st>>>(r.ln->cfsm_part, p->cfsm_w[1], r.ln->gates, parts, HW);
     CU(cudaGetLastError());
   }
-  Launch l(r, PC_CFSM, 0.0, 64.0 * total4);
+  Launch l(r, PC_CFSM, 0.0, (all_maps16(p) ? 32.0 : 64.0) * total4);
   cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, r.ln->gates, out, HW, C, total4, all_maps16(p));
   CU(cudaGetLastError());
   return 0;
@@ -1109,7 +1109,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     r.st = L.gst;
     const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
     {
-      Launch l(r, PC_TOKENIZE, 0.0, 16.0 * n4 * 17, "tok_global H%d C%d", Hl, C);
+      Launch l(r, PC_TOKENIZE, 0.0, n4 * ((all_maps16(p) ? 8.0 : 16.0) * 16 + 16.0 + 8.0), "tok_global H%d C%d", Hl, C);
       tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.gws.t0, L.gws.x16, r.nb, Hl, Hl, C, all_maps16(p));
       CU(cudaGetLastError());
     }

@@ -25,8 +25,12 @@ namespace cfen {
 // wide-channel layers keep small tiles (accumulator registers, halo size).
 template <class S, bool BIG>
 struct Conv16Tile {
-  static constexpr int MR = (BIG && S::STRIDE == 1 && S::CIN <= 24 && S::COUT <= 24) ? 2 : 1;   // strided halos grow 2x per row
-  static constexpr int MC = (BIG && S::CIN <= 48 && S::COUT <= 48 && (S::STRIDE == 1 || S::CIN <= 12)) ? 2 : 1;   // strided halos: smem
+  // (transposed layers tile the INPUT map and their halo is +2 whatever the stride: they take the large tile too -
+  //  with the 8 x 16 tile the four phase weight sets of up_24_12 outweighed the input tile, r40: 67 TFLOP/s)
+  static constexpr bool UNIT = S::STRIDE == 1 || S::TRANSPOSED;
+  static constexpr int MR = (BIG && UNIT && S::CIN <= 24 && S::COUT <= 24) ? 2 : 1;   // strided halos grow 2x per row
+  static constexpr int MC = (BIG && ((S::CIN <= 48 && S::COUT <= 48 && (UNIT || S::CIN <= 12)) ||
+                                     (S::TRANSPOSED && S::CIN <= 96 && S::COUT <= 48))) ? 2 : 1;   // strided halos: smem
 };
 
 constexpr int c16_max(int a, int b) { return a > b ? a : b; }
