@@ -56,14 +56,21 @@ constexpr int c16_min(int a, int b) { return a < b ? a : b; }
 template <class S, bool BIG = true>
 struct Conv16 {
   static constexpr int MR = Conv16Tile<S, BIG>::MR, MC = Conv16Tile<S, BIG>::MC, MB = MR * MC;
-  static constexpr int TH = 8 * MR, TW = 16 * MC;            // CTA tile (output pixels; input pixels when transposed)
+  // Row-pair mode of the 7x7 tails (COUT = 3 or 1 fills 3 / 1 of the 8 MMA columns): one MMA row block computes
+  // YS = 2 vertically adjacent output rows at once.  The contraction window grows to (KS + YS - 1) x KS taps, the
+  // MMA columns are (row shift sy, output channel): B[sy * COUT + co][ky', kx, c] = w[co][c][ky' - sy][kx] (zero
+  // outside the kernel), so 56 tap steps yield 32 output pixels instead of 49 steps for 16 (1.75x fewer MMAs and
+  // ldmatrix loads; the A rows stay consecutive pixels, so ldmatrix stays conflict-free).
+  static constexpr int YS = (S::KS == 7 && !S::TRANSPOSED && S::STRIDE == 1 && S::COUT * 2 <= 8) ? 2 : 1;
+  static constexpr int NOUT = YS * S::COUT;                  // MMA output columns in use
+  static constexpr int TH = 8 * MR * YS, TW = 16 * MC;       // CTA tile (output pixels; input pixels when transposed)
   static constexpr int IN_H = S::TRANSPOSED ? TH + 2 : (TH - 1) * S::STRIDE + S::KS;
   static constexpr int IN_W = S::TRANSPOSED ? TW + 2 : (TW - 1) * S::STRIDE + S::KS;
   static constexpr int CIN_P = (S::CIN + 15) / 16 * 16;     // channels per pixel seen by the MMA (zero padded)
   static constexpr int CPITCH = CIN_P + 8;                  // halves between pixels: (2*CPITCH) % 128 is an odd multiple of 16
   static constexpr int KG = CIN_P / 16;                     // k16 steps per tap
   static constexpr int NPAD = S::NPAD, NT = S::NT;
-  static constexpr int KTAP = S::KTAP, NPHASE = S::NPHASE;
+  static constexpr int KTAP = YS > 1 ? (S::KS + YS - 1) * S::KS : S::KTAP, NPHASE = S::NPHASE;
   static constexpr int K_FULL = KTAP * CIN_P;               // contraction length per phase
   // weight chunk = whole taps; at most ~32 KB of smem per buffer
   static constexpr int TPC_MAX = (16384 / NPAD - 8) / CIN_P;
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
   for (int mb = 0; mb < C::MB; ++mb) {
     const int py = warp * C::MR + mb / C::MC, px = (mb % C::MC) * 16 + a_px;
     a_base[mb] = S::TRANSPOSED ? (py * C::IN_W + px) * C::CPITCH + a_k
-                               : ((py * S::STRIDE) * C::IN_W + px * S::STRIDE) * C::CPITCH + a_k;
+                               : ((py * S::STRIDE * C::YS) * C::IN_W + px * S::STRIDE) * C::CPITCH + a_k;
   }
   // B (x4), NT >= 2: matrices (n-tile j, k 0-7) (j, k 8-15) (j+1, k 0-7) (j+1, k 8-15);
   //          NT == 1: matrices (k-step s, k 0-7) (s, k 8-15) (s+1, k 0-7) (s+1, k 8-15)
@@ -464,9 +471,12 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
 #pragma unroll
     for (int j = 0; j < C::NT; ++j) {
       const int c = j * 8 + 2 * t;
-      const bool ok0 = c < S::COUT, ok1 = c + 1 < S::COUT;
-      const float s0 = ok0 ? a.scale[c] : 0.f, h0 = ok0 ? a.shift[c] : 0.f;
-      const float s1 = ok1 ? a.scale[c + 1] : 0.f, h1 = ok1 ? a.shift[c + 1] : 0.f;
+      const bool ok0 = c < C::NOUT, ok1 = c + 1 < C::NOUT;
+      // row-pair mode: MMA column n = (row shift, channel); otherwise n is the channel
+      const int co0 = C::YS > 1 ? c % S::COUT : c, co1 = C::YS > 1 ? (c + 1) % S::COUT : c + 1;
+      const int sy0 = C::YS > 1 ? c / S::COUT : 0, sy1 = C::YS > 1 ? (c + 1) / S::COUT : 0;
+      const float s0 = ok0 ? a.scale[co0] : 0.f, h0 = ok0 ? a.shift[co0] : 0.f;
+      const float s1 = ok1 ? a.scale[co1] : 0.f, h1 = ok1 ? a.shift[co1] : 0.f;
       float st_s0 = 0.f, st_s1 = 0.f, st_q0 = 0.f, st_q1 = 0.f;
 #pragma unroll
       for (int mb = 0; mb < C::MB; ++mb) {
@@ -490,8 +500,9 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
         }
         if constexpr (C::STAGED) {
           if (flags & CF_OUT_NCHW) {   // [COUT][TH][TW]
-            if (ok0) { ost[(c * C::TH + py) * C::TW + pxa] = v[0]; ost[(c * C::TH + py) * C::TW + pxb] = v[2]; }
-            if (ok1) { ost[((c + 1) * C::TH + py) * C::TW + pxa] = v[1]; ost[((c + 1) * C::TH + py) * C::TW + pxb] = v[3]; }
+            const int y0 = py * C::YS + sy0, y1 = py * C::YS + sy1;
+            if (ok0) { ost[(co0 * C::TH + y0) * C::TW + pxa] = v[0]; ost[(co0 * C::TH + y0) * C::TW + pxb] = v[2]; }
+            if (ok1) { ost[(co1 * C::TH + y1) * C::TW + pxa] = v[1]; ost[(co1 * C::TH + y1) * C::TW + pxb] = v[3]; }
           } else if (ok0) {            // [TH][TW][COUT]; COUT is even on every NHWC-output geometry
             *reinterpret_cast<float2*>(ost + (py * C::TW + pxa) * S::COUT + c) = make_float2(v[0], v[1]);
             *reinterpret_cast<float2*>(ost + (py * C::TW + pxb) * S::COUT + c) = make_float2(v[2], v[3]);
@@ -669,6 +680,8 @@ inline bool conv16_use_big(int H, int W) { return H % Conv16<S, true>::TH == 0 &
 template <class S>
 inline cudaError_t launch_conv16(const ConvArgs& a, const __half* wpack, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  // the row-pair mode only has the NCHW staged epilogue the tails use, and no statistics
+  if (Conv16<S>::YS > 1 && (!(a.flags & CF_OUT_NCHW) || a.stats)) return cudaErrorInvalidValue;
   if (conv16_use_big<S>(a.H, a.W)) {
     using C = Conv16<S, true>;
     dim3 grid(a.W / C::TW, a.H / C::TH, a.B);
@@ -701,7 +714,12 @@ __global__ void conv16_pack_kernel(const float* __restrict__ src, __half* __rest
     const int ph = i / (C::K_FULL * C::NPAD);
     const int tap = k / C::CIN_P, cin = k - tap * C::CIN_P;
     float v = 0.f;
-    if (n < S::COUT && cin < cin_src && cin < S::CIN) {
+    if (C::YS > 1) {   // row-pair mode: n = (sy, co), tap = (ky', kx) over the (KS + YS - 1) x KS window
+      const int co = n % S::COUT, sy = n / S::COUT;
+      const int kyp = tap / S::KS, kx = tap % S::KS, ky = kyp - sy;
+      if (n < C::NOUT && cin < cin_src && cin < S::CIN && ky >= 0 && ky < S::KS)
+        v = src[(((size_t)co * cin_src + cin) * S::KS + ky) * S::KS + kx];
+    } else if (n < S::COUT && cin < cin_src && cin < S::CIN) {
       if (S::TRANSPOSED) {
         const int ky = convt_kidx(ph >> 1, tap >> 1), kx = convt_kidx(ph & 1, tap & 1);
         v = src[(((size_t)cin * S::COUT + n) * 4 + ky) * 4 + kx];

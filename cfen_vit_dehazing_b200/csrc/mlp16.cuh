@@ -263,13 +263,17 @@ mlp16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const int c = w / MH, it = w >> 1;
       tc::mbar_wait(&s_full[g], it & 1);
       tc::tc_fence_after();
+      uint32_t vv[2][32];   // both halves of the chunk are requested before the single wait
+      tc::tmem_ld32(lane_addr + Cfg::S_COL0 + g * Cfg::HC, vv[0]);
+      tc::tmem_ld32(lane_addr + Cfg::S_COL0 + g * Cfg::HC + 32, vv[1]);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s_empty[g]);      // S is in registers: GEMM1 of item w + 2 may overwrite the slot now
       tc::mbar_wait(&f_empty[g], (it & 1) ^ 1);   // GEMM2 of the previous item on this slot has read F
       const float* b1 = a.b1 + c * Cfg::HC;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        uint32_t v[32];
-        tc::tmem_ld32(lane_addr + Cfg::S_COL0 + g * Cfg::HC + kb * 32, v);
-        tc::tmem_ld_wait();
+        uint32_t (&v)[32] = vv[kb];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {   // 8 columns -> one 16-byte chunk of fp16
           const float4 ba = *reinterpret_cast<const float4*>(b1 + kb * 32 + 8 * j);
@@ -282,8 +286,6 @@ mlp16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           *reinterpret_cast<uint4*>(fline + (((kb * 4 + j) ^ sw) << 4)) = o;
         }
       }
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s_empty[g]);      // S slot may be overwritten by GEMM1 of item w + 2
       tc::fence_async_smem();            // F writes visible to the tensor-core (async) proxy
       tc::mbar_arrive(&f_full[g]);
     }

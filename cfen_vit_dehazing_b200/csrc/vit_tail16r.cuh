@@ -253,14 +253,18 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
       tc::mbar_wait(&s_full[sl], it & 1);
       tc::tc_fence_after();
       if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 311);
+      uint8_t* fline = fbuf + sl * 16384 + roff;
+      uint32_t vv[2][32];   // both halves of the chunk are requested before the single wait
+      tc::tmem_ld32(lane_addr + S_COL0 + sl * HC, vv[0]);
+      tc::tmem_ld32(lane_addr + S_COL0 + sl * HC + 32, vv[1]);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s_empty[sl]);   // S slot is in registers: the next GEMM1 into it may start now
       tc::mbar_wait(&f_empty[sl], (it & 1) ^ 1);
       if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 312);
-      uint8_t* fline = fbuf + sl * 16384 + roff;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        uint32_t v[32];
-        tc::tmem_ld32(lane_addr + S_COL0 + sl * HC + kb * 32, v);
-        tc::tmem_ld_wait();
+        uint32_t (&v)[32] = vv[kb];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 ba = *reinterpret_cast<const float4*>(bias + kb * 32 + 8 * j);
@@ -273,8 +277,6 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
           *reinterpret_cast<uint4*>(fline + (((kb * 4 + j) ^ sw) << 4)) = o;
         }
       }
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s_empty[sl]);
       tc::fence_async_smem();
       tc::mbar_arrive(&f_full[sl]);
       if (q == 0 && lane == 0) tl_stamp(2 + g, tln, 313);
