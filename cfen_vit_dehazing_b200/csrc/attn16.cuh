@@ -21,6 +21,14 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// k = 8 variant for the 8-column tail of a head dimension that is 8 mod 16 (hd = 24): half the tensor work of a
+// zero-padded k = 16 step.  a0 = (row g, k 2t..2t+1), a1 = (row g+8, ...), b0 = (k 2t..2t+1, n g).
+__device__ __forceinline__ void mma_f16_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
 // two base-2 exponentials on a packed fp16 pair (one MUFU.EX2 for both)
 __device__ __forceinline__ uint32_t exp2_f16x2(uint32_t x) {
   uint32_t y;
@@ -130,10 +138,18 @@ attention16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int
       for (int e = 0; e < 4; ++e) { s[j][e] = 0.f; s[j + 1][e] = 0.f; }
 #pragma unroll
       for (int kk = 0; kk < KS; ++kk) {
-        uint32_t b[4];
-        ldmatrix_x4(b, ks + ((j + (lm_id >> 1)) * 8 + lm_row) * LD + kk * 16 + (lm_id & 1) * 8);
-        mma_f16_16x8x16(s[j], qa[kk], b[0], b[1]);
-        mma_f16_16x8x16(s[j + 1], qa[kk], b[2], b[3]);
+        if (HD % 16 == 8 && kk == KS - 1) {
+          // last 8 columns of the head: one k = 8 step per key tile; matrices (tile j, k 16..23), (tile j+1, k 16..23)
+          uint32_t b[2];
+          ldmatrix_x2(b, ks + ((j + (lm_id & 1)) * 8 + lm_row) * LD + kk * 16);
+          mma_f16_16x8x8(s[j], qa[kk][0], qa[kk][1], b[0]);
+          mma_f16_16x8x8(s[j + 1], qa[kk][0], qa[kk][1], b[1]);
+        } else {
+          uint32_t b[4];
+          ldmatrix_x4(b, ks + ((j + (lm_id >> 1)) * 8 + lm_row) * LD + kk * 16 + (lm_id & 1) * 8);
+          mma_f16_16x8x16(s[j], qa[kk], b[0], b[1]);
+          mma_f16_16x8x16(s[j + 1], qa[kk], b[2], b[3]);
+        }
       }
     }
     // ---- online softmax on the raw scores: the 1/sqrt(hd) * log2(e) factor is folded into the exponent FFMA
