@@ -1449,7 +1449,7 @@ extern "C" int32_t cfen_vit_front_f16(const float* src, int32_t src_is_map, int3
   const bool ok = make_tmap_2d(&twle, Wle16, 2, E, E, 64, E) && make_tmap_2d(&twin, Win16, 2, 3 * E, E, 64, 96) &&
                   make_tmap_2d(&tt1, T1, 4, M, E, 32, 128) && make_tmap_2d(&tq, QKV16, 2, M, 3 * E, 32, 128);
   if (!ok) return fail(11, "cfen_vit_front_f16: cuTensorMapEncodeTiled failed");
-  Front16Args a{src, src_is_map != 0, H, W, C, win, b_le, pos, L, ln_g, ln_b, M};
+  Front16Args a{src, src_is_map == 2 ? 2 : (src_is_map != 0 ? 1 : 0), H, W, C, win, b_le, pos, L, ln_g, ln_b, M};
   CU(launch_front16(E, twle, twin, tt1, tq, a, static_cast<cudaStream_t>(stream)));
   return 0;
 }

@@ -199,15 +199,28 @@ vit_front16_kernel(const __grid_constant__ CUtensorMap tmWle, const __grid_const
     constexpr int PB = 3;
 #pragma unroll 1
     for (int i0 = 0; i0 < NP; i0 += PB) {
-      float4 t[PB][8];
+      float4 t[PB][8];     // fp32 source: 8 x 16 B per panel
+      uint4 raw[PB][4];    // fp16 map: 4 x 16 B (8 halves) per panel - the halves are also the GEMM operand as they are
+      if (h16) {
+        const uint4* src16 = reinterpret_cast<const uint4*>(a.src);
 #pragma unroll
-      for (int ii = 0; ii < PB; ++ii)
+        for (int ii = 0; ii < PB; ++ii)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int f = 32 * (i0 + ii) + 4 * j;
-          const size_t off = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
-          t[ii][j] = valid ? ld_map4(a.src, off >> 2, h16) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int j = 0; j < 4; ++j) {
+            const int f = 32 * (i0 + ii) + 8 * j;          // segments are multiples of 8 elements long and aligned
+            const size_t off = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
+            raw[ii][j] = valid ? __ldg(src16 + (off >> 3)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+      } else {
+#pragma unroll
+        for (int ii = 0; ii < PB; ++ii)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int f = 32 * (i0 + ii) + 4 * j;
+            const size_t off = f < E / 2 ? seg0 + f : seg1 + (f - E / 2);
+            t[ii][j] = valid ? __ldg(reinterpret_cast<const float4*>(a.src) + (off >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      }
       if (i0 == 0) {   // pull the same rows of the tile that runs one wave later into L2
         const int mp = m + 128 * C::MIN_CTAS * 148;
         if (mp < a.M) {
@@ -232,9 +245,20 @@ vit_front16_kernel(const __grid_constant__ CUtensorMap tmWle, const __grid_const
           const int f = 32 * i + 4 * j;
           const float4 ps = __ldg(reinterpret_cast<const float4*>(posrow + f));
           const float4 bb = __ldg(reinterpret_cast<const float4*>(a.ble + f));
-          const float4 x = t[ii][j];
-          hx[2 * j] = pack_half2(x.x, x.y);
-          hx[2 * j + 1] = pack_half2(x.z, x.w);
+          float4 x;
+          if (h16) {
+            const uint32_t w0 = (j & 1) ? raw[ii][j >> 1].z : raw[ii][j >> 1].x;
+            const uint32_t w1 = (j & 1) ? raw[ii][j >> 1].w : raw[ii][j >> 1].y;
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
+            hx[2 * j] = w0;
+            hx[2 * j + 1] = w1;
+          } else {
+            x = t[ii][j];
+            hx[2 * j] = pack_half2(x.x, x.y);
+            hx[2 * j + 1] = pack_half2(x.z, x.w);
+          }
           v[4 * j + 0] = __float_as_uint(x.x + (ps.x + bb.x)); v[4 * j + 1] = __float_as_uint(x.y + (ps.y + bb.y));
           v[4 * j + 2] = __float_as_uint(x.z + (ps.z + bb.z)); v[4 * j + 3] = __float_as_uint(x.w + (ps.w + bb.w));
         }

@@ -143,8 +143,8 @@ int32_t cfen_vit_tail_f16(const void* O16, const float* T, const void* Wout16, c
                           const float* b2, const void* M0_16, const float* bm0, const void* M3_16,
                           const float* bm3, float* Y, int32_t M, int32_t E, int32_t hid, void* stream);
 /* First half of a local ViT call as one kernel (E in {96,192}; v3.py:1140-1160, 1382-1384):
- *   x = token rows (src_is_map: 2x2-patch tokens of win x win windows gathered from the NHWC map [B,H,W,C], C = E/4,
- *       feature order (ky,kx,c); else the token matrix src[M,E]);
+ *   x = token rows (src_is_map 1 / 2: 2x2-patch tokens of win x win windows gathered from the fp32 / fp16 NHWC map
+ *       [B,H,W,C], C = E/4, feature order (ky,kx,c); 0: the fp32 token matrix src[M,E]);
  *   T1[M,E] = x + fp16(x) Wle16^T + b_le + pos[row % L];  QKV16[M,3E] = fp16(LayerNorm(T1)) Win16^T.
  * M must equal B*(H/win)*(W/win)*L in map mode. */
 int32_t cfen_vit_front_f16(const float* src, int32_t src_is_map, int32_t B, int32_t H, int32_t W, int32_t C,

@@ -188,14 +188,17 @@ def test_vit_tail_f16(M, E, hid, inplace):
     assert U.rel_err(Y, ref) <= 5e-4             # three fp16 roundings of on-chip operands (ties may flip)
 
 
-@pytest.mark.parametrize("B,H,C,win,from_map", [(2, 64, 24, 32, True), (3, 32, 48, 16, True), (1, 64, 24, 32, False),
-                                                 (5, 32, 48, 32, True), (2, 96, 24, 32, True), (1, 32, 48, 16, False)])
+@pytest.mark.parametrize("B,H,C,win,from_map", [(2, 64, 24, 32, 1), (3, 32, 48, 16, 1), (1, 64, 24, 32, 0),
+                                                 (5, 32, 48, 32, 1), (2, 96, 24, 32, 1), (1, 32, 48, 16, 0),
+                                                 (2, 64, 24, 32, 2), (3, 32, 48, 16, 2), (2, 96, 24, 32, 2)])
 def test_vit_front_f16(B, H, C, win, from_map):
     """window gather + linear_encoding (+x, +pos) + LayerNorm + in-projection in one kernel (residual in TMEM) vs
     fp64 torch with the kernel's fp16 operand roundings; map mode reads the NHWC map, token mode a token matrix."""
     L = _native.lib()
     E, Lw = 4 * C, (win // 2) ** 2
     x = dev(B, C, H, H, seed=1, scale=2.0)
+    if from_map == 2:
+        x = x.half().float()                              # the map is stored as fp16: its values are the operand
     tok = G.local_tokens_ref(x, win)                      # [M, E], feature order (ky,kx,c)
     M = tok.shape[0]
     if not from_map:
@@ -212,7 +215,7 @@ def test_vit_front_f16(B, H, C, win, from_map):
     qkv = r16(F.layer_norm(t1, (E,), g.double(), b.double(), 1e-5)) @ Win16.double().t()
     T1 = torch.full((M, E), float("nan"), device="cuda")
     Q16 = torch.full((M, 3 * E), float("nan"), device="cuda", dtype=torch.float16)
-    src = U.to_nhwc(x) if from_map else tok
+    src = (U.to_nhwc(x).half() if from_map == 2 else U.to_nhwc(x)) if from_map else tok
     G.check(L.cfen_vit_front_f16(G.ptr(src), int(from_map), B, H, H, C, win, G.ptr(Wle16), G.ptr(ble), G.ptr(pos), Lw,
                                  G.ptr(g), G.ptr(b), G.ptr(Win16), G.ptr(T1), G.ptr(Q16), M, E, G.stream()))
     torch.cuda.synchronize()
