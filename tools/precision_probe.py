@@ -36,7 +36,9 @@ ROUND = {"f32": lambda x: x, "tf32": r_tf32, "f16": r_f16, "bf16": r_bf16}
 
 
 @contextlib.contextmanager
-def patched(lin_a, lin_w, conv, attn):
+def patched(lin_a, lin_w, conv, attn, t1_16=False):
+    """t1_16: the residual stream the first fused token kernel hands to the second (t1 = x + LE(x) + pos) is stored
+    as fp16 in HBM: LayerNorm / in-projection still see the fp32 value, the residual adds see the rounded one."""
     lin0, conv0, convt0, sm0 = F.linear, F.conv2d, F.conv_transpose2d, torch.softmax
     ra, rw, rc, rt = ROUND[lin_a], ROUND[lin_w], ROUND[conv], ROUND[attn]
 
@@ -67,6 +69,8 @@ def patched(lin_a, lin_w, conv, attn):
         s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))
         att = rt(torch.softmax(s, dim=-1))
         o = (att @ v).transpose(1, 2).reshape(n, l, e)
+        if t1_16:
+            t = r_f16(t)
         t = t + F.linear(o, sd[enc + ".self_attn.out_proj.weight"])
         h = F.layer_norm(t, (e,), sd[enc + ".norm2.weight"], sd[enc + ".norm2.bias"], 1e-5)
         h = F.relu(F.linear(h, sd[enc + ".linear1.weight"], sd[enc + ".linear1.bias"]))
@@ -115,6 +119,7 @@ def maps16(on, tokens16=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--maps16", action="store_true", help="also run 'f16 everywhere' with fp16 map storage")
+    ap.add_argument("--t1-16", action="store_true", help="with --maps16: also store the t1 residual stream as fp16")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--hr", type=int, default=4)
     ap.add_argument("--seeds", type=int, nargs="+", default=[1, 2])
@@ -144,6 +149,12 @@ def main():
             worst = max((o - r).abs().max().item() / 2 for o, r in zip(out, ref))
             ps = min(orc.psnr01(o, r) for o, r in zip(out, ref))
             print("seed %d  %-38s max|d| on [0,1] = %.5f   min PSNR = %.1f dB" % (seed, "f16 everywhere + fp16 maps", worst, ps), flush=True)
+            if a.t1_16:
+                with patched("f16", "f16", "f16", "f16", t1_16=True), maps16(True):
+                    out = orc.forward(sd, x1)
+                worst = max((o - r).abs().max().item() / 2 for o, r in zip(out, ref))
+                ps = min(orc.psnr01(o, r) for o, r in zip(out, ref))
+                print("seed %d  %-38s max|d| on [0,1] = %.5f   min PSNR = %.1f dB" % (seed, "... + fp16 t1 residual stream", worst, ps), flush=True)
 
 
 if __name__ == "__main__":
