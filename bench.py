@@ -405,7 +405,9 @@ def run_ours(args):
                        "algorithmic_gflop_per_image": FLOPS_PER_IMAGE.get((size, hr), 0) / 1e9},
             "clocks": clocks.summary(),
             "e2e": {"value": images / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "api": "dec_ipt.forward_host(pinned [B,3,H,W] fp32, out=pinned [xr,xs,xd], defer_sync=True) per step, "
+                           "host_sync() before the closing event: every H2D and D2H lies inside the timed region"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roof,
             "kernel_breakdown": breakdown,
