@@ -4,15 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one forward pass of the generator over one per-GPU batch of synthetic hazy images
-(BASELINE.json configs[3]: v3, hidden_dim_ratio=4, 512x512, image-sharded with replicated weights
-and no collective on the data path => weak scaling, per-GPU batch fixed).  `value` is whole-job
-images/s with inputs resident in HBM; `e2e` is the same metric through the public module API with
-pinned HOST inputs and outputs (H2D + D2H inside the timed region).  Rank 0 prints ONE JSON line.
+A "step" is one forward pass of the generator over the workload's GLOBAL batch of synthetic hazy images, sharded
+256/N images per GPU with replicated weights and no collective on the data path (BASELINE.json configs[3]: v3,
+hidden_dim_ratio=4, 512x512, batch 256 => "scaling": "strong", the total work is fixed as N grows).  --hr 2 selects
+configs[2] (batch 32), --size 1024 configs[4] (batch 16).  --batch B fixes the PER-GPU batch instead (weak scaling,
+labelled as such; not a BASELINE config).  `value` is whole-job images/s with inputs resident in HBM; `e2e` is the
+same metric through the public module API with pinned HOST inputs and outputs (H2D + D2H inside the timed region).
+Rank 0 prints ONE JSON line.
 
---impl reference times the reference algorithm's CPU implementation (the oracle port of
-models/networks_iid_hlgvit_crs_gd4_cfs_v3.py; the reference checkout itself does not travel to the
-GPU box) on the host cores, one image per step.
+--impl reference times the reference's own CPU implementation of the path on the host cores, one image per step:
+the UNMODIFIED reference sources from baseline/_ref (installed by __graft_entry__.build() from /root/reference;
+git-ignored, travels with gpurun) through define_G(gpu_ids=[]) -> dec_ipt.forward; when baseline/_ref is absent,
+the oracle port (oracle/cfen_oracle.py) and `cpu_baseline.kind` says "port".
 """
 import argparse
 import contextlib
@@ -40,8 +43,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("CFEN_BENCH_BATCH", 128)),
-                    help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="images per GPU per step (weak scaling); default: the BASELINE config's global batch / N")
     ap.add_argument("--size", type=int, default=SIZE)
     ap.add_argument("--hr", type=int, default=HR)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -116,26 +119,54 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_forward(size, hr, seconds_budget=20.0, min_iters=3, max_iters=30):
-    """Times the oracle port of the reference forward on the host cores (B=1)."""
+# BASELINE.json configs: (size, hidden_dim_ratio) -> (global batch, label)
+BASELINE_CONFIGS = {(512, 4): (256, "configs[3]"), (512, 2): (32, "configs[2]"), (1024, 4): (16, "configs[4]")}
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def cpu_forward_fn(size, hr):
+    """The reference's CPU forward for one image, primed (ActNorm initialised by a first forward), plus its kind:
+    "reference" = the unmodified reference sources under baseline/_ref (define_G(gpu_ids=[]) -> dec_ipt.forward,
+    models/networks_iid_hlgvit_crs_gd4_cfs_v3.py:93-100, 392-1020), "port" = the oracle restatement."""
     import torch
-    import cfen_vit_dehazing_b200 as prod
     from oracle import cfen_oracle as orc
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     opt = orc.default_opt(hr, size)
+    x0, x1 = orc.make_inputs(size, [1, 1])
+    if os.path.exists(os.path.join(REF_DIR, "models", "networks_iid_hlgvit_crs_gd4_cfs_v3.py")):
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        from models import common as rcommon
+        from models import networks_iid_hlgvit_crs_gd4_cfs_v3 as rv3
+        torch.manual_seed(1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = rv3.define_G(opt, rcommon.default_conv)
+        with torch.no_grad():
+            net(x0)                                               # primes ActNorm (models/actnorm.py:25-37) + warm-up
+
+        def step():
+            with torch.no_grad():
+                return net(x1)
+        return step, "reference", threads
+    import cfen_vit_dehazing_b200 as prod
     torch.manual_seed(1)
     with contextlib.redirect_stdout(io.StringIO()):
-        net = prod.define_G(opt, prod.common.default_conv)   # parameter containers only
-    x0, x1 = orc.make_inputs(size, [1, 1])
-    sd = orc.prime(net.state_dict(), x0)                       # also the warm-up forward
+        net = prod.define_G(opt, prod.common.default_conv)       # parameter containers only
+    sd = orc.prime(net.state_dict(), x0)                          # also the warm-up forward
+    return (lambda: orc.forward(sd, x1)), "port", threads
+
+
+def cpu_reference_forward(size, hr, seconds_budget=20.0, min_iters=3, max_iters=30):
+    """Times the reference's CPU forward on the host cores (B=1), a bounded sample."""
+    step, kind, threads = cpu_forward_fn(size, hr)
     times = []
     t_end = time.time() + seconds_budget
     while len(times) < min_iters or (time.time() < t_end and len(times) < max_iters):
         t = time.perf_counter()
-        orc.forward(sd, x1)
+        step()
         times.append(time.perf_counter() - t)
-    return times, threads
+    return times, threads, kind
 
 
 def cpu_model_name():
@@ -152,36 +183,31 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    import torch
-    from oracle import cfen_oracle as orc
-    import cfen_vit_dehazing_b200 as prod
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    opt = orc.default_opt(args.hr, args.size)
-    torch.manual_seed(1)
-    with contextlib.redirect_stdout(io.StringIO()):
-        net = prod.define_G(opt, prod.common.default_conv)
-    x0, x1 = orc.make_inputs(args.size, [1, 1])
-    sd = orc.prime(net.state_dict(), x0)
+    step, kind, threads = cpu_forward_fn(args.size, args.hr)
     for _ in range(max(0, args.warmup)):
-        orc.forward(sd, x1)
+        step()
     times = []
     for _ in range(args.steps):
         t = time.perf_counter()
-        orc.forward(sd, x1)
+        step()
         times.append(time.perf_counter() - t)
     total = sum(times)
     val = args.steps / total
-    sample = "1 image (1x3x%dx%d) per step, %d steps, fp32, torch CPU %d threads" % (args.size, args.size,
-                                                                                    args.steps, threads)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    gb, per_gpu, scaling = batch_plan(args, world)
+    sample = "bounded sample of the workload: 1 image (1x3x%dx%d) per step, %d steps, fp32, torch CPU %d threads" % (
+        args.size, args.size, args.steps, threads)
     line = {
         "impl": "reference", "metric": "images_per_s_%dx%d" % (args.size, args.size), "value": val,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "cpu_model": cpu_model_name(),
-                   "note": "oracle port of the reference forward (reference checkout does not travel to the GPU box)"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+        "config": {"workload": workload_name(args, gb), "global_batch": gb, "sample": sample,
+                   "cpu_model": cpu_model_name(),
+                   "note": ("unmodified reference sources (baseline/_ref): define_G(gpu_ids=[]) -> dec_ipt.forward"
+                            if kind == "reference" else
+                            "oracle port of the reference forward (baseline/_ref absent on this box)")},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample,
                          "p50_s": statistics.median(times), "min_s": min(times)},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -189,36 +215,96 @@ def run_reference(args):
 
 
 def kernels_from_trace(path):
-    """Per-launch CSV (class, tag, us, gflop, mbytes) -> {kernel-at-shape: totals}.  The three decoder branches run
-    the same kernels at the same shapes under different layer names: those are one kernel here."""
+    """Per-launch CSV (class, tag, us, gflop, mbytes, kernel) -> ({kernel symbol: totals}, {kernel-at-shape: totals}).
+    The first groups by the kernel SYMBOL (template arguments included, every shape and layer it ran at summed):
+    that is what the roofline line reports.  The second keeps one entry per shape for the breakdown; the three
+    decoder branches run the same kernels at the same shapes under different layer names: those are one entry."""
     import csv
     import re
-    out = {}
+    by_sym, by_shape = {}, {}
     for r in csv.DictReader(open(path)):
         tag = re.sub(r"(tail_|_d0\d)[RSDrsd]\b", r"\1*", r["tag"]) or r["class"]
-        k = out.setdefault(tag, {"class": r["class"], "us": 0.0, "gflop": 0.0, "mbytes": 0.0, "launches": 0})
-        k["us"] += float(r["us"]); k["gflop"] += float(r["gflop"]); k["mbytes"] += float(r["mbytes"]); k["launches"] += 1
-    return out
+        sym = r.get("kernel") or tag.split(" ")[0]
+        for table, key in ((by_sym, sym), (by_shape, tag)):
+            k = table.setdefault(key, {"class": r["class"], "us": 0.0, "gflop": 0.0, "mbytes": 0.0, "launches": 0,
+                                       "kernel": sym, "units": 0.0})
+            k["us"] += float(r["us"]); k["gflop"] += float(r["gflop"]); k["mbytes"] += float(r["mbytes"])
+            k["launches"] += 1
+            k["units"] += launch_units(r["tag"])
+    return by_sym, by_shape
 
 
-def ncu_traffic(table, name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `name`, from one ncu --set full capture of the same
-    kernel (bytes per row / pixel recorded in profiles/ncu_traffic.json) scaled to this launch's row count."""
+def launch_units(tag):
+    """Work units of one launch, from its tag: token rows (M / n*L) or output-tile pixels (HxW)."""
     import re
-    for key, ent in table.items():
-        if name.startswith(key.split(" ")[0]) and all(tok in name for tok in key.split(" ")[1:]):
-            m = re.search(r"\bM(\d+)", name)
-            px = re.search(r"(\d+)x(\d+)$", name)
-            units = int(m.group(1)) if m else (int(px.group(1)) * int(px.group(2)) * ent.get("images", 1) if px else None)
-            if units is None:
-                return None
-            return ent["bytes_per_unit"] * units
-    return None
+    m = re.search(r"\bM(\d+)", tag)
+    if m:
+        return float(m.group(1))
+    m = re.search(r"\bn(\d+) L(\d+)", tag)
+    if m:
+        return float(m.group(1)) * float(m.group(2))
+    m = re.search(r"(\d+)x(\d+)(?: b(\d+))?", tag)
+    if m:
+        return float(m.group(1)) * float(m.group(2)) * float(m.group(3) or 1)
+    return 0.0
 
 
-def workload_name(args):
-    return ("v3 generator (iid_hlgvit_crs_gd4_cfs_v3) n_feats=24 hidden_dim_ratio=%d, %dx%d, per-GPU batch %d "
-            "(BASELINE configs[3]: image-sharded, replicated weights)" % (args.hr, args.size, args.size, args.batch))
+def ncu_traffic(table, sym, units, launches):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of kernel `sym`: bytes per work unit (token row or
+    pixel x image) measured by one `ncu --set full` capture of that kernel (profiles/ncu_traffic.json) times the
+    units an average launch of the timed region processed."""
+    ent = table.get(sym)
+    if not ent or not launches or not units:
+        return None
+    return ent["bytes_per_unit"] * units / launches
+
+
+def batch_plan(args, world):
+    """(global batch, per-GPU batch, scaling) of this run."""
+    if args.batch is not None:
+        return args.batch * world, args.batch, "weak"
+    gb = BASELINE_CONFIGS.get((args.size, args.hr), (256, None))[0]
+    if gb % world:
+        raise SystemExit("global batch %d does not shard over %d GPUs" % (gb, world))
+    return gb, gb // world, "strong"
+
+
+def workload_name(args, global_batch):
+    cfg = BASELINE_CONFIGS.get((args.size, args.hr))
+    label = ("BASELINE %s" % cfg[1]) if (cfg and cfg[0] == global_batch and args.batch is None) else \
+        "not a BASELINE config: per-GPU batch fixed by --batch"
+    return ("v3 generator (iid_hlgvit_crs_gd4_cfs_v3) n_feats=24 hidden_dim_ratio=%d, %dx%d, global batch %d "
+            "image-sharded over the GPUs, replicated weights (%s)" % (args.hr, args.size, args.size, global_batch, label))
+
+
+def roofline_of(d, peaks):
+    """Roofline entry of one kernel's totals: bound by whichever of tensor peak / HBM peak takes longer on its
+    algorithmic flops / bytes."""
+    t_s = d["us"] / 1e6
+    tf = d["gflop"] * 1e9 / t_s / 1e12 if t_s > 0 else 0.0
+    gbs = d["mbytes"] * 1e6 / t_s / 1e9 if t_s > 0 else 0.0
+    tensor_bound = d["gflop"] * 1e9 / (peaks["tf_sustained"] * 1e12) >= d["mbytes"] * 1e6 / (peaks["hbm_gbs"] * 1e9)
+    if tensor_bound:
+        return {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": tf / peaks["tf_sustained"]}
+    return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+
+
+def parity_vs_oracle(net, x_host, out, hr, size, picks):
+    """max|diff| on the [0,1] scale and PSNR of the timed batch's own outputs against the CPU oracle on the same
+    weights, for a sample of its images (images are independent)."""
+    from oracle import cfen_oracle as orc
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    worst, psnr = 0.0, 1e9
+    for i in picks:
+        ref = orc.forward(sd, x_host[i:i + 1])
+        for a, b in zip(out, ref):
+            a = a[i:i + 1].detach().cpu()
+            worst = max(worst, (a.double() - b.double()).abs().max().item() / 2.0)
+            psnr = min(psnr, orc.psnr01(a, b))
+    return {"max_abs_err_01": worst, "min_psnr_db": psnr, "images_checked": list(picks), "gate": "<= 1e-2 and >= 45 dB",
+            "pass": bool(worst <= 1e-2 and psnr >= 45.0),
+            "against": "oracle/cfen_oracle.py (pinned to the reference's outputs, tests/golden) on this run's weights"}
 
 
 def run_ours(args):
@@ -253,7 +339,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    size, hr, B = args.size, args.hr, args.batch
+    size, hr = args.size, args.hr
+    global_batch, B, scaling = batch_plan(args, world)
     opt = make_opt(hr, size)
     torch.manual_seed(1)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -294,16 +381,17 @@ def run_ours(args):
         barrier()
         ms_instrumented = p0.elapsed_time(p1)
         prof = plan.profile()
-        kernels = {}
+        kernels, shapes = {}, {}
         if rank == 0:
             import tempfile
             trace_path = os.environ.get("CFEN_BENCH_TRACE") or os.path.join(tempfile.gettempdir(), "cfen_trace_%d.csv" % os.getpid())
             plan.profile_trace(trace_path)
-            kernels = kernels_from_trace(trace_path)
+            kernels, shapes = kernels_from_trace(trace_path)
         plan.set_option("timing", 0)
         chunks = (B + plan.max_batch - 1) // plan.max_batch
         launches_per_step = plan.launches_per_forward * chunks
         finite = all(bool(torch.isfinite(o).all()) for o in out)
+        parity = parity_vs_oracle(net, host_in, out, hr, size, sorted({0, B - 1})) if rank == 0 else None
 
         # ---------------- end to end through the module API with host buffers
         host_outs = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in out] for _ in range(2)]
@@ -367,27 +455,29 @@ def run_ours(args):
         peaks = measured_peaks()
         images = B * world * args.steps
         value = images / (ms_total / 1e3)
-        # dominant kernel (one kernel at one shape, summed over its launches of the timed region) -> roofline
+        # dominant kernel = the kernel SYMBOL with the largest total time over the instrumented pass of the same K
+        # steps (all shapes and layers it ran at summed); roofline_all lists every kernel the same way
+        t_all = max(1e-9, sum(k["us"] for k in kernels.values()))
+        traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        traffic_table = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+        roofline_all = []
+        for sym, d in sorted(kernels.items(), key=lambda kv: -kv[1]["us"]):
+            e = roofline_of(d, peaks)
+            e.update({"kernel": sym, "share_of_step": d["us"] / t_all, "launches": d["launches"],
+                      "avg_launch_us": d["us"] / max(1, d["launches"]),
+                      "traffic": ncu_traffic(traffic_table, sym, d["units"], d["launches"])})
+            roofline_all.append(e)
         name, d = max(kernels.items(), key=lambda kv: kv[1]["us"])
         nl = max(1, d["launches"])
-        t_s = d["us"] / 1e6
-        tf = d["gflop"] * 1e9 / t_s / 1e12 if t_s > 0 else 0.0
-        gbs = d["mbytes"] * 1e6 / t_s / 1e9 if t_s > 0 else 0.0
-        tensor_bound = d["gflop"] * 1e9 / (peaks["tf_sustained"] * 1e12) >= d["mbytes"] * 1e6 / (peaks["hbm_gbs"] * 1e9)
-        roof = ({"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                 "frac": tf / peaks["tf_sustained"]} if tensor_bound else
-                {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                 "frac": gbs / peaks["hbm_gbs"]})
-        roof.update({"kernel": name, "traffic": None, "launches": d["launches"],
-                     "avg_launch_us": d["us"] / nl, "share_of_step": d["us"] / max(1e-9, sum(k["us"] for k in kernels.values())),
-                     "algorithmic_gflop_per_launch": d["gflop"] / nl, "algorithmic_mbytes_per_launch": d["mbytes"] / nl,
+        roof = dict(roofline_all[0])
+        roof.update({"algorithmic_gflop_per_launch": d["gflop"] / nl, "algorithmic_mbytes_per_launch": d["mbytes"] / nl,
                      "peak_source": peaks["source"],
-                     "note": "algorithmic flops/bytes per launch over CUDA-event launch time (second, instrumented "
-                             "pass of the same K steps); tensor peak = measured dense bf16 (sustained); traffic = ncu "
-                             "dram bytes per launch scaled to this launch's rows (profiles/ncu_traffic.json)"})
-        traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(traffic_file):
-            roof["traffic"] = ncu_traffic(json.load(open(traffic_file)), name)
+                     "shapes": {k: {"us_per_launch": v["us"] / max(1, v["launches"]), "launches": v["launches"]}
+                                for k, v in shapes.items() if v["kernel"] == name},
+                     "note": "dominant kernel by symbol; algorithmic flops/bytes summed over its launches / CUDA-event "
+                             "launch time (second, instrumented pass of the same K steps, launches serialised); "
+                             "tensor peak = measured dense bf16 (sustained); traffic = ncu dram bytes per work unit "
+                             "(profiles/ncu_traffic.json) x units of an average launch, null without a capture"})
         tprof = sum(v["ms"] for v in prof.values())
         breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / tprof if tprof else 0,
                          "launches_per_step": v["launches"] / args.steps,
@@ -397,9 +487,10 @@ def run_ours(args):
         line = {
             "metric": "images_per_s_%dx%d" % (size, size), "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (10-bit mantissa, as TF32)", "data": "synthetic",
-            "config": {"workload": workload_name(args), "images_per_pass": plan.max_batch, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "config": {"workload": workload_name(args, global_batch), "images_per_pass": plan.max_batch,
+                       "global_batch": global_batch, "per_gpu_batch": B, "parallelism": "dp%d" % world,
                        "l2": "inputs_larger_than_l2 (%.0f MB per step per GPU)" % (h2d / 1e6),
                        "weights": "seeded random init (seed 1), ActNorm initialised by the first GPU forward",
                        "algorithmic_gflop_per_image": FLOPS_PER_IMAGE.get((size, hr), 0) / 1e9},
@@ -410,19 +501,22 @@ def run_ours(args):
                            "host_sync() before the closing event: every H2D and D2H lies inside the timed region"},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roof,
+            "roofline_all": roofline_all,
             "kernel_breakdown": breakdown,
             "whole_net_tflops": value / world * FLOPS_PER_IMAGE.get((size, hr), 0) / 1e12,
             "ms_per_step_instrumented": ms_instrumented / args.steps,
             "outputs_finite": finite,
+            "parity": parity,
         }
         if lat:
             line["latency_batch1"] = lat
         if world == 1 and not args.no_cpu_baseline:
-            times, threads = cpu_reference_forward(size, hr)
+            times, threads, kind = cpu_reference_forward(size, hr)
             line["cpu_baseline"] = {
-                "value": 1.0 / statistics.median(times), "unit": "images/s", "cores": threads, "kind": "port",
-                "sample": "%d forwards of 1x3x%dx%d (BASELINE configs[0]) on %s, torch CPU fp32" % (
-                    len(times), size, size, cpu_model_name()),
+                "value": 1.0 / statistics.median(times), "unit": "images/s", "cores": threads, "kind": kind,
+                "sample": "%d forwards of 1x3x%dx%d (BASELINE configs[0]) on %s, torch CPU fp32, %s" % (
+                    len(times), size, size, cpu_model_name(),
+                    "unmodified reference sources from baseline/_ref" if kind == "reference" else "oracle port"),
                 "p50_s": statistics.median(times), "min_s": min(times)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -7,6 +7,8 @@ fallback: if the library is missing every entry point raises ``RuntimeError``.
 import ctypes
 import os
 
+import torch
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CFEN_LIB selects an instrumented build of the same library (csrc/build.py --timeline) for the profiling tools
 LIB_PATH = os.environ.get("CFEN_LIB") or os.path.join(_HERE, "csrc", "libcfen_b200.so")
@@ -23,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "cfen_plan_stage_ptr",
     "cfen_f32_to_f16", "cfen_debug_set_buffer", "cfen_gemm_f16", "cfen_mlp_f16", "cfen_layernorm_f16", "cfen_attention_f16", "cfen_vit_tail_f16", "cfen_vit_front_f16",
     "cfen_gemm_tf32", "cfen_gemm_tc", "cfen_mlp_tc", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
-    "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_cfsm", "cfen_merge_lg",
+    "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_conv2d_instnorm_relu_nhwc", "cfen_cfsm", "cfen_merge_lg",
     "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward",
 )
 
@@ -49,7 +51,7 @@ def lib():
         L.cfen_last_error.restype = cp
         L.cfen_plan_create.argtypes = [ctypes.POINTER(cfen_config), ctypes.POINTER(vp)]
         L.cfen_plan_destroy.argtypes = [vp]
-        L.cfen_plan_set_weight.argtypes = [vp, cp, vp, i64]
+        L.cfen_plan_set_weight.argtypes = [vp, cp, vp, i64, i32]
         L.cfen_plan_pack_weights.argtypes = [vp, vp]
         L.cfen_plan_workspace_bytes.argtypes = [vp]
         L.cfen_plan_workspace_bytes.restype = i64
@@ -79,6 +81,7 @@ def lib():
         L.cfen_vit_tail_f16.argtypes = [vp] * 14 + [i32] * 3 + [vp]
         L.cfen_vit_front_f16.argtypes = [vp] + [i32] * 6 + [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp]
         L.cfen_conv2d_nhwc.argtypes = [cp] + [vp] * 7 + [i32] * 4 + [vp]
+        L.cfen_conv2d_instnorm_relu_nhwc.argtypes = [cp] + [vp] * 4 + [i32] * 4 + [vp]
         L.cfen_cfsm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.cfen_merge_lg.argtypes = [vp] * 8 + [i32] * 5 + [vp]
         L.cfen_deform_conv2d_forward.argtypes = [vp, vp, vp, vp] + [i32] * 16 + [vp]
@@ -133,9 +136,15 @@ class Plan:
                 continue
             if not t.is_floating_point():
                 continue
+            if t.dtype != torch.float32:
+                # the pack kernels read fp32: after net.half() / .bfloat16() / .double() they would read past the
+                # buffers or reinterpret bits.  The reference's checkpoints are fp32 (models/base_model.py:96-103).
+                raise RuntimeError("parameter %s is %s: cfen_vit_dehazing_b200 packs fp32 parameters only "
+                                   "(call net.float(); the kernels choose their own operand precision)" % (name, t.dtype))
             if not t.is_contiguous():
                 raise RuntimeError("parameter %s must be contiguous" % name)
-            check(L.cfen_plan_set_weight(self._h, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()))
+            check(L.cfen_plan_set_weight(self._h, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(),
+                                         t.element_size()))
         check(L.cfen_plan_pack_weights(self._h, ctypes.c_void_p(stream)))
         self.needs_calibration = need_cal
 

@@ -4,7 +4,7 @@ In the B200 build an ActNorm2d is a per-channel affine ``(x + bias) * exp(weight
 CUDA kernels fold into the epilogue of the convolution in front of it; this class only owns
 the three state_dict entries (``weight``, ``bias``, ``initialized``) so that checkpoints
 round-trip bit-for-bit.  The data-dependent first-forward initialisation of the reference
-(models/actnorm.py:25-37) is reproduced on the GPU by ``dec_ipt.calibrate_actnorm``.
+(models/actnorm.py:25-37) is reproduced on the GPU by the first ``dec_ipt.forward`` (C ABI ``cfen_forward_calibrate``).
 """
 import torch
 import torch.nn as nn

@@ -34,7 +34,7 @@ def build(force=False, verbose=False, timeline=False):
     if not force and not timeline and up_to_date():
         return OUT
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-DCFEN_NO_FAST_MATH", "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC]
+           "-DCFEN_NO_FAST_MATH", "-diag-suppress", "179,39", "-Xcompiler", "-fPIC", "-shared", "-o", out, SRC]
     if timeline:
         cmd.insert(1, "-DCFEN_TIMELINE")
     if verbose:

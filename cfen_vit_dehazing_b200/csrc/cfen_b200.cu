@@ -76,6 +76,26 @@ static bool tail_in_tmem(int variant, int E) { return (variant == 1 && E == 96) 
 struct cfen_plan;
 static bool all_maps16(const cfen_plan* p);
 
+// Every entry point that needs the plan's device current restores the caller's device on exit: a plan may be
+// destroyed by the host's garbage collector at any time, on any thread, and must not move that thread's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 static cudaError_t set_kernel_attributes() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<128, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -244,7 +264,7 @@ static int conv16_parts(int kind, int H, int W) {
 enum ProfClass { PC_GEMM, PC_MLP, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"linear_gemm", "fused_mlp", "attention", "layernorm", "tokenize", "conv",
                                            "merge_lg", "instnorm", "cfsm", "misc"};
-struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; char tag[56]; };
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; char tag[56]; char sym[48]; };
 
 struct ConvLayer {
   int kind = 0;
@@ -486,7 +506,8 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
     return fail(3, "loadSize must be H/2 and patch_size H/16 (got %d, %d for H=%d)", cfg->load_size,
                 cfg->patch_size, cfg->height);
   if (cfg->max_batch < 1) return fail(1, "max_batch must be >= 1");
-  CU(cudaSetDevice(cfg->device));
+  DeviceGuard dg(cfg->device);
+  CU(dg.err);
   int major = 0;
   CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
   if (major != 10) return fail(4, "libcfen_b200 needs an sm_100 device (found sm_%d*)", major);
@@ -535,7 +556,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
 
 extern "C" int32_t cfen_plan_destroy(cfen_plan* p) {
   if (!p) return 0;
-  cudaSetDevice(p->cfg.device);
+  DeviceGuard dg(p->cfg.device);
   if (p->wa.base) cudaFree(p->wa.base);
   if (p->ws.base) cudaFree(p->ws.base);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
@@ -546,8 +567,11 @@ extern "C" int32_t cfen_plan_destroy(cfen_plan* p) {
   return 0;
 }
 
-extern "C" int32_t cfen_plan_set_weight(cfen_plan* p, const char* key, const void* dev_ptr, int64_t numel) {
+extern "C" int32_t cfen_plan_set_weight(cfen_plan* p, const char* key, const void* dev_ptr, int64_t numel,
+                                        int32_t elem_bytes) {
   if (!p || !key || !dev_ptr) return fail(1, "cfen_plan_set_weight: null argument");
+  if (elem_bytes != 4)
+    return fail(1, "cfen_plan_set_weight: '%s' has %d-byte elements; the pack kernels read fp32 (4 bytes) only", key, elem_bytes);
   p->reg[key] = std::make_pair(static_cast<const float*>(dev_ptr), numel);
   p->packed = false;
   return 0;
@@ -588,7 +612,8 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "conv_path") == 0) { p->conv_path = value != 0; return 0; }
   if (strcmp(name, "streams") == 0) { p->streams = value != 0; return 0; }
   if (strcmp(name, "timing_reset") == 0) {
-    CU(cudaSetDevice(p->cfg.device));
+    DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
     CU(cudaDeviceSynchronize());
     p->prof.clear(); p->ev_used = 0;
     return 0;
@@ -600,7 +625,8 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
 // {"gemm_tf32": {"launches": n, "ms": t, "flops": f, "bytes": b}, ...}.  Synchronises the device.
 extern "C" int32_t cfen_plan_profile_json(cfen_plan* p, char* buf, int64_t cap) {
   if (!p || !buf || cap < 64) return fail(1, "cfen_plan_profile_json: bad argument");
-  CU(cudaSetDevice(p->cfg.device));
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
   CU(cudaDeviceSynchronize());
   double ms[PC_COUNT] = {0}, fl[PC_COUNT] = {0}, by[PC_COUNT] = {0};
   long long n[PC_COUNT] = {0};
@@ -625,15 +651,17 @@ extern "C" int32_t cfen_plan_profile_json(cfen_plan* p, char* buf, int64_t cap) 
 // Per-launch records (class, tag, ms, flops, bytes) as CSV into `path`; same lifetime as profile_json.
 extern "C" int32_t cfen_plan_profile_trace(cfen_plan* p, const char* path) {
   if (!p || !path) return fail(1, "cfen_plan_profile_trace: bad argument");
-  CU(cudaSetDevice(p->cfg.device));
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
   CU(cudaDeviceSynchronize());
   FILE* f = fopen(path, "w");
   if (!f) return fail(1, "cfen_plan_profile_trace: cannot open %s", path);
-  fprintf(f, "class,tag,us,gflop,mbytes\n");
+  fprintf(f, "class,tag,us,gflop,mbytes,kernel\n");
   for (const ProfRec& r : p->prof) {
     float t = 0.f;
     cudaEventElapsedTime(&t, r.a, r.b);
-    fprintf(f, "%s,%s,%.3f,%.4f,%.4f\n", kProfNames[r.cls], r.tag, t * 1e3, r.flops * 1e-9, r.bytes * 1e-6);
+    fprintf(f, "%s,%s,%.3f,%.4f,%.4f,%s\n", kProfNames[r.cls], r.tag, t * 1e3, r.flops * 1e-9, r.bytes * 1e-6,
+            r.sym[0] ? r.sym : kProfNames[r.cls]);
   }
   fclose(f);
   return 0;
@@ -662,7 +690,8 @@ static int pack_linear(cfen_plan* p, const std::string& key, float* dst, int row
 extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
   if (!p) return fail(1, "cfen_plan_pack_weights: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(p->cfg.device));
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
   for (int i = 0; i < 12; ++i)
     for (int g = 0; g < 2; ++g) {
       VitW& v = g ? p->gvit[i] : p->lvit[i];
@@ -761,12 +790,17 @@ struct Launch {
       : p(r.p), st(r.st), on(r.p->timing) {
     p->launches++;
     if (!on) return;
-    rec.tag[0] = 0;
+    rec.tag[0] = 0; rec.sym[0] = 0;
     if (fmt) { va_list ap; va_start(ap, fmt); vsnprintf(rec.tag, sizeof(rec.tag), fmt, ap); va_end(ap); }
     while (p->ev_pool.size() < p->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); p->ev_pool.push_back(e); }
     rec.cls = cls; rec.flops = flops; rec.bytes = bytes;
     rec.a = p->ev_pool[p->ev_used++]; rec.b = p->ev_pool[p->ev_used++];
     cudaEventRecord(rec.a, st);
+  }
+  // kernel symbol of this launch (template arguments included): bench.py groups the roofline by it
+  void sym(const char* fmt, ...) {
+    if (!on) return;
+    va_list ap; va_start(ap, fmt); vsnprintf(rec.sym, sizeof(rec.sym), fmt, ap); va_end(ap);
   }
   ~Launch() {
     if (!on) return;
@@ -825,10 +859,12 @@ static int run_gemm16(Run& r, const __half* A, const __half* W, float* C32, __ha
     {
       Launch l(r, PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + 4.0 * split * (double)Mpad * N,
                "gemm16 M%d N%d K%d split%d", M, N, K, split);
+      l.sym("gemm16_kernel<%d>", BN);
       CU(launch_gemm16(*ta, *tw, *tp, *ta, *ta, BN, M, N, K, ep0, r.st, split));
     }
     Launch l(r, PC_GEMM, 0.0, 4.0 * split * (double)M * N + (double)M * N * ((C32 ? 4 : 0) + (C16 ? 2 : 0) + (res ? 4 : 0)),
              "splitk_reduce M%d N%d S%d", M, N, split);
+    l.sym("splitk_reduce_kernel");
     const long long n4 = (long long)M * N / 4;
     splitk_reduce_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(part, split, Mpad, M, N, bias, res, pos, period > 0 ? period : 1,
                                                          relu, C32, C16);
@@ -843,6 +879,7 @@ static int run_gemm16(Run& r, const __half* A, const __half* W, float* C32, __ha
   Launch l(r, PC_GEMM, 2.0 * M * N * K,
            2.0 * ((double)M * K + (double)N * K) + (double)M * N * ((C32 ? 4 : 0) + (C16 ? 2 : 0) + (res ? 4 : 0)),
            "gemm16 M%d N%d K%d", M, N, K);
+  l.sym("gemm16_kernel<%d>", BN);
   CU(launch_gemm16(*ta, *tw, *tc32, *tr, *tc16, BN, M, N, K, ep, r.st));
   return 0;
 }
@@ -861,6 +898,7 @@ static int run_mlp16(Run& r, const __half* X, const __half* W1, const float* b1,
   Mlp16Args a{b1, b2, Y32 != nullptr, Y16 != nullptr, M, E, hid, {}};
   Launch l(r, PC_MLP, 4.0 * M * E * hid,
            (double)M * E * (2 + 4 + (Y32 ? 4 : 0) + (Y16 ? 2 : 0)) + 4.0 * E * hid, "mlp16 M%d E%d hid%d", M, E, hid);
+  l.sym("mlp16_kernel");
   CU(launch_mlp16(*tx, *t1, *t2, *tr, *ty32, *ty16, a, r.st));
   return 0;
 }
@@ -877,6 +915,7 @@ static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
   RET(get_tmap2(r.p, v.h_m3, 2, E, hid, 64, E, &m3));
   Launch l(r, PC_MLP, 2.0 * M * E * E + 8.0 * M * E * hid, (double)M * E * (2 + 4 + 4) + 2.0 * (E * E + 4.0 * E * hid),
            "tail16 M%d E%d hid%d", M, E, hid);
+  l.sym(tail_in_tmem(r.p->tail_variant, E) ? "vit_tail16r_kernel<%d>" : "vit_tail16_kernel<%d>", E);
   if (tail_in_tmem(r.p->tail_variant, E)) {
     Tail16RArgs ra{T, v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, hid};
     CU(launch_tail16r(E, *to, *two, *t1, *t2, *m0, *m3, *tt, ra, r.st));
@@ -898,16 +937,19 @@ static int run_front16(Run& r, const VitW& v, const FrontSrc* src, const float* 
   Front16Args a{src ? src->map : T0, src ? (src->h16 ? 2 : 1) : 0, src ? src->H : 0, src ? src->W : 0, src ? src->C : 0,
                 src ? src->win : 0, v.b_le, v.pos, v.L, v.ln1g, v.ln1b, M};
   Launch l(r, PC_GEMM, 8.0 * M * E * E, (double)M * E * ((src && src->h16 ? 2 : 4) + 4 + 6) + 8.0 * E * E, "front16 M%d E%d", M, E);
+  l.sym("vit_front16_kernel<%d>", E);
   CU(launch_front16(E, *twle, *twin, *tt1, *tq, a, r.st));
   return 0;
 }
 static int run_ln16(Run& r, const float* x, __half* y16, const float* g, const float* b, int M, int E) {
   Launch l(r, PC_LN, 0.0, 6.0 * M * E, "ln16 M%d E%d", M, E);
+  l.sym("layernorm_kernel");
   CU(launch_layernorm(x, nullptr, y16, g, b, M, E, 1e-5f, r.st));
   return 0;
 }
 static int run_attn16(Run& r, const __half* qkv, __half* o, int nseq, int L, int E, int heads) {
   Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 8.0 * nseq * L * E, "attn16 n%d L%d E%d h%d", nseq, L, E, heads);
+  l.sym("attention16_kernel<%d>", E / heads);
   CU(launch_attention16(qkv, o, nseq, L, E, heads, r.st));
   return 0;
 }
@@ -917,6 +959,7 @@ static int run_gemm(Run& r, const float* A, const float* W, float* C, int M, int
   GemmEpilogue ep{bias, res, pos, period > 0 ? period : 1, relu};
   Launch l(r, PC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N * (res ? 2 : 1)),
            "gemm M%d N%d K%d", M, N, K);
+  l.sym(r.p->gemm_path == 1 ? "gemm_tc_kernel" : "gemm_tf32_kernel");
   if (r.p->gemm_path == 1) {
     const int BN = gemm_tc_pick_bn(M, N);
     const CUtensorMap *ta, *tw, *tcm, *trm;
@@ -945,16 +988,19 @@ static int run_mlp(Run& r, const float* X, const float* W1, const float* b1, con
   MlpTcArgs a{b1, b2, R != nullptr, M, E, hid, {}};
   Launch l(r, PC_MLP, 4.0 * M * E * hid, 4.0 * ((X == R ? 2.0 : 3.0) * M * E + 2.0 * E * hid), "mlp M%d E%d hid%d", M,
            E, hid);
+  l.sym("mlp_tc_kernel");
   CU(launch_mlp_tc(*tx, *t1, *t2, *tr, *ty, a, r.st));
   return 0;
 }
 static int run_ln(Run& r, const float* x, float* y, const float* g, const float* b, int M, int E) {
   Launch l(r, PC_LN, 0.0, 8.0 * M * E, "ln M%d E%d", M, E);
+  l.sym("layernorm_kernel");
   CU(launch_layernorm(x, y, nullptr, g, b, M, E, 1e-5f, r.st));
   return 0;
 }
 static int run_attn(Run& r, const float* qkv, float* o, int nseq, int L, int E, int heads) {
   Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 16.0 * nseq * L * E, "attn n%d L%d E%d h%d", nseq, L, E, heads);
+  l.sym("attention_kernel<%d>", E / heads);
   CU(launch_attention(qkv, o, nseq, L, E, heads, r.st));
   return 0;
 }
@@ -1009,6 +1055,13 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
   return 0;
 }
 
+static const char* conv_kind_name(int kind) {
+  static const char* names[K_COUNT] = {"ConvHead5x5", "Conv3x3_12", "ConvDs12_24", "ConvDs24_48", "ConvDs48_96",
+                                       "ConvUp96_48", "ConvUp48_24", "ConvUp24_12", "ConvLg1", "ConvLg2", "ConvLg3",
+                                       "ConvSk96_48", "ConvSk48_24", "ConvTail7_3", "ConvTail7_1"};
+  return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
+}
+
 // One conv-family layer; handles ActNorm calibration (two-pass) when the plan is calibrating.
 static int run_conv(Run& r, const std::string& name, const float* in0, const float* in1, const float* res,
                     float* out, int H, int W, int flags, float* stats = nullptr) {
@@ -1039,16 +1092,19 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
     a.scale = p->ones; a.shift = c.bias_src; a.flags = flags & CF_FMT_MASK; a.stats = r.ln->partials;
     {
       Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str());
+      l.sym("%s<%s>", p->conv_path ? "conv16_kernel" : "conv_igemm_kernel", conv_kind_name(c.kind));
       CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
     }
     const long long count = (long long)r.nb * H * W * (is_up ? 4 : 1);
     Launch l(r, PC_NORM, 0.0, 0.0);
+    l.sym("actnorm_calibrate_kernel");
     actnorm_calibrate_kernel<<<1, 128, 0, r.st>>>(r.ln->partials, r.nb * parts, cout, count, c.bias_src, c.an_w,
                                                   c.an_b, c.scale, c.shift);
     CU(cudaGetLastError());
   }
   a.scale = c.scale; a.shift = c.shift; a.flags = flags; a.stats = stats;
-  Launch l(r, pcls, cflops, cbytes, "%s %dx%d", name.c_str(), H, W);
+  Launch l(r, pcls, cflops, cbytes, "%s %dx%d b%d", name.c_str(), H, W, r.nb);
+  l.sym("%s<%s>", p->conv_path ? "conv16_kernel" : "conv_igemm_kernel", conv_kind_name(c.kind));
   CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
   return 0;
 }
@@ -1060,12 +1116,14 @@ static int run_conv_in_relu(Run& r, const std::string& name, const float* in0, f
   RET(run_conv(r, name, in0, nullptr, nullptr, out, H, W, fmt_flags, r.ln->partials));
   const int parts = p->conv_path ? conv16_parts(p->conv[name].kind, H, W) : conv_parts(p->conv[name].kind, H, W);
   {
-    Launch l(r, PC_NORM, 0.0, 8.0 * r.nb * parts * C);
+    Launch l(r, PC_NORM, 0.0, 8.0 * r.nb * parts * C, "in_finalize C%d", C);
+    l.sym("instnorm_finalize_kernel");
     instnorm_finalize_kernel<<<r.nb, 128, 0, r.st>>>(r.ln->partials, r.ln->mean_rstd, parts, C, Hout * Wout, 1e-5f);
     CU(cudaGetLastError());
   }
   const long long total4 = (long long)r.nb * Hout * Wout * C / 4;
-  Launch l(r, PC_NORM, 0.0, (all_maps16(p) ? 16.0 : 32.0) * total4);
+  Launch l(r, PC_NORM, 0.0, (all_maps16(p) ? 16.0 : 32.0) * total4, "in_apply %dx%d C%d", Hout, Wout, C);
+  l.sym("instnorm_relu_apply_kernel");
   instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(out, r.ln->mean_rstd, Hout * Wout, C, total4,
                                                                all_maps16(p));
   CU(cudaGetLastError());
@@ -1078,18 +1136,21 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
   const int C = which == 0 ? 48 : 24, HW = H * W, parts = 64;
   const long long total4 = (long long)r.nb * HW * C / 4;
   {
-    Launch l(r, PC_CFSM, 0.0, (all_maps16(p) ? 24.0 : 48.0) * total4);
+    Launch l(r, PC_CFSM, 0.0, (all_maps16(p) ? 24.0 : 48.0) * total4, "cfsm_reduce %dx%d C%d", H, W, C);
+    l.sym("cfsm_reduce_kernel<%d>", C);
     if (C == 48) cfsm_reduce_kernel<48><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW, all_maps16(p));
     else cfsm_reduce_kernel<24><<<dim3(parts, r.nb), 192, 0, r.st>>>(x0, x1, x2, r.ln->cfsm_part, HW, all_maps16(p));
     CU(cudaGetLastError());
   }
   {
-    Launch l(r, PC_CFSM, 0.0, 0.0);
+    Launch l(r, PC_CFSM, 0.0, 0.0, "cfsm_gate C%d", C);
+    l.sym("cfsm_gate_kernel<%d>", C);
     if (C == 48) cfsm_gate_kernel<48><<<r.nb, 128, 0, r.st>>>(r.ln->cfsm_part, p->cfsm_w[0], r.ln->gates, parts, HW);
     else cfsm_gate_kernel<24><<<r.nb, 128, 0, r.st>>>(r.ln->cfsm_part, p->cfsm_w[1], r.ln->gates, parts, HW);
     CU(cudaGetLastError());
   }
-  Launch l(r, PC_CFSM, 0.0, (all_maps16(p) ? 32.0 : 64.0) * total4);
+  Launch l(r, PC_CFSM, 0.0, (all_maps16(p) ? 32.0 : 64.0) * total4, "cfsm_apply %dx%d C%d", H, W, C);
+  l.sym("cfsm_apply_kernel");
   cfsm_apply_kernel<<<ew_blocks(total4), 256, 0, r.st>>>(x0, x1, x2, r.ln->gates, out, HW, C, total4, all_maps16(p));
   CU(cudaGetLastError());
   return 0;
@@ -1110,6 +1171,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     const long long n4 = (long long)r.nb * (Hl / 16) * (Hl / 16) * 16 * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, n4 * ((all_maps16(p) ? 8.0 : 16.0) * 16 + 16.0 + 8.0), "tok_global H%d C%d", Hl, C);
+      l.sym("tokenize_global_kernel");
       tokenize_global_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.gws.t0, L.gws.x16, r.nb, Hl, Hl, C, all_maps16(p));
       CU(cudaGetLastError());
     }
@@ -1124,6 +1186,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
       Launch l(r, PC_TOKENIZE, 0.0, 32.0 * n4, "tok_local H%d C%d", Hl, C);
+      l.sym("tokenize_local_kernel");
       tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.lws.t0, L.lws.x16, r.nb, Hl, Hl, C, p->win, all_maps16(p));
       CU(cudaGetLastError());
     }
@@ -1224,7 +1287,8 @@ static int forward_impl(cfen_plan* p, int batch, const float* in, float* xr, flo
     return fail(9, "calibration batch %d exceeds plan max_batch %d (ActNorm statistics span the whole batch)",
                 batch, p->nbmax);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(p->cfg.device));
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
   const size_t HW = (size_t)p->H * p->W;
   p->launches = 0;
   p->calibrating = calibrate;
@@ -1252,7 +1316,8 @@ extern "C" int32_t cfen_forward_u8(cfen_plan* p, int32_t batch, const uint8_t* i
                                    uint8_t* xd, void* stream) {
   if (!p || !in || !xr || !xs || !xd) return fail(1, "cfen_forward_u8: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CU(cudaSetDevice(p->cfg.device));
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
   const int HW = p->H * p->W;
   for (int b0 = 0; b0 < batch; b0 += p->nbmax) {
     const int nb = batch - b0 < p->nbmax ? batch - b0 : p->nbmax;
@@ -1516,7 +1581,7 @@ static int conv_kind_from_name(const char* kind) {
 // Test-only convenience: packs the weights into temporaries (cudaMalloc + sync), runs, frees.
 static int conv_oneoff(int kind, const float* in0, const float* in1, const float* res, const float* weight,
                        const float* bias, const float* an_w, const float* an_b, float* out, int B, int H, int W,
-                       int flags, int win, cudaStream_t st) {
+                       int flags, int win, cudaStream_t st, float* stats = nullptr) {
   CU(set_kernel_attributes());
   const char* cpe = getenv("CFEN_CONV_PATH");
   const bool gen2 = !cpe || atoi(cpe) != 0;
@@ -1533,7 +1598,7 @@ static int conv_oneoff(int kind, const float* in0, const float* in1, const float
   if (e == cudaSuccess) {
     ConvArgs a;
     a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = tmp; a.scale = scale; a.shift = shift; a.out = out;
-    a.stats = nullptr; a.B = B; a.H = H; a.W = W; a.flags = flags; a.win = win;
+    a.stats = stats; a.B = B; a.H = H; a.W = W; a.flags = flags; a.win = win;
     e = gen2 ? conv16_launch_dispatch(kind, a, reinterpret_cast<const __half*>(tmp), st) : conv_launch_dispatch(kind, a, st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1556,6 +1621,39 @@ extern "C" int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const flo
   if ((f & CF_FMT_MASK) && ((f & CF_OUT_NCHW) && (f & CF_OUT16))) return fail(1, "cfen_conv2d_nhwc: fp16 output is NHWC only");
   return conv_oneoff(k, in, extra_is_input ? extra : nullptr, (f & CF_RES) ? extra : nullptr, weight, bias,
                      an_weight, an_bias, out, B, H, W, f, 0, static_cast<cudaStream_t>(stream));
+}
+
+// conv (strided 3x3 or transposed 4x4) + InstanceNorm2d + ReLU (v3.py:292-298, 301) exactly as the plan runs it:
+// the conv emits per-CTA partial statistics, instnorm_finalize reduces them in fp64, instnorm_relu_apply normalises
+// in place.  H, W = the conv's tile domain (output size of the strided convs, input size of the transposed ones).
+extern "C" int32_t cfen_conv2d_instnorm_relu_nhwc(const char* kind, const float* in, const float* weight,
+                                                  const float* bias, float* out, int32_t B, int32_t H, int32_t W,
+                                                  int32_t flags, void* stream) {
+  if (!kind || !in || !weight || !out) return fail(1, "cfen_conv2d_instnorm_relu_nhwc: null argument");
+  const int k = conv_kind_from_name(kind);
+  const bool is_ds = k == K_DS1 || k == K_DS2 || k == K_DS3, is_up = k == K_UP3 || k == K_UP2 || k == K_UP1;
+  if (!is_ds && !is_up) return fail(1, "cfen_conv2d_instnorm_relu_nhwc: kind '%s' is not a strided / transposed conv", kind);
+  const char* cpe = getenv("CFEN_CONV_PATH");
+  const bool gen2 = !cpe || atoi(cpe) != 0;
+  const int f = ((flags & 256) ? CF_IN16 : 0) | ((flags & 512) ? CF_OUT16 : 0);
+  if (!gen2 && f) return fail(1, "cfen_conv2d_instnorm_relu_nhwc: fp16 maps need the conv16 generation");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = conv_cout(k), parts = gen2 ? conv16_parts(k, H, W) : conv_parts(k, H, W);
+  const int Ho = is_up ? 2 * H : H, Wo = is_up ? 2 * W : W;
+  float* tmp = nullptr;
+  CU(cudaMalloc(&tmp, ((size_t)B * parts * 2 * C + (size_t)B * 2 * C) * sizeof(float)));
+  float* mean_rstd = tmp + (size_t)B * parts * 2 * C;
+  int rc = conv_oneoff(k, in, nullptr, nullptr, weight, bias, nullptr, nullptr, out, B, H, W, f, 0, st, tmp);
+  if (rc == 0) {
+    instnorm_finalize_kernel<<<B, 128, 0, st>>>(tmp, mean_rstd, parts, C, Ho * Wo, 1e-5f);
+    const long long total4 = (long long)B * Ho * Wo * C / 4;
+    instnorm_relu_apply_kernel<<<ew_blocks(total4), 256, 0, st>>>(out, mean_rstd, Ho * Wo, C, total4, (f & CF_OUT16) != 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(2, "cfen_conv2d_instnorm_relu_nhwc failed: %s", cudaGetErrorString(e));
+  }
+  cudaFree(tmp);
+  return rc;
 }
 
 extern "C" int32_t cfen_merge_lg(const float* local_tokens, const float* global_tokens, const float* x,

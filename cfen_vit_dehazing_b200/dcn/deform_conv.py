@@ -39,19 +39,17 @@ def _f32c(t):
 
 
 def _output_size(input, weight, padding, dilation, stride):
-    """DeformConvFunction._output_size (deform_conv.py:80-93)."""
-    channels = weight.size(0)
-    output_size = (input.size(0), channels)
-    for d in range(input.dim() - 2):
-        in_size = input.size(d + 2)
-        pad = padding[d]
-        kernel = dilation[d] * (weight.size(d + 2) - 1) + 1
-        stride_ = stride[d]
-        output_size += ((in_size + (2 * pad) - kernel) // stride_ + 1, )
-    if not all(map(lambda s: s > 0, output_size)):
-        raise ValueError("convolution input is too small (output would be {})".format('x'.join(
-            map(str, output_size))))
-    return output_size
+    """Shape of the dcn output, [B, Cout, Ho, Wo]: each spatial extent follows the usual convolution arithmetic
+    floor((in + 2*pad - (dil*(k-1)+1)) / stride) + 1.  Same contract as the reference's
+    DeformConvFunction._output_size (dcn/deform_conv.py:80-93): ValueError when an extent is not positive."""
+    spatial = []
+    for axis in range(2, input.dim()):
+        span = dilation[axis - 2] * (weight.shape[axis] - 1) + 1
+        spatial.append((input.shape[axis] + 2 * padding[axis - 2] - span) // stride[axis - 2] + 1)
+    shape = (input.shape[0], weight.shape[0]) + tuple(spatial)
+    if min(shape) <= 0:
+        raise ValueError("convolution input is too small (output would be %s)" % "x".join(str(v) for v in shape))
+    return shape
 
 
 def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,

@@ -63,13 +63,29 @@ def init_weights(net, init_type="normal", gain=0.02):
     net.apply(visit)
 
 
+class ImageShardedDataParallel(torch.nn.DataParallel):
+    """Stands where the reference puts ``torch.nn.DataParallel`` (v3.py:81): same constructor, same ``.module``
+    attribute (``BaseModel.save_networks`` saves ``net.module.state_dict()``, models/base_model.py:96-103), same
+    scatter-along-dim-0 / gather-on-``output_device`` semantics.  ``nn.DataParallel.forward`` re-broadcasts every
+    parameter into throw-away replicas on each call; here each device owns a persistent plan (packed weights +
+    workspace) that is re-packed from the master parameters only when they change, and one host thread enqueues the
+    image shards on the devices' streams - no replica, no collective, no Python thread pool."""
+
+    def forward(self, *inputs, **kwargs):
+        if kwargs or len(inputs) != 1:
+            raise RuntimeError("dec_ipt takes exactly one positional input tensor")
+        if len(self.device_ids) <= 1:
+            return self.module(inputs[0])
+        return self.module.forward_sharded(inputs[0], self.device_ids, self.output_device)
+
+
 def init_net(net, init_type="normal", gpu_ids=()):
-    """Move to ``gpu_ids[0]`` (+DataParallel) then initialise, like v3.py:77-83."""
+    """Move to ``gpu_ids[0]`` (+ data-parallel wrapper) then initialise, like v3.py:77-83."""
     gpu_ids = list(gpu_ids)
     if len(gpu_ids) > 0:
         assert torch.cuda.is_available()
         net.to(gpu_ids[0])
-        net = torch.nn.DataParallel(net, gpu_ids)
+        net = ImageShardedDataParallel(net, gpu_ids)
     init_weights(net, init_type)
     return net
 
@@ -328,6 +344,7 @@ class dec_ipt(nn.Module):
 
         # ---- native state (not part of state_dict)
         self._plans = {}
+        self._retired_plans = []
         self._weights_version = 0
         self.register_load_state_dict_post_hook(_mark_dirty)
 
@@ -366,7 +383,12 @@ class dec_ipt(nn.Module):
         """Call after mutating parameters in place; the next forward re-packs them."""
         _mark_dirty(self, None)
 
-    def _plan_for(self, device, height, width, batch):
+    def _tensors_version(self):
+        """In-place updates (optimizer.step(), p.data.mul_(), copy_()) bump the tensors' version counters:
+        their sum detects stale packed weights without hooks."""
+        return sum(t._version for t in self.parameters()) + sum(t._version for t in self.buffers())
+
+    def _plan_for(self, device, height, width, batch, exact_batch=False):
         opt = self.opt
         if height != width or height != 2 * int(opt.loadSize):
             raise RuntimeError(
@@ -375,21 +397,38 @@ class dec_ipt(nn.Module):
                 % (height, width, 2 * int(opt.loadSize)))
         key = (device.index, height, width)
         plan = self._plans.get(key)
-        need = _native.chunk_images(height, batch)
+        need = batch if exact_batch else _native.chunk_images(height, batch)
         if plan is None or plan.max_batch < need:   # grow the workspace when a larger batch arrives
+            # the superseded plan stays alive: a CUDA graph captured over it still references its workspace
+            if plan is not None:
+                self._retired_plans.append(plan)
             plan = _native.Plan(device=device.index, height=height, width=width,
                                 n_feats=opt.n_feats, hidden_dim_ratio=opt.hidden_dim_ratio,
                                 num_heads=opt.num_heads, patch_dim=opt.patch_dim,
                                 patch_size=int(opt.patch_size), load_size=int(opt.loadSize),
                                 max_batch=need)
             self._plans[key] = plan
-        if plan.weights_version != self._weights_version:
+        version = (self._weights_version, self._tensors_version())
+        if plan.weights_version != version:
             tensors = {k: v for k, v in self.state_dict(keep_vars=True).items()}
-            for name, t in tensors.items():
-                if t.device != device:
-                    raise RuntimeError("parameter %s lives on %s, input on %s" % (name, t.device, device))
-            plan.pack(tensors, torch.cuda.current_stream(device).cuda_stream)
-            plan.weights_version = self._weights_version
+            master = next(self.parameters()).device
+            stream = torch.cuda.current_stream(device)
+            if master != device:
+                # a plan on another GPU of the box (forward_sharded): pack from a transient copy of the master
+                # parameters; the plan keeps only its packed copy
+                if master.type != "cuda":
+                    raise RuntimeError("parameters live on %s, input on %s" % (master, device))
+                tensors = {k: v.detach().to(device) for k, v in tensors.items()}
+            else:
+                for name, t in tensors.items():
+                    if t.device != device:
+                        raise RuntimeError("parameter %s lives on %s, input on %s" % (name, t.device, device))
+            plan.pack(tensors, stream.cuda_stream)
+            if master != device:
+                stream.synchronize()        # the pack kernels have consumed the transient copies
+                if plan.needs_calibration:
+                    raise RuntimeError("uninitialised ActNorm layers on a secondary device: calibrate on the master first")
+            plan.weights_version = version
         return plan
 
     def _actnorm_modules(self):
@@ -414,14 +453,52 @@ class dec_ipt(nn.Module):
             xd = torch.empty((b, 3, h, w), dtype=torch.float32, device=x.device)
             if plan.needs_calibration:
                 # reference semantics: the first forward initialises every ActNorm2d from the
-                # batch statistics of its input (models/actnorm.py:25-37)
+                # batch statistics of its input (models/actnorm.py:25-37).  The statistics span the whole batch, so
+                # a batch beyond the plan's images-per-pass gets a plan sized for all of it (one pass).
+                if b > plan.max_batch:
+                    try:
+                        plan = self._plan_for(x.device, h, w, b, exact_batch=True)
+                    except RuntimeError as e:
+                        raise RuntimeError(
+                            "first (ActNorm-initialising) forward with batch %d needs a one-pass workspace that did "
+                            "not fit (%s); prime the model with a smaller batch or load a checkpoint whose "
+                            "*.initialized buffers are 1" % (b, e))
                 plan.calibrate(b, x.data_ptr(), xr.data_ptr(), xs.data_ptr(), xd.data_ptr(), stream)
                 for m in self._actnorm_modules():
                     m.initialized.fill_(1)
                 plan.needs_calibration = False
+                # the calibration kernels wrote weight / bias through raw pointers and refreshed the plan's folded
+                # scale / shift themselves: this plan is current, every other plan re-packs
+                self._weights_version += 1
+                plan.weights_version = (self._weights_version, self._tensors_version())
             else:
                 plan.forward(b, x.data_ptr(), xr.data_ptr(), xs.data_ptr(), xd.data_ptr(), stream)
         return [xr, xs, xd]
+
+    def forward_sharded(self, input, device_ids, output_device=None):
+        """One process, several GPUs: the batch is cut into contiguous image shards (parallel.shard_sizes), shard i
+        runs on ``device_ids[i]`` through that device's own plan and stream, outputs are gathered on
+        ``output_device`` - what nn.DataParallel(dec_ipt) does at v3.py:81, minus the per-call replication.  All
+        launches are asynchronous, so the devices run concurrently under one host thread."""
+        from .parallel import shard_sizes
+        ids = [torch.device("cuda", int(d)) if not isinstance(d, torch.device) else d for d in device_ids]
+        out_dev = ids[0] if output_device is None else torch.device("cuda", int(output_device)) \
+            if not isinstance(output_device, torch.device) else output_device
+        b = input.shape[0]
+        master = next(self.parameters()).device
+        if any(int(m.initialized) == 0 for m in self._actnorm_modules()):
+            # data-dependent ActNorm initialisation spans the whole batch: one pass on the master device
+            outs = self.forward(input.to(master))
+            return [o.to(out_dev) for o in outs]
+        sizes = shard_sizes(b, len(ids))
+        parts, lo = [], 0
+        for dev, n in zip(ids, sizes):
+            if n == 0:
+                continue
+            with torch.cuda.device(dev):
+                parts.append(self.forward(input[lo:lo + n].to(dev, non_blocking=True)))
+            lo += n
+        return [torch.cat([p[i].to(out_dev, non_blocking=True) for p in parts], 0) for i in range(3)]
 
     def forward_host(self, input, out=None, device=None, defer_sync=False):
         """Host-to-host forward for batches that start and end in (pinned) host memory - what

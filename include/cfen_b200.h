@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CFEN_ABI_VERSION 1
+#define CFEN_ABI_VERSION 2
 
 typedef struct cfen_plan cfen_plan;
 
@@ -61,7 +61,8 @@ int32_t cfen_plan_destroy(cfen_plan* plan);
  * "localvit_encoder_01.encoder.layers.0.self_attn.in_proj_weight".  fp32, contiguous, reference
  * layout.  Keys the forward never reads (dead decoder weights, query_embed, sub_mean...) are
  * accepted and ignored.  Replaces load_state_dict (models/base_model.py:114-131). */
-int32_t cfen_plan_set_weight(cfen_plan* plan, const char* key, const void* dev_ptr, int64_t numel);
+int32_t cfen_plan_set_weight(cfen_plan* plan, const char* key, const void* dev_ptr, int64_t numel,
+                             int32_t elem_bytes /* must be 4 (fp32); anything else is rejected */);
 
 /* Permute / TF32-round / fold the registered tensors into the kernels' layouts.  Must be called
  * after all set_weight calls and again whenever the registered tensors change. */
@@ -189,6 +190,13 @@ int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const float* extra, 
                          const float* bias, const float* an_weight, const float* an_bias,
                          float* out, int32_t B, int32_t H, int32_t W, int32_t flags, void* stream);
 /* (argument order in the .so: kind,in,extra,weight,bias,an_weight,an_bias,out,B,H,W,flags,stream) */
+
+/* Strided 3x3 ("ds_*") or transposed 4x4 ("up_*") convolution + InstanceNorm2d (eps 1e-5, biased variance, no
+ * affine) + ReLU, i.e. ds_conv_e0x / us_conv_d03x (v3.py:292-298, 301), run the way the plan runs it: per-CTA partial
+ * statistics out of the conv epilogue, fp64 finalize, in-place normalise.  H, W = output size for "ds_*", input size
+ * for "up_*"; flags bit8 / bit9: fp16 NHWC input / output maps. */
+int32_t cfen_conv2d_instnorm_relu_nhwc(const char* kind, const float* in, const float* weight, const float* bias,
+                                       float* out, int32_t B, int32_t H, int32_t W, int32_t flags, void* stream);
 
 /* CFSM2G (v3.py:1502-1517): out = x0 + x1*sig1 + x2*sig2 on NHWC maps; w = the 8 bias-free 1x1
  * weights concatenated in state_dict order (avg_cf1.0, avg_cf1.2, avg_cf2.0, avg_cf2.2,

@@ -1,7 +1,11 @@
-"""Host-side logic of bench.py that needs no GPU: per-launch trace aggregation and the ncu traffic table."""
+"""Host-side logic of bench.py that needs no GPU: per-launch trace aggregation, the batch plan of the BASELINE
+configs, the roofline arithmetic and the ncu traffic table."""
+import argparse
 import importlib.util
 import json
 import os
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -13,34 +17,84 @@ def _bench():
     return mod
 
 
-def test_trace_groups_decoder_branches_into_one_kernel(tmp_path):
+TRACE = ("class,tag,us,gflop,mbytes,kernel\n"
+         "conv,tail_R.c2 512x512 b64,400.0,10.0,100.0,conv16_kernel<ConvTail7_3>\n"
+         "conv,tail_S.c2 512x512 b64,380.0,10.0,100.0,conv16_kernel<ConvTail7_1>\n"
+         "conv,tail_D.c2 512x512 b64,410.0,10.0,100.0,conv16_kernel<ConvTail7_3>\n"
+         "conv,us_conv_d01r 256x256 b64,300.0,5.0,50.0,conv16_kernel<ConvUp24_12>\n"
+         "conv,us_conv_d01s 256x256 b64,300.0,5.0,50.0,conv16_kernel<ConvUp24_12>\n"
+         "attention,attn16 n4096 L256 E96 h4,300.0,100.0,400.0,attention16_kernel<24>\n"
+         "attention,attn16 n1024 L256 E192 h8,200.0,50.0,200.0,attention16_kernel<24>\n"
+         "attention,attn16 n256 L256 E384 h16,150.0,25.0,100.0,attention16_kernel<24>\n"
+         "fused_mlp,tail16 M1048576 E96 hid384,600.0,328.0,1000.0,vit_tail16r_kernel<96>\n"
+         "instnorm,,10.0,0.0,1.0,instnorm_finalize_kernel\n")
+
+
+def test_trace_groups_by_kernel_symbol_and_by_shape(tmp_path):
     b = _bench()
     p = tmp_path / "trace.csv"
-    p.write_text("class,tag,us,gflop,mbytes\n"
-                 "conv,tail_R.c2 512x512,400.0,10.0,100.0\n"
-                 "conv,tail_S.c2 512x512,380.0,10.0,100.0\n"
-                 "conv,tail_D.c2 512x512,410.0,10.0,100.0\n"
-                 "conv,us_conv_d01r 256x256,300.0,5.0,50.0\n"
-                 "conv,us_conv_d01s 256x256,300.0,5.0,50.0\n"
-                 "fused_mlp,tail16 M1048576 E96 hid384,700.0,328.0,1000.0\n"
-                 "instnorm,,10.0,0.0,1.0\n")
-    k = b.kernels_from_trace(str(p))
-    assert k["tail_*.c2 512x512"]["launches"] == 3 and abs(k["tail_*.c2 512x512"]["us"] - 1190.0) < 1e-6
-    assert k["us_conv_d01* 256x256"]["launches"] == 2
-    assert k["instnorm"]["launches"] == 1                      # untagged launches fall back to their class
-    name, d = max(k.items(), key=lambda kv: kv[1]["us"])
-    assert name == "tail_*.c2 512x512" and d["class"] == "conv"
+    p.write_text(TRACE)
+    by_sym, by_shape = b.kernels_from_trace(str(p))
+    # one symbol over three shapes: attention is the dominant KERNEL although no single shape of it is the largest
+    assert by_sym["attention16_kernel<24>"]["launches"] == 3
+    assert abs(by_sym["attention16_kernel<24>"]["us"] - 650.0) < 1e-6
+    assert by_sym["conv16_kernel<ConvTail7_3>"]["launches"] == 2
+    name, d = max(by_sym.items(), key=lambda kv: kv[1]["us"])
+    assert name == "conv16_kernel<ConvTail7_3>" and d["class"] == "conv"
+    # per-shape view: the three decoder branches are one entry
+    assert by_shape["tail_*.c2 512x512 b64"]["launches"] == 3
+    assert by_shape["us_conv_d01* 256x256 b64"]["launches"] == 2
+    assert by_shape["instnorm"]["launches"] == 1               # untagged launches fall back to their class
+    # work units: token rows, sequences x length, pixels x images
+    assert by_sym["vit_tail16r_kernel<96>"]["units"] == 1048576
+    assert by_sym["attention16_kernel<24>"]["units"] == (4096 + 1024 + 256) * 256
+    assert by_sym["conv16_kernel<ConvUp24_12>"]["units"] == 2 * 256 * 256 * 64
 
 
-def test_ncu_traffic_table_scales_with_rows():
+def test_old_trace_without_kernel_column_still_parses(tmp_path):
+    b = _bench()
+    p = tmp_path / "trace.csv"
+    p.write_text("class,tag,us,gflop,mbytes\nfused_mlp,tail16 M1024 E96 hid384,7.0,1.0,1.0\n")
+    by_sym, _ = b.kernels_from_trace(str(p))
+    assert by_sym["tail16"]["launches"] == 1
+
+
+def test_roofline_bound_selection():
+    b = _bench()
+    pk = {"hbm_gbs": 6500.0, "tf_sustained": 1400.0}
+    t = b.roofline_of({"us": 1000.0, "gflop": 700.0, "mbytes": 100.0}, pk)        # 700 TF/s vs 100 GB/s
+    assert t["bound"] == "tensor" and abs(t["frac"] - 0.5) < 1e-9
+    h = b.roofline_of({"us": 1000.0, "gflop": 1.0, "mbytes": 3250.0}, pk)
+    assert h["bound"] == "hbm" and abs(h["frac"] - 0.5) < 1e-9 and h["unit"] == "GB/s"
+
+
+def test_ncu_traffic_table_scales_with_units():
     b = _bench()
     table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-    t1 = b.ncu_traffic(table, "tail16 M524288 E96 hid384")
-    t2 = b.ncu_traffic(table, "tail16 M1048576 E96 hid384")
+    sym = "vit_tail16r_kernel<96>"
+    assert sym in table
+    t1 = b.ncu_traffic(table, sym, 524288.0 * 4, 4)
+    t2 = b.ncu_traffic(table, sym, 1048576.0 * 4, 4)
     assert t1 and abs(t2 / t1 - 2.0) < 1e-9
-    assert abs(t1 - 857.7 * 524288) < 1.0
-    assert b.ncu_traffic(table, "tail16 M262144 E192 hid768") is None     # no capture for that shape family
-    assert b.ncu_traffic(table, "gemm16 M512 N1536 K6144") is None
+    assert abs(t1 - table[sym]["bytes_per_unit"] * 524288) < 1.0
+    assert b.ncu_traffic(table, "gemm16_kernel<192>", 512.0, 1) is None     # no capture for that kernel
+
+
+@pytest.mark.parametrize("size,hr,world,gb,per", [(512, 4, 1, 256, 256), (512, 4, 2, 256, 128), (512, 4, 8, 256, 32),
+                                                  (512, 2, 1, 32, 32), (1024, 4, 4, 16, 4)])
+def test_batch_plan_follows_baseline_configs(size, hr, world, gb, per):
+    """BASELINE.json configs[2..4]: the GLOBAL batch is fixed and sharded over the GPUs (strong scaling)."""
+    b = _bench()
+    args = argparse.Namespace(size=size, hr=hr, batch=None)
+    assert b.batch_plan(args, world) == (gb, per, "strong")
+    assert "BASELINE configs" in b.workload_name(args, gb)
+
+
+def test_batch_plan_explicit_per_gpu_batch_is_weak_and_labelled():
+    b = _bench()
+    args = argparse.Namespace(size=512, hr=4, batch=128)
+    assert b.batch_plan(args, 4) == (512, 128, "weak")
+    assert "not a BASELINE config" in b.workload_name(args, 512)
 
 
 def test_measured_peaks_fallback_and_file(tmp_path, monkeypatch):

@@ -20,6 +20,7 @@ from tests.golden.make_goldens import CONFIGS  # noqa: E402
 
 MAX_ABS_01 = 1e-2
 MIN_PSNR = 45.0
+MAX_STAGE_REL = 5e-3     # max|stage map - reference map| / max|reference map|, every stage of the graph
 
 STAGE_TAPS = {"xf": "xf", "e1": "e1", "e1d": "e1d", "e2": "e2", "e2d": "e2d", "e3": "e3"}
 for _b in "rsd":
@@ -68,6 +69,9 @@ def _run_and_check(name, hr, size, batch):
         ok = ok and mx <= MAX_ABS_01 and ps >= MIN_PSNR and bool(torch.isfinite(a).all())
     G.dump_json("parity_%s.json" % name, rep)
     assert ok, rep
+    # every stage-boundary map agrees with the reference's map of the same name (fp16 storage: 2^-11 per rounding)
+    worst = max(rep["stages"].items(), key=lambda kv: kv[1]["rel"])
+    assert worst[1]["rel"] <= MAX_STAGE_REL, worst
     return gnet, out, ref, x1
 
 
@@ -84,6 +88,101 @@ def test_forward_parity_vs_oracle_and_goldens(name):
 
 def test_forward_parity_1024():
     _run_and_check("v3_hr4_1024_b1", 4, 1024, 1)
+
+
+# BASELINE.json configs[3] (hr=4, 512x512: one full 64-image pass of the plan), configs[2] (hr=2, batch 32) and
+# configs[4] (1024x1024, batch 16 = one full pass): the batches bench.py times.  At these tile counts the plan
+# selects the fused token kernels, mlp16 at E=384 / M=65536 and the non-split-K GEMMs - none of which a batch-1 or
+# 128x128 forward reaches.  Images are independent, so the oracle runs on a sample of the batch.
+@pytest.mark.parametrize("hr,size,batch,picks", [(4, 512, 64, (0, 21, 42, 63)), (2, 512, 32, (0, 9, 22, 31)),
+                                                 (4, 1024, 16, (0, 5, 10, 15))])
+def test_forward_parity_at_benchmark_batches(hr, size, batch, picks):
+    gnet, sd0, sd1, x0 = _gpu_net(hr, size)
+    x = orc.make_inputs(size, [1, batch])[1]
+    with torch.no_grad():
+        out = gnet(x.cuda())
+    torch.cuda.synchronize()
+    assert all(bool(torch.isfinite(o).all()) for o in out)
+    rep = {}
+    for i in picks:
+        ref = orc.forward(sd1, x[i:i + 1])
+        for tag, a, b in zip(("xr", "xs", "xd"), out, ref):
+            mx, ps = U.err01(a[i:i + 1], b)
+            rep["%s[%d]" % (tag, i)] = {"max_abs_01": mx, "psnr": ps}
+    G.dump_json("parity_bench_hr%d_%d_b%d.json" % (hr, size, batch), rep)
+    bad = {k: v for k, v in rep.items() if not (v["max_abs_01"] <= MAX_ABS_01 and v["psnr"] >= MIN_PSNR)}
+    assert not bad, bad
+
+
+def test_cuda_graph_replay_equals_eager():
+    """BASELINE configs[1]: the batch-1 512x512 forward captured in a CUDA graph (what bench.py's latency leg
+    replays) returns bit for bit what the eager forward returns, on fresh input written into the captured buffer."""
+    gnet, sd0, sd1, x0 = _gpu_net(4, 512)
+    xa, xb = orc.make_inputs(512, [1, 1, 1])[1:]
+    stream = torch.cuda.current_stream()
+    with torch.no_grad():
+        xin = xa.cuda()
+        side = torch.cuda.Stream()
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                gnet(xin)
+        stream.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            yg = gnet(xin)
+        for x in (xa, xb):
+            xin.copy_(x.cuda())
+            graph.replay()
+            torch.cuda.synchronize()
+            got = [y.clone() for y in yg]
+            eager = gnet(x.cuda())
+            torch.cuda.synchronize()
+            for a, b in zip(got, eager):
+                assert torch.equal(a, b)
+        ref = orc.forward(sd1, xb)
+    for a, b in zip(got, ref):
+        mx, ps = U.err01(a, b)
+        assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (mx, ps)
+
+
+# Every runtime option INTEGRATION.md advertises computes the same function: whole-forward parity against the oracle
+# with the option set (environment variables are read when the plan is created).  CFEN_FUSE_MIN_TILES=1 forces the
+# fused token kernels at this small size (16-token windows, 8 images -> 64 tiles).
+OPTION_SETS = [
+    {"CFEN_FUSE_MIN_TILES": "1"},
+    {"CFEN_FUSE_MIN_TILES": "1", "CFEN_FUSE_FRONT": "0"},
+    {"CFEN_FUSE_MIN_TILES": "1", "CFEN_FUSE_TAIL": "0"},
+    {"CFEN_FUSE_MIN_TILES": "1", "CFEN_FUSE_TAIL": "0", "CFEN_FUSE_MLP": "0"},
+    {"CFEN_FUSE_MIN_TILES": "1", "CFEN_TAIL_VARIANT": "0"},
+    {"CFEN_FUSE_MIN_TILES": "1", "CFEN_TAIL_VARIANT": "1"},
+    {"CFEN_FUSE_MIN_TILES": "1", "CFEN_ATTN_TC": "0"},
+    {"CFEN_SPLIT_K": "0"},
+    {"CFEN_STREAMS": "0"},
+    {"CFEN_MAPS16": "0"},
+    {"CFEN_MAPS16": "1"},
+    {"CFEN_CONV_PATH": "0"},
+    {"CFEN_GEMM_PATH": "1"},
+    {"CFEN_GEMM_PATH": "0"},
+    {"CFEN_GEMM_PATH": "1", "CFEN_CONV_PATH": "0"},
+]
+
+
+@pytest.mark.parametrize("env", OPTION_SETS, ids=lambda e: ",".join("%s=%s" % (k[5:], v) for k, v in e.items()))
+def test_forward_parity_option_paths(monkeypatch, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    hr, size, batch = 2, 128, 8
+    gnet, sd0, sd1, x0 = _gpu_net(hr, size)
+    x1 = orc.make_inputs(size, [1, batch])[1]
+    ref = orc.forward(sd1, x1)
+    with torch.no_grad():
+        out = gnet(x1.cuda())
+    torch.cuda.synchronize()
+    for tag, a, b in zip(("xr", "xs", "xd"), out, ref):
+        mx, ps = U.err01(a, b)
+        assert mx <= MAX_ABS_01 and ps >= MIN_PSNR and bool(torch.isfinite(a).all()), (env, tag, mx, ps)
 
 
 def test_batch_chunking_and_batch_invariance(monkeypatch):

@@ -350,6 +350,35 @@ def test_conv_strided(kind, cin, cout):
     assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
 
 
+@pytest.mark.parametrize("kind,cin,cout,up", [("ds_12_24", 12, 24, False), ("ds_24_48", 24, 48, False),
+                                              ("ds_48_96", 48, 96, False), ("up_96_48", 96, 48, True)])
+@pytest.mark.parametrize("f16", [False, True])
+def test_conv_instnorm_relu(kind, cin, cout, up, f16):
+    """ds_conv_e0x / us_conv_d03x (v3.py:292-298, 301): conv + InstanceNorm2d + ReLU.  Exercises the conv epilogue's
+    per-CTA partial statistics, instnorm_finalize_kernel (fp64 reduction) and instnorm_relu_apply_kernel (in place,
+    fp32 and fp16 maps) against F.instance_norm (eps 1e-5, biased variance, no affine).  Three images with different
+    scales and offsets: statistics must be per (image, channel)."""
+    B, H = 3, 32                                    # tile domain
+    Hi = H if up else 2 * H
+    Ho = 2 * H if up else H
+    x = dev(B, cin, Hi, Hi, seed=1) * torch.tensor([1.0, 3.0, 0.25], device="cuda").view(B, 1, 1, 1) \
+        + torch.tensor([0.0, 2.0, -1.0], device="cuda").view(B, 1, 1, 1)
+    w = dev(cin, cout, 4, 4, seed=2, scale=0.1) if up else dev(cout, cin, 3, 3, seed=2, scale=0.1)
+    b = dev(cout, seed=3)
+    xi = U.to_nhwc(x).half() if f16 else U.to_nhwc(x)
+    out = torch.empty(B, Ho, Ho, cout, device="cuda", dtype=torch.float16 if f16 else torch.float32)
+    G.check(_native.lib().cfen_conv2d_instnorm_relu_nhwc(kind.encode(), G.ptr(xi), G.ptr(w), G.ptr(b), G.ptr(out), B, H, H,
+                                                         (256 | 512) if f16 else 0, G.stream()))
+    xd = U.to_nchw(xi.float()).double()
+    y = F.conv_transpose2d(xd, w.double(), b.double(), stride=2, padding=1) if up else \
+        F.conv2d(xd, w.double(), b.double(), stride=2, padding=1)
+    ref = torch.relu(F.instance_norm(y, eps=1e-5))
+    got = U.to_nchw(out.float()).double()
+    assert got.shape == ref.shape
+    # normalised outputs are O(1): absolute tolerance of the TF32-class contraction (+ one fp16 rounding of the map)
+    assert (got - ref).abs().max().item() <= (8e-3 if f16 else 5e-3) * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("kind,cin,cout", [("up_96_48", 96, 48), ("up_48_24", 48, 24), ("up_24_12", 24, 12)])
 @pytest.mark.parametrize("f16", [False, True])
 def test_conv_transposed(kind, cin, cout, f16):

@@ -90,7 +90,7 @@ def test_library_exports_every_header_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _native.lib().cfen_abi_version() == 1
+    assert _native.lib().cfen_abi_version() == 2
 
 
 def test_missing_library_fails_loudly(monkeypatch):
@@ -99,3 +99,44 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_native, "LIB_PATH", "/nonexistent/libcfen_b200.so")
     with pytest.raises(RuntimeError, match="not built"):
         _native.lib()
+
+
+def test_pack_rejects_non_fp32_parameters():
+    """after net.half() / .double() the pack kernels would read past or reinterpret the buffers; the shim
+    refuses (the check sits before any native call, so it runs without a GPU)."""
+    from cfen_vit_dehazing_b200 import _native
+
+    class _FakePlan(_native.Plan):
+        def __init__(self):      # no native handle: pack() must raise before it is needed
+            self._h = None
+
+    for dt in (torch.float16, torch.bfloat16, torch.float64):
+        with pytest.raises(RuntimeError, match="fp32 parameters only"):
+            _FakePlan().pack({"head.0.0.weight": torch.zeros(4, dtype=dt)}, 0)
+
+
+def test_in_place_parameter_updates_change_the_tensors_version():
+    """optimizer.step() / p.data.mul_() / copy_() must invalidate the packed weights."""
+    net, _, _, _, _ = U.seeded_state(2, 128)
+    v0 = net._tensors_version()
+    with torch.no_grad():
+        net.head[0][0].bias.add_(1.0)
+    v1 = net._tensors_version()
+    with torch.no_grad():
+        net.head[0][0].bias.copy_(net.head[0][0].bias - 1.0)
+    v2 = net._tensors_version()
+    assert v1 > v0 and v2 > v1
+    # writes through .data bypass autograd's version counter (torch semantics): those need mark_weights_changed()
+    net.head[0][0].bias.data.mul_(1.0)
+    assert net._tensors_version() == v2
+    w0 = net._weights_version
+    net.mark_weights_changed()
+    assert net._weights_version > w0
+
+
+def test_define_g_with_gpu_ids_wraps_like_the_reference(monkeypatch):
+    """init_net (v3.py:77-83) moves to gpu_ids[0] and wraps in DataParallel; the wrapper here IS an nn.DataParallel
+    (isinstance checks, .module for save_networks) that shards images over per-device plans."""
+    import cfen_vit_dehazing_b200.networks_iid_hlgvit_crs_gd4_cfs_v3 as v3
+    assert issubclass(v3.ImageShardedDataParallel, torch.nn.DataParallel)
+    assert hasattr(v3.dec_ipt, "forward_sharded")
