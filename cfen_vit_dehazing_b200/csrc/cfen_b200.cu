@@ -25,6 +25,7 @@
 #include "conv_igemm.cuh"
 #include "dcn.cuh"
 #include "attn16.cuh"
+#include "attn_tc.cuh"
 #include "gemm16.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tf32.cuh"
@@ -121,6 +122,7 @@ static cudaError_t set_kernel_attributes() {
   if ((e = gemm16_set_attr()) != cudaSuccess) return e;
   if ((e = mlp16_set_attr()) != cudaSuccess) return e;
   if ((e = attention16_set_attr()) != cudaSuccess) return e;
+  if ((e = attention_tc_set_attr()) != cudaSuccess) return e;
   if ((e = tail16_set_attr()) != cudaSuccess) return e;
   if ((e = tail16r_set_attr()) != cudaSuccess) return e;
   if ((e = front16_set_attr()) != cudaSuccess) return e;
@@ -342,6 +344,7 @@ struct cfen_plan {
                              // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
   int maps16 = 2;      // 0: fp32 maps; 1: fp16 full-resolution maps only; 2: every stage map is fp16
   //     // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
+  int attn_tc = 1;     // gemm_path 2, 256-token windows with 24-wide heads: tcgen05 / TMEM attention (attn_tc.cuh)
   int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
                        // as one kernel reading the NHWC map (vit_front16.cuh); tokenize_local is not launched
   int tail_variant = 1;  // 0: residual tile in shared memory (vit_tail16.cuh); 1: residual in TMEM for E = 96, two CTAs
@@ -525,6 +528,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* ft = getenv("CFEN_FUSE_TAIL")) p->fuse_tail = atoi(ft) != 0;
   p->tail_variant = default_tail_variant();
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
+  if (const char* at = getenv("CFEN_ATTN_TC")) p->attn_tc = atoi(at) != 0;
   if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm);
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
@@ -585,6 +589,7 @@ extern "C" int32_t cfen_plan_get_option(const cfen_plan* p, const char* name, in
   if (strcmp(name, "gemm_path") == 0) { *value = p->gemm_path; return 0; }
   if (strcmp(name, "conv_path") == 0) { *value = p->conv_path; return 0; }
   if (strcmp(name, "fuse_front") == 0) { *value = p->fuse_front; return 0; }
+  if (strcmp(name, "attn_tc") == 0) { *value = p->attn_tc; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { *value = p->fuse_tail; return 0; }
   if (strcmp(name, "split_k") == 0) { *value = p->split_k; return 0; }
   return fail(5, "unknown option '%s'", name);
@@ -606,6 +611,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_tail") == 0) { p->fuse_tail = value != 0; return 0; }
   if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
+  if (strcmp(name, "attn_tc") == 0) { p->attn_tc = value != 0; return 0; }
   if (strcmp(name, "maps16") == 0) { p->maps16 = (int)value; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
@@ -949,6 +955,11 @@ static int run_ln16(Run& r, const float* x, __half* y16, const float* g, const f
 }
 static int run_attn16(Run& r, const __half* qkv, __half* o, int nseq, int L, int E, int heads) {
   Launch l(r, PC_ATTN, 4.0 * nseq * (double)L * L * E, 8.0 * nseq * L * E, "attn16 n%d L%d E%d h%d", nseq, L, E, heads);
+  if (r.p->attn_tc && attention_tc_supported(L, E, heads)) {
+    l.sym("attention_tc_kernel");
+    CU(launch_attention_tc(qkv, o, nseq, L, E, heads, r.st));
+    return 0;
+  }
   l.sym("attention16_kernel<%d>", E / heads);
   CU(launch_attention16(qkv, o, nseq, L, E, heads, r.st));
   return 0;
@@ -1530,6 +1541,12 @@ extern "C" int32_t cfen_attention_f16(const void* qkv16, void* out16, int32_t ns
   if (heads <= 0 || E % heads != 0 || (E / heads != 24 && E / heads != 96))
     return fail(1, "cfen_attention_f16: head dim must be 24 or 96");
   CU(set_kernel_attributes());
+  const char* at = getenv("CFEN_ATTN_TC");   // same selection as the plan (option "attn_tc")
+  if ((!at || atoi(at) != 0) && attention_tc_supported(L, E, heads)) {
+    CU(launch_attention_tc(static_cast<const __half*>(qkv16), static_cast<__half*>(out16), nseq, L, E, heads,
+                           static_cast<cudaStream_t>(stream)));
+    return 0;
+  }
   CU(launch_attention16(static_cast<const __half*>(qkv16), static_cast<__half*>(out16), nseq, L, E, heads,
                         static_cast<cudaStream_t>(stream)));
   return 0;

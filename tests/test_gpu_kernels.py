@@ -247,6 +247,36 @@ def test_attention_f16(nseq, Lq, E, heads):
     assert U.rel_err(out, ref) <= 2e-3           # P and the output are rounded to fp16
 
 
+@pytest.mark.parametrize("nseq,E,heads", [(1, 96, 4), (3, 96, 4), (5, 192, 8), (2, 384, 16), (100, 96, 4), (333, 96, 4)])
+@pytest.mark.parametrize("scale", [1.0, 4.0])
+def test_attention_tc(nseq, E, heads, scale, monkeypatch):
+    """attention_tc_kernel (tcgen05 / TMEM; 256-token windows, 24-wide heads; attn_tc.cuh) through cfen_attention_f16,
+    against fp64 softmax attention AND against the mma.sync kernel it replaces (CFEN_ATTN_TC=0) on the same operands.
+    nseq*heads runs from fewer items than CTAs (1 window) to several items per CTA (333 windows x 4 heads over 296
+    CTAs: both operand stages, barrier phases beyond the first wrap); scale 4 gives peaked softmax rows (|s| ~ 80)."""
+    L = _native.lib()
+    Lq, hd = 256, 24
+    qkv16 = to_f16(dev(nseq * Lq, 3 * E, seed=1) * scale)
+    out = torch.full((nseq * Lq, E), float("nan"), device="cuda", dtype=torch.float16)
+    monkeypatch.setenv("CFEN_ATTN_TC", "1")
+    G.check(L.cfen_attention_f16(G.ptr(qkv16), G.ptr(out), nseq, Lq, E, heads, G.stream()))
+    torch.cuda.synchronize()
+    old = torch.full_like(out, float("nan"))
+    monkeypatch.setenv("CFEN_ATTN_TC", "0")
+    G.check(L.cfen_attention_f16(G.ptr(qkv16), G.ptr(old), nseq, Lq, E, heads, G.stream()))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all())
+    ref = torch.empty(nseq * Lq, E, dtype=torch.float64, device="cuda")
+    for lo in range(0, nseq, 64):      # fp64 reference in slices (memory)
+        hi = min(nseq, lo + 64)
+        blk = qkv16[lo * Lq:hi * Lq]
+        q, k, v = (z.view(hi - lo, Lq, heads, hd).transpose(1, 2).double() for z in blk.split(E, dim=-1))
+        att = torch.softmax(q @ k.transpose(-1, -2) / hd ** 0.5, dim=-1)
+        ref[lo * Lq:hi * Lq] = (att @ v).transpose(1, 2).reshape((hi - lo) * Lq, E)
+    assert U.rel_err(out, ref) <= 2e-3           # P and the output are rounded to fp16
+    assert U.rel_err(out, old.double()) <= 3e-3
+
+
 @pytest.mark.parametrize("rows,E", [(1001, 96), (257, 192), (64, 384), (33, 768), (16, 1536)])
 def test_layernorm(rows, E):
     L = _native.lib()

@@ -23,6 +23,27 @@ def h16(x):
 
 
 which = sys.argv[1]
+if which == "attn":      # prof_one.py attn E heads nseq [L]   (CFEN_ATTN_TC=0/1 selects the kernel)
+    E, heads, nseq = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    Lq = int(sys.argv[5]) if len(sys.argv) > 5 else 256
+    qkv = h16(torch.randn(nseq * Lq, 3 * E, device="cuda"))
+    o = torch.empty(nseq * Lq, E, device="cuda", dtype=torch.float16)
+    run = lambda: _native.check(L.cfen_attention_f16(P(qkv), P(o), nseq, Lq, E, heads, ST()))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    N = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(N):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / N
+    print("attn tc=%s E%d h%d nseq%d L%d: %.1f us/launch  %.1f TFLOP/s  %.0f GB/s" % (
+        os.environ.get("CFEN_ATTN_TC", "1"), E, heads, nseq, Lq, us, 4.0 * nseq * Lq * Lq * E / us / 1e6,
+        8.0 * nseq * Lq * E / us / 1e3))
+    sys.exit(0)
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 hid = int(sys.argv[3]) if len(sys.argv) > 3 else 4 * E
 M = int(sys.argv[4]) if len(sys.argv) > 4 else 148 * 256
