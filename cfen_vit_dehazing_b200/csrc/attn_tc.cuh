@@ -6,19 +6,23 @@
 // against all 256 keys.  A CTA walks a contiguous range of items; two CTAs share an SM (256 TMEM columns each) and
 // overlap each other's MMA / softmax phases.
 //
-//   warp 0     loader: cp.async (16-byte chunks) of the item's Q, K, V into UMMA's canonical NO-SWIZZLE layout -
+//   warp 5     loader: cp.async (16-byte chunks) of the item's Q, K, V into UMMA's canonical NO-SWIZZLE layout -
 //              per operand four panels [8-column chunk][256 rows][16 bytes]: the three chunks of the 24-wide head plus
 //              a constant fourth panel (zeros for Q / K: the contraction is padded 24 -> 32; a ones column for V: the
 //              softmax row sums fall out of the P V product in fp32, from exactly the rounded probabilities) -
 //              double-buffered over items, handed to the tensor core through an mbarrier
-//   warp 1     MMA issuer, owns TMEM.  S = Q K^T: 2 x tcgen05.mma kind::f16 M=128 N=256 K=16 (both operands K-major from
+//   warp 4     MMA issuer, owns TMEM.  S = Q K^T: 2 x tcgen05.mma kind::f16 M=128 N=256 K=16 (both operands K-major from
 //              shared memory) into TMEM columns [0,256).  O = P V: 16 x tcgen05.mma M=128 N=32 K=16 with the A operand
-//              (P, fp16 pairs) read FROM TENSOR MEMORY and V as an MN-major shared-memory operand, into columns [128,160)
-//   warps 2-5  softmax + epilogue, one query row per thread (TMEM lane = row): row max straight from tcgen05.ld (no
+//              (P, fp16 pairs) read FROM TENSOR MEMORY and V as an MN-major shared-memory operand, into columns [64,96);
+//              issued in two parts (12 + 4 key steps) as the softmax hands P over
+//   warps 0-3  softmax + epilogue, one query row per thread (TMEM lane = row): row max straight from tcgen05.ld (no
 //              shuffles), P = exp2((s - max) * c) in fp32 (ex2.approx.f16x2 is two MUFU ops in SASS anyway), rounded to
 //              fp16 pairs and written back over S with tcgen05.st (P aliases the first 128 columns of S), then
 //              O / rowsum -> fp16 -> global
 //
+// The two single-lane roles sit on the HIGHEST warp ids: the sub-partition arbiter prefers the higher warp id, and as
+// warps 0 / 1 they were starved by the softmax warps sharing their sub-partition (16 MMA issues took 500+ cycles, the
+// loader 7000; device-side timeline, tools/attn_tc_timeline.cu).
 // Nothing but q, k, v is read from and o written to HBM; S and P never leave the SM.
 #pragma once
 #include "tc_common.cuh"
@@ -34,7 +38,9 @@ struct AttnTcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE + 128;
   static constexpr int THREADS = 192;
   static constexpr int TMEM_COLS = 256;
-  static constexpr int O_COL = 128;               // O accumulator columns [128,160) (behind P, inside the S region)
+  static constexpr int P_COL = 128;               // P (fp16 pairs) columns [128,256)
+  static constexpr int O_COL = 64;                // O accumulator columns [64,96): free once six S chunks are consumed
+  static constexpr int KS_A = 4;                  // first P V part = key steps [4,16) (keys 64..255), second = [0,4)
 };
 
 namespace tc {
@@ -86,6 +92,14 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 }  // namespace tc
 
+#ifdef ATC_TIMELINE
+// device-side timeline of CTA 0 (tools/attn_tc_timeline.cu; compiled out of the library)
+__device__ long long* g_atc_tl = nullptr;   // [6 warps][4096] (id, clock) pairs
+#define ATC_TL(id) do { if (blockIdx.x == 0 && lane == 0 && g_atc_tl && tl_n < 2040) { \
+    g_atc_tl[warp * 4096 + 2 * tl_n] = (id); g_atc_tl[warp * 4096 + 2 * tl_n + 1] = clock64(); ++tl_n; } } while (0)
+#else
+#define ATC_TL(id) do {} while (0)
+#endif
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -98,7 +112,7 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
   using Cfg = AttnTcCfg;
   extern __shared__ uint8_t atc_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES];
-  __shared__ __align__(8) uint64_t s_full, p_full, o_full, o_free;
+  __shared__ __align__(8) uint64_t s_full, p_full, p_full2, o_full, o_free;
   __shared__ uint32_t tmem_slot;
 
   const uint32_t raw = smem_u32(atc_smem_raw);
@@ -115,11 +129,12 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
     *reinterpret_cast<uint4*>(smem + st * Cfg::STAGE + op * Cfg::OPERAND + 3 * Cfg::PANEL + row * 16) = v;
   }
   tc::fence_async_smem();
-  if (warp == 1) {
+  if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
       tc::mbar_init(&s_full, 1);
       tc::mbar_init(&p_full, 128);
+      tc::mbar_init(&p_full2, 128);
       tc::mbar_init(&o_full, 1);
       tc::mbar_init(&o_free, 128);
       tc::mbar_fence_init();
@@ -132,32 +147,42 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const int E3 = 3 * E;
+  int tl_n = 0; (void)tl_n;
 
-  if (warp == 0) {  // ------------------------------------------------ loader
+  if (warp == 5) {  // ------------------------------------------------ loader
     for (int it = first, k = 0; it < last; ++it, ++k) {
       const int s = k & 1;
       tc::mbar_wait(&empty_bar[s], ((k >> 1) & 1) ^ 1);
+      ATC_TL(1);
       const int seq = it / heads, h = it - seq * heads;
       const __half* src = qkv + (size_t)seq * Cfg::L * E3 + h * Cfg::HD;
       uint8_t* dst = smem + s * Cfg::STAGE;
       // 256 rows x 3 operands x 3 chunks of 16 bytes; consecutive lanes take the 3 chunks of a row, then the next row
+      // (a warp-wide copy touches 11 cache lines instead of 32); the (chunk, row, operand) of element lane + 32 k is
+      // stepped incrementally: 32 = 10 rows + 2 chunks
+      int c = lane % 3, row = lane / 3, op = 0;
 #pragma unroll 4
-      for (int i = lane; i < 3 * Cfg::L * 3; i += 32) {
-        const int c = i % 3, row = (i / 3) % Cfg::L, op = i / (3 * Cfg::L);
+      for (int k = 0; k < 3 * Cfg::L * 3 / 32; ++k) {
         cp_async16(dst + op * Cfg::OPERAND + c * Cfg::PANEL + row * 16, src + (size_t)row * E3 + op * E + c * 8, true);
+        c += 2; row += 10;
+        if (c >= 3) { c -= 3; row += 1; }
+        if (row >= Cfg::L) { row -= Cfg::L; op += 1; }
       }
+      ATC_TL(2);
       tc::cp_async_wait_all();
+      ATC_TL(3);
       tc::fence_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[s]);
     }
-  } else if (warp == 1) {  // ----------------------------------------- MMA issuer
+  } else if (warp == 4) {  // ----------------------------------------- MMA issuer
     constexpr uint32_t idesc_s = tc::umma_idesc_f16(128, 256);
     constexpr uint32_t idesc_o = tc::umma_idesc_f16_bmn(128, 32);
     int t = 0;
     for (int it = first, k = 0; it < last; ++it, ++k) {
       const int s = k & 1;
       tc::mbar_wait(&full_bar[s], (k >> 1) & 1);
+      ATC_TL(10);
       tc::tc_fence_after();
       const uint32_t q_addr = smem_u32(smem + s * Cfg::STAGE);
       const uint32_t k_addr = q_addr + Cfg::OPERAND, v_addr = q_addr + 2 * Cfg::OPERAND;
@@ -166,6 +191,7 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
           tc::mbar_wait(&o_free, (t - 1) & 1);
           tc::tc_fence_after();
         }
+        ATC_TL(11);
         if (tc::elect_one()) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)   // k-step j = chunks 2j, 2j+1 (chunk 3 = zeros)
@@ -174,75 +200,99 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
           tc::umma_commit(&s_full);
         }
         __syncwarp();
+        ATC_TL(12);
         tc::mbar_wait(&p_full, t & 1);
+        ATC_TL(13);
         tc::tc_fence_after();
         if (tc::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < Cfg::L / 16; ++ks)   // 16 keys per step: 8 TMEM columns of P, 2 K-groups of V
-            tc::umma_f16_ts(tmem + Cfg::O_COL, tmem + ks * 8, tc::umma_desc_nosw(v_addr + ks * 256, 128, Cfg::PANEL),
-                            idesc_o, ks);
+          for (int ks = Cfg::KS_A; ks < Cfg::L / 16; ++ks)   // 16 keys per step: 8 TMEM columns of P, 2 K-groups of V
+            tc::umma_f16_ts(tmem + Cfg::O_COL, tmem + Cfg::P_COL + ks * 8,
+                            tc::umma_desc_nosw(v_addr + ks * 256, 128, Cfg::PANEL), idesc_o, ks != Cfg::KS_A);
+        }
+        __syncwarp();
+        tc::mbar_wait(&p_full2, t & 1);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < Cfg::KS_A; ++ks)
+            tc::umma_f16_ts(tmem + Cfg::O_COL, tmem + Cfg::P_COL + ks * 8,
+                            tc::umma_desc_nosw(v_addr + ks * 256, 128, Cfg::PANEL), idesc_o, 1);
           tc::umma_commit(&o_full);
           if (qt == 1) tc::umma_commit(&empty_bar[s]);   // Q, K, V of this item are no longer read
         }
         __syncwarp();
+        ATC_TL(14);
       }
     }
-  } else {  // -------------------------------------------------------- softmax + epilogue (warps 2..5)
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+  } else {  // -------------------------------------------------------- softmax + epilogue (warps 0..3)
+    const int q = warp;                           // TMEM lane quarter this warp may access (warp id % 4)
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     int t = 0;
     for (int it = first; it < last; ++it) {
       const int seq = it / heads, h = it - seq * heads;
       for (int qt = 0; qt < 2; ++qt, ++t) {
         tc::mbar_wait(&s_full, t & 1);
+        ATC_TL(20);
         tc::tc_fence_after();
         // ---- pass 1: row max of the raw scores
         uint32_t a[32], b[32];
         float m = -INFINITY;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: FMNMX3 has 4-cycle latency
         tc::tmem_ld32(trow, a);
         tc::tmem_ld_wait_dep(a);
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           tc::tmem_ld32(trow + 32 * (j + 1), b);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+          for (int i = 0; i < 32; i += 2) m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
           tc::tmem_ld_wait_dep(b);
           if (j + 2 < 8) tc::tmem_ld32(trow + 32 * (j + 2), a);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
+          for (int i = 0; i < 32; i += 2) m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
           if (j + 2 < 8) tc::tmem_ld_wait_dep(a);
         }
-        // ---- pass 2: P = exp2(s*c - m*c) as fp16 pairs, written over S (chunk j of P lands in columns S chunk j/2
-        // occupied, which this thread has already consumed)
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        // ---- pass 2: P = exp2(s*c - m*c) as fp16 pairs.  The 256 TMEM columns hold S (fp32), P (fp16 pairs, 128
+        // columns) and O (32 columns) at once: the chunks are consumed from the top (keys 224.. first), chunk j of P
+        // goes to columns 128 + 16 j - inside S chunk 4 + j/2, which this thread has consumed by then - and after six
+        // chunks the columns [64,128) are free for O.  P is handed to the tensor core in two parts (keys 64..255, then
+        // keys 0..63) so that most of the P V product runs under the rest of the softmax.
         const float nb = -m * scale_log2e;
-        tc::tmem_ld32(trow, a);
+        ATC_TL(21);
+        tc::tmem_ld32(trow + 32 * 7, a);
         tc::tmem_ld_wait_dep(a);
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
+        for (int j = 7; j > 0; j -= 2) {
           uint32_t p[16];
-          tc::tmem_ld32(trow + 32 * (j + 1), b);
+          tc::tmem_ld32(trow + 32 * (j - 1), b);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             p[i] = pack_half2(fast_exp2(fmaf(__uint_as_float(a[2 * i]), scale_log2e, nb)),
                               fast_exp2(fmaf(__uint_as_float(a[2 * i + 1]), scale_log2e, nb)));
           tc::tmem_ld_wait_dep(b);
-          tc::tmem_st16(trow + 16 * j, p);
-          if (j + 2 < 8) tc::tmem_ld32(trow + 32 * (j + 2), a);
+          tc::tmem_st16(trow + Cfg::P_COL + 16 * j, p);
+          if (j > 1) tc::tmem_ld32(trow + 32 * (j - 2), a);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             p[i] = pack_half2(fast_exp2(fmaf(__uint_as_float(b[2 * i]), scale_log2e, nb)),
                               fast_exp2(fmaf(__uint_as_float(b[2 * i + 1]), scale_log2e, nb)));
-          if (j + 2 < 8) tc::tmem_ld_wait_dep(a);
-          tc::tmem_st16(trow + 16 * (j + 1), p);
+          if (j > 1) tc::tmem_ld_wait_dep(a);
+          tc::tmem_st16(trow + Cfg::P_COL + 16 * (j - 1), p);
+          if (j == 3 || j == 1) {   // chunks 7..2 (keys 64..255) / chunks 1, 0 written
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(j == 3 ? &p_full : &p_full2);
+          }
         }
-        tc::tmem_st_wait();
-        tc::tc_fence_before();
-        tc::mbar_arrive(&p_full);
+        ATC_TL(22);
         // ---- O = P V (+ row sum in column 24)
         tc::mbar_wait(&o_full, t & 1);
+        ATC_TL(23);
         tc::tc_fence_after();
         tc::tmem_ld32(trow + Cfg::O_COL, a);
         tc::tmem_ld_wait_dep(a);
+        ATC_TL(24);
         tc::tc_fence_before();
         tc::mbar_arrive(&o_free);
         const float inv = 1.f / __uint_as_float(a[24]);
@@ -255,12 +305,13 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        ATC_TL(25);
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem);
+  if (warp == 4) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem);
 }
 
 inline bool attention_tc_supported(int L, int E, int heads) {
