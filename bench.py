@@ -416,6 +416,29 @@ def run_ours(args):
         barrier()
         e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
 
+        # ---------------- the same end-to-end call on uint8 HWC images (fused boundary): all three
+        # outputs, and fake_A only (test.py:47-55).  Extra keys; `e2e` above stays the fp32 module contract.
+        e2e_variants = {}
+        g3 = torch.Generator().manual_seed(2000 + rank)
+        host_u8 = torch.randint(0, 256, (B, size, size, 3), generator=g3, dtype=torch.uint8).pin_memory()
+        for vname, outs_sel in (("uint8_all_outputs", None), ("uint8_fake_A_only", ("fake_A",))):
+            n_out = 1 if outs_sel else 3
+            bufs = [[torch.empty((B, size, size, 3), dtype=torch.uint8).pin_memory() for _ in range(n_out)] for _ in range(2)]
+            for k in range(2):
+                net.forward_host(host_u8, out=bufs[k & 1], defer_sync=True, outputs=outs_sel)
+            net.host_sync()
+            barrier()
+            t0 = time.perf_counter()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record(stream)
+            for k in range(args.steps):
+                net.forward_host(host_u8, out=bufs[k & 1], defer_sync=True, outputs=outs_sel)
+            net.host_sync()
+            u1.record(stream)
+            barrier()
+            e2e_variants[vname] = {"ms": max(u0.elapsed_time(u1), 1e3 * (time.perf_counter() - t0)),
+                                   "h2d_bytes_per_step": host_u8.numel(), "d2h_bytes_per_step": n_out * host_u8.numel()}
+
         # ---------------- batch-1 latency, CUDA-graph replay (BASELINE configs[1])
         lat = None
         if rank == 0 and not args.no_latency:
@@ -444,9 +467,12 @@ def run_ours(args):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+        vnames = sorted(e2e_variants)
+        t = torch.tensor([ms_total, e2e_ms] + [e2e_variants[v]["ms"] for v in vnames], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = t.tolist()
+        ms_total, e2e_ms = t.tolist()[:2]
+        for v, ms in zip(vnames, t.tolist()[2:]):
+            e2e_variants[v]["ms"] = ms
         fin = torch.tensor([1 if finite else 0], device=dev)
         dist.all_reduce(fin, op=dist.ReduceOp.MIN)
         finite = bool(fin.item())
@@ -499,6 +525,11 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "api": "dec_ipt.forward_host(pinned [B,3,H,W] fp32, out=pinned [xr,xs,xd], defer_sync=True) per step, "
                            "host_sync() before the closing event: every H2D and D2H lies inside the timed region"},
+            "e2e_variants": {v: {"value": images / (d["ms"] / 1e3), "unit": "images/s", "ms_per_step": d["ms"] / args.steps,
+                                 "h2d_bytes_per_step": d["h2d_bytes_per_step"], "d2h_bytes_per_step": d["d2h_bytes_per_step"],
+                                 "api": "dec_ipt.forward_host(pinned uint8 [B,H,W,3]%s): normalisation / tensor2im fused into "
+                                        "the head loader / tail epilogues" % (", outputs=('fake_A',)" if "fake_A" in v else "")}
+                             for v, d in e2e_variants.items()},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roof,
             "roofline_all": roofline_all,

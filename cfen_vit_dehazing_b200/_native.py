@@ -21,13 +21,16 @@ EXPORTED_SYMBOLS = (
     "cfen_plan_create", "cfen_plan_destroy", "cfen_plan_set_weight", "cfen_plan_pack_weights",
     "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option", "cfen_plan_get_option",
     "cfen_plan_profile_json", "cfen_plan_profile_trace",
-    "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8",
+    "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8", "cfen_forward_ex",
     "cfen_plan_stage_ptr",
     "cfen_f32_to_f16", "cfen_debug_set_buffer", "cfen_gemm_f16", "cfen_mlp_f16", "cfen_layernorm_f16", "cfen_attention_f16", "cfen_vit_tail_f16", "cfen_vit_front_f16",
     "cfen_gemm_tf32", "cfen_gemm_tc", "cfen_mlp_tc", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
     "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_conv2d_instnorm_relu_nhwc", "cfen_cfsm", "cfen_merge_lg",
     "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward",
 )
+
+
+IO_U8, ONLY_FAKE_A = 1, 2     # cfen_forward_ex io_flags (include/cfen_b200.h)
 
 
 class cfen_config(ctypes.Structure):
@@ -64,6 +67,7 @@ def lib():
         L.cfen_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_forward_calibrate.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.cfen_forward_u8.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.cfen_forward_ex.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
         L.cfen_plan_stage_ptr.argtypes = [vp, cp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
         L.cfen_gemm_tf32.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]
         L.cfen_gemm_tc.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]
@@ -153,6 +157,10 @@ class Plan:
 
     def calibrate(self, batch, x, xr, xs, xd, stream):
         check(lib().cfen_forward_calibrate(self._h, batch, x, xr, xs, xd, ctypes.c_void_p(stream)))
+
+    def forward_ex(self, batch, x, xr, xs, xd, io_flags, stream):
+        """io_flags: IO_U8 (uint8 HWC images) | ONLY_FAKE_A (xr / xs may be None / 0)."""
+        check(lib().cfen_forward_ex(self._h, batch, x, xr or None, xs or None, xd, io_flags, ctypes.c_void_p(stream)))
 
     def forward_u8(self, batch, x_u8, xr_u8, xs_u8, xd_u8, stream):
         check(lib().cfen_forward_u8(self._h, batch, x_u8, xr_u8, xs_u8, xd_u8, ctypes.c_void_p(stream)))

@@ -330,7 +330,6 @@ struct cfen_plan {
   size_t sync_used = 0;
   int streams = 1;                   // 1: lanes run concurrently (default); 0: everything on the caller's stream
   std::map<std::string, std::pair<float*, int64_t>> stage;  // named maps (per-image floats)
-  float *u8_in = nullptr, *u8_xr = nullptr, *u8_xs = nullptr, *u8_xd = nullptr;
   long long launches = 0, launches_last = 0;
   bool calibrating = false;
   // 2: fp16 operands on tcgen05 + TMA (gemm16 / mlp16 / attn16, default); 1: TF32 tcgen05 (gemm_tc / mlp_tc);
@@ -449,8 +448,6 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
       add(("d2" + b).c_str(), M2); add(("u2" + b).c_str(), M1); add(("d1in" + b).c_str(), M1);
       add(("d1" + b).c_str(), M1);
     }
-    p->u8_in = a.take(HH * 3 * nb); p->u8_xr = a.take(HH * 3 * nb);
-    p->u8_xs = a.take(HH * nb); p->u8_xd = a.take(HH * 3 * nb);
   }
 }
 
@@ -1208,8 +1205,12 @@ static int run_block(Run& r, int si, const float* x, float* out) {
   return run_conv(r, name, L.lws.t1, L.gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES);
 }
 
+// io: CFEN_IO_U8 = uint8 HWC images at the boundary (fused into the head loader / tail epilogue),
+//     CFEN_ONLY_FAKE_A = only xd is produced: the R / S level-1 blocks, last up-convolutions and tails do not feed it
+//     (v3.py:607-697, 709-853; test.py:47-55 keeps only fake_A)
 static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float* xs, float* xd,
-                         cudaStream_t st) {
+                         cudaStream_t st, int io) {
+  const bool u8 = (io & CFEN_IO_U8) != 0, only_d = (io & CFEN_ONLY_FAKE_A) != 0;
   const int H = p->H, H1 = p->Hl[1], H2 = p->Hl[2], H3 = p->Hl[3];
   auto S = [&](const std::string& n) { return p->stage[n].first; };
   // streams: lanes run concurrently unless disabled, timing every launch (serial per-kernel numbers) or
@@ -1230,7 +1231,7 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
     Run& r = r0;
     float *f0 = r.ln->f0, *f1 = r.ln->f1, *f2 = S("f2");
     // head: conv5x5 + ResBlock (v3.py:395)
-    RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, O16));
+    RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H, H, O16 | (u8 ? CF_IN_U8 : 0)));
     RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H, H, CF_RELU | I16 | O16));
     RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, f2, H, H, CF_RES | I16 | O16 | R16));
     RET(run_conv_in_relu(r, "ds_conv_e01", f2, S("xf"), H1, H1, H1, H1, 24, I16));
@@ -1272,6 +1273,7 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
   for (int bi = 0; bi < 3; ++bi) {
     Run& r = rr[bi];
     const std::string b(brs[bi]);
+    if (bi < 2 && only_d) continue;
     if (bi < 2) {
       RET(run_conv(r, "sk_conv_d02" + b, S("u2" + b), S("e1"), nullptr, S("d1in" + b), H1, H1, CF_RELU));
     } else {
@@ -1283,17 +1285,22 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
     float *f0 = r.ln->f0, *f1 = r.ln->f1;
     RET(run_conv(r, "us_conv_d01" + b, S("d1" + b), S("xf"), nullptr, f0, H1, H1, CF_RELU | O16));
     RET(run_conv(r, std::string(tails[bi]) + ".c1", f0, nullptr, nullptr, f1, H, H, CF_RELU | I16 | O16));
-    RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H, H, CF_TANH | CF_OUT_NCHW | I16));
+    RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H, H,
+                 CF_TANH | CF_OUT_NCHW | I16 | (u8 ? CF_OUT_U8 : 0)));
   }
   for (int bi = 1; bi < 3; ++bi) RET(stream_edge(p, rr[bi].st, st));   // join
   return 0;
 }
 
-static int forward_impl(cfen_plan* p, int batch, const float* in, float* xr, float* xs, float* xd, void* stream,
-                        bool calibrate) {
+static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void* xs, void* xd, void* stream,
+                        bool calibrate, int io) {
   if (!p) return fail(1, "cfen_forward: null plan");
   if (!p->packed) return fail(8, "cfen_forward: weights not packed (call cfen_plan_pack_weights)");
-  if (batch < 0 || !in || !xr || !xs || !xd) return fail(1, "cfen_forward: bad argument");
+  const bool only_d = (io & CFEN_ONLY_FAKE_A) != 0, u8 = (io & CFEN_IO_U8) != 0;
+  if (batch < 0 || !in || !xd || (!only_d && (!xr || !xs))) return fail(1, "cfen_forward: bad argument");
+  if (io & ~(CFEN_IO_U8 | CFEN_ONLY_FAKE_A)) return fail(1, "cfen_forward_ex: unknown io flag bits 0x%x", io);
+  if (calibrate && io) return fail(1, "cfen_forward_calibrate takes fp32 tensors and produces all three outputs");
+  if (u8 && !p->conv_path) return fail(3, "the fused uint8 boundary needs the conv16 generation (conv_path 1)");
   if (calibrate && batch > p->nbmax)
     return fail(9, "calibration batch %d exceeds plan max_batch %d (ActNorm statistics span the whole batch)",
                 batch, p->nbmax);
@@ -1301,13 +1308,18 @@ static int forward_impl(cfen_plan* p, int batch, const float* in, float* xr, flo
   DeviceGuard dg(p->cfg.device);
   CU(dg.err);
   const size_t HW = (size_t)p->H * p->W;
+  // bytes per image of the input / of a three-channel output / of the one-channel output (uint8 outputs are HWC x3)
+  const size_t in_b = u8 ? 3 * HW : 12 * HW, o3_b = u8 ? 3 * HW : 12 * HW, o1_b = u8 ? 3 * HW : 4 * HW;
   p->launches = 0;
   p->calibrating = calibrate;
 
   int rc = 0;
   for (int b0 = 0; b0 < batch && rc == 0; b0 += p->nbmax) {
     const int nb = batch - b0 < p->nbmax ? batch - b0 : p->nbmax;
-    rc = forward_chunk(p, nb, in + b0 * 3 * HW, xr + b0 * 3 * HW, xs + b0 * HW, xd + b0 * 3 * HW, st);
+    auto at = [&](const void* base, size_t per) {
+      return base ? reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(base)) + (size_t)b0 * per) : nullptr;
+    };
+    rc = forward_chunk(p, nb, at(in, in_b), at(xr, o3_b), at(xs, o1_b), at(xd, o3_b), st, io);
     if (b0 == 0) p->launches_last = p->launches;
   }
   p->calibrating = false;
@@ -1316,33 +1328,19 @@ static int forward_impl(cfen_plan* p, int batch, const float* in, float* xr, flo
 
 extern "C" int32_t cfen_forward(cfen_plan* p, int32_t batch, const float* in, float* xr, float* xs, float* xd,
                                 void* stream) {
-  return forward_impl(p, batch, in, xr, xs, xd, stream, false);
+  return forward_impl(p, batch, in, xr, xs, xd, stream, false, 0);
 }
 extern "C" int32_t cfen_forward_calibrate(cfen_plan* p, int32_t batch, const float* in, float* xr, float* xs,
                                           float* xd, void* stream) {
-  return forward_impl(p, batch, in, xr, xs, xd, stream, true);
+  return forward_impl(p, batch, in, xr, xs, xd, stream, true, 0);
 }
-
+extern "C" int32_t cfen_forward_ex(cfen_plan* p, int32_t batch, const void* in, void* xr, void* xs, void* xd,
+                                   int32_t io_flags, void* stream) {
+  return forward_impl(p, batch, in, xr, xs, xd, stream, false, io_flags);
+}
 extern "C" int32_t cfen_forward_u8(cfen_plan* p, int32_t batch, const uint8_t* in, uint8_t* xr, uint8_t* xs,
                                    uint8_t* xd, void* stream) {
-  if (!p || !in || !xr || !xs || !xd) return fail(1, "cfen_forward_u8: null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DeviceGuard dg(p->cfg.device);
-  CU(dg.err);
-  const int HW = p->H * p->W;
-  for (int b0 = 0; b0 < batch; b0 += p->nbmax) {
-    const int nb = batch - b0 < p->nbmax ? batch - b0 : p->nbmax;
-    const long long n = (long long)nb * HW;
-    u8hwc_to_f32nchw_kernel<<<ew_blocks(n), 256, 0, st>>>(in + (size_t)b0 * HW * 3, p->u8_in, nb, HW);
-    CU(cudaGetLastError());
-    RET(forward_impl(p, nb, p->u8_in, p->u8_xr, p->u8_xs, p->u8_xd, stream, false));
-    f32nchw_to_u8hwc_kernel<<<ew_blocks(n), 256, 0, st>>>(p->u8_xr, xr + (size_t)b0 * HW * 3, nb, 3, HW);
-    f32nchw_to_u8hwc_kernel<<<ew_blocks(n), 256, 0, st>>>(p->u8_xs, xs + (size_t)b0 * HW * 3, nb, 1, HW);
-    f32nchw_to_u8hwc_kernel<<<ew_blocks(n), 256, 0, st>>>(p->u8_xd, xd + (size_t)b0 * HW * 3, nb, 3, HW);
-    CU(cudaGetLastError());
-    p->launches_last += 4;
-  }
-  return 0;
+  return forward_impl(p, batch, in, xr, xs, xd, stream, false, CFEN_IO_U8);
 }
 
 extern "C" int32_t cfen_plan_stage_ptr(cfen_plan* p, const char* name, void** dev_ptr, int64_t* numel) {
@@ -1633,8 +1631,13 @@ extern "C" int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const flo
   // public flag bits: 0 relu, 1 tanh, 2 residual(extra), 3 out NCHW ; bit5: extra is a second input
   const bool extra_is_input = (flags & 32) != 0;
   // bits 8 / 9 / 10: `in` / `out` / the residual `extra` are fp16 NHWC maps (conv16 generation, plain NHWC loader)
+  // bit 11: `in` is a uint8 HWC image ("head5x5" only); bit 12: `out` is a uint8 HWC x3 image (with bit 3, tails only)
   const int f = (flags & (CF_RELU | CF_TANH | CF_RES | CF_OUT_NCHW)) | ((flags & 256) ? CF_IN16 : 0) |
-                ((flags & 512) ? CF_OUT16 : 0) | ((flags & 1024) ? CF_RES16 : 0);
+                ((flags & 512) ? CF_OUT16 : 0) | ((flags & 1024) ? CF_RES16 : 0) | ((flags & 2048) ? CF_IN_U8 : 0) |
+                ((flags & 4096) ? CF_OUT_U8 : 0);
+  if ((f & CF_IN_U8) && k != K_HEAD5) return fail(1, "cfen_conv2d_nhwc: uint8 input is the head convolution's loader");
+  if ((f & CF_OUT_U8) && ((k != K_T3 && k != K_T1) || !(f & CF_OUT_NCHW)))
+    return fail(1, "cfen_conv2d_nhwc: uint8 output is the tail convolutions' epilogue (with bit 3)");
   if ((f & CF_FMT_MASK) && ((f & CF_OUT_NCHW) && (f & CF_OUT16))) return fail(1, "cfen_conv2d_nhwc: fp16 output is NHWC only");
   return conv_oneoff(k, in, extra_is_input ? extra : nullptr, (f & CF_RES) ? extra : nullptr, weight, bias,
                      an_weight, an_bias, out, B, H, W, f, 0, static_cast<cudaStream_t>(stream));

@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
           const int c = c4 * 4;
           v = c < C1 ? ld_map4(a.in0, (img * C1 + (pidx * C1 + c)) >> 2, in16)
                      : ld_map4(a.in1, (img * C1 + (pidx * C1 + (c - C1))) >> 2, in16);
+        } else if (a.flags & CF_IN_U8) {   // uint8 HWC image: ToTensor + Normalize(0.5, 0.5) on load
+          const uint8_t* p = reinterpret_cast<const uint8_t*>(a.in0) + (img + pidx) * 3;
+          v = make_float4(((float)p[0] / 255.f - 0.5f) / 0.5f, ((float)p[1] / 255.f - 0.5f) / 0.5f,
+                          ((float)p[2] / 255.f - 0.5f) / 0.5f, 0.f);
         } else {  // LD_NCHW3
           const size_t plane = (size_t)Hin * Win;
           const float* p = a.in0 + img * 3 + pidx;
@@ -580,7 +584,23 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
     if constexpr (C::STAGED) {
       // coalesced copy-out: 16-byte pieces of the tile's output rows; residual loads of a batch go first
       constexpr int UO = 4;
-      if (flags & CF_OUT_NCHW) {
+      if ((flags & CF_OUT_NCHW) && (flags & CF_OUT_U8)) {
+        // tensor2im in the epilogue: 4 pixels x 3 channels = 12 bytes per thread, rows of the tile contiguous in HWC
+        constexpr int RW4 = C::TW / 4, TOTALP = C::TH * RW4;
+        constexpr int C1 = S::COUT > 1 ? 1 : 0, C2 = S::COUT > 2 ? 2 : 0;   // one-channel maps are tiled x3
+        uint8_t* obase = reinterpret_cast<uint8_t*>(a.out) + (((size_t)b * Hout + ty0) * Wout + tx0) * 3;
+        auto q8 = [](float y) -> uint32_t { return (uint32_t)fminf(fmaxf((y + 1.f) * 0.5f * 255.f, 0.f), 255.f); };
+        for (int i = tid; i < TOTALP; i += S::THREADS) {
+          const int y = i / RW4, x4 = i - y * RW4;
+          const float4 r = *reinterpret_cast<const float4*>(ost + (0 * C::TH + y) * C::TW + x4 * 4);
+          const float4 g4 = *reinterpret_cast<const float4*>(ost + (C1 * C::TH + y) * C::TW + x4 * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(ost + (C2 * C::TH + y) * C::TW + x4 * 4);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(obase + ((size_t)y * Wout + x4 * 4) * 3);
+          dst[0] = q8(r.x) | (q8(g4.x) << 8) | (q8(b4.x) << 16) | (q8(r.y) << 24);
+          dst[1] = q8(g4.y) | (q8(b4.y) << 8) | (q8(r.z) << 16) | (q8(g4.z) << 24);
+          dst[2] = q8(b4.z) | (q8(r.w) << 8) | (q8(g4.w) << 16) | (q8(b4.w) << 24);
+        }
+      } else if (flags & CF_OUT_NCHW) {
         constexpr int RW4 = C::TW / 4, TOTAL4 = S::COUT * C::TH * RW4;
         const size_t plane = (size_t)Hout * Wout;
         float* obase = a.out + (size_t)b * S::COUT * plane + (size_t)ty0 * Wout + tx0;

@@ -22,7 +22,13 @@ enum ConvLoader { LD_NHWC = 0, LD_NCHW3 = 1, LD_SUM2 = 2, LD_CAT2 = 3, LD_LG = 4
 enum ConvFlags {
   CF_RELU = 1, CF_TANH = 2, CF_RES = 4, CF_OUT_NCHW = 8,
   // fp16 map storage (conv16 generation only): in0 / out / res are __half NHWC maps
-  CF_IN16 = 16, CF_OUT16 = 32, CF_RES16 = 64, CF_FMT_MASK = 16 | 32 | 64
+  CF_IN16 = 16, CF_OUT16 = 32, CF_RES16 = 64, CF_FMT_MASK = 16 | 32 | 64,
+  // uint8 boundary fused into the first / last layer (conv16 generation only):
+  //   CF_IN_U8  (LD_NCHW3 loader): in0 is a uint8 HWC image [B,H,W,3]; the loader applies ToTensor + Normalize(0.5, 0.5)
+  //             (data/base_dataset.py:44-46): (u / 255 - 0.5) / 0.5
+  //   CF_OUT_U8 (with CF_OUT_NCHW staging): out is a uint8 HWC image [B,H,W,3] = tensor2im (util/util.py:12-24):
+  //             (y + 1) / 2 * 255 truncated to uint8, one-channel maps tiled to three channels
+  CF_IN_U8 = 128, CF_OUT_U8 = 256
 };
 
 struct ConvArgs {

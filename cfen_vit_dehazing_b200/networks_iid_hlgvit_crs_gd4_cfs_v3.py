@@ -500,7 +500,44 @@ class dec_ipt(nn.Module):
             lo += n
         return [torch.cat([p[i].to(out_dev, non_blocking=True) for p in parts], 0) for i in range(3)]
 
-    def forward_host(self, input, out=None, device=None, defer_sync=False):
+    # ------------------------------------------------------------------ fused uint8 boundary / fake_A-only (F1)
+    _OUTPUT_NAMES = ("fake_R", "fake_S", "fake_A")      # DECHLGVIT.forward, model_iid_dehazing.py:143
+
+    @classmethod
+    def _io_flags(cls, uint8, outputs):
+        names = tuple(outputs) if outputs is not None else cls._OUTPUT_NAMES
+        if names == cls._OUTPUT_NAMES:
+            only_a = False
+        elif names == ("fake_A",):
+            only_a = True
+        else:
+            raise ValueError("outputs must be %r or ('fake_A',), got %r" % (cls._OUTPUT_NAMES, names))
+        return (_native.IO_U8 if uint8 else 0) | (_native.ONLY_FAKE_A if only_a else 0), only_a
+
+    def forward_u8(self, images, outputs=None):
+        """uint8 HWC images in, uint8 HWC images out, on the device: [B,H,W,3] uint8 -> [fake_R, fake_S, fake_A] (or
+        [fake_A] with outputs=("fake_A",)) as [B,H,W,3] uint8.  ToTensor + Normalize(0.5, 0.5)
+        (data/base_dataset.py:44-46) runs inside the head convolution's loader, tensor2im (util/util.py:12-24: tanh
+        output -> (y+1)/2*255 -> uint8, one-channel maps tiled x3) inside the 7x7 tail epilogues."""
+        if not isinstance(images, torch.Tensor) or images.dim() != 4 or images.size(3) != 3 or images.dtype != torch.uint8:
+            raise RuntimeError("dec_ipt.forward_u8 expects a [B, H, W, 3] uint8 tensor")
+        if not images.is_cuda:
+            raise RuntimeError("cfen_vit_dehazing_b200 runs on sm_100a GPUs only: got a %s tensor and there is "
+                               "no CPU fallback" % images.device)
+        flags, only_a = self._io_flags(True, outputs)
+        x = images.contiguous()
+        b, h, w, _ = x.shape
+        with torch.cuda.device(x.device):
+            plan = self._plan_for(x.device, h, w, b)
+            if plan.needs_calibration:
+                raise RuntimeError("forward_u8 needs initialised ActNorm layers: run one forward() first or load a checkpoint")
+            outs = [None if (only_a and i < 2) else torch.empty((b, h, w, 3), dtype=torch.uint8, device=x.device)
+                    for i in range(3)]
+            plan.forward_ex(b, x.data_ptr(), *[o.data_ptr() if o is not None else None for o in outs], flags,
+                            torch.cuda.current_stream(x.device).cuda_stream)
+        return [o for o in outs if o is not None]
+
+    def forward_host(self, input, out=None, device=None, defer_sync=False, outputs=None):
         """Host-to-host forward for batches that start and end in (pinned) host memory - what
         DECHLGVIT.set_input (.to(device), model_iid_dehazing.py:126-136) + forward + tensor2im's .cpu()
         (util/util.py:12-24) do around the generator, restated as a three-stream pipeline: the H2D copy
@@ -508,38 +545,66 @@ class dec_ipt(nn.Module):
         images-per-pass chunk).  Returns [xr, xs, xd] as host tensors (`out` if given); they are
         complete when the current stream of `device` has been synchronised.  No CPU compute path.
 
+        input fp32 [B,3,H,W] in [-1,1] -> fp32 NCHW outputs (the module contract); input uint8 [B,H,W,3] -> uint8 HWC
+        outputs with the conversions fused into the first / last kernels (see forward_u8): 0.75 MB per image and
+        direction instead of 3.1 MB in / 7.3 MB out.  outputs=("fake_A",) produces and copies back only the dehazed
+        image (test.py:47-55) and skips the kernels that feed nothing else.
+
         defer_sync=True leaves the current stream independent of the trailing D2H copies, so the next
         forward_host call's copies and kernels overlap them (streaming a sequence of batches); the
         outputs of deferred calls are complete after host_sync()."""
-        if not isinstance(input, torch.Tensor) or input.dim() != 4 or input.size(1) != 3:
-            raise RuntimeError("dec_ipt.forward_host expects a [B, 3, H, W] tensor")
+        if not isinstance(input, torch.Tensor) or input.dim() != 4:
+            raise RuntimeError("dec_ipt.forward_host expects a [B, 3, H, W] fp32 or [B, H, W, 3] uint8 tensor")
         if input.is_cuda:
             raise RuntimeError("forward_host takes a host tensor; use forward() for device tensors")
-        if input.dtype != torch.float32 or not input.is_contiguous():
+        u8 = input.dtype == torch.uint8
+        if (u8 and input.size(3) != 3) or (not u8 and input.size(1) != 3):
+            raise RuntimeError("dec_ipt.forward_host expects a [B, 3, H, W] fp32 or [B, H, W, 3] uint8 tensor")
+        if u8:
+            input = input.contiguous()
+        elif input.dtype != torch.float32 or not input.is_contiguous():
             input = input.float().contiguous()
+        flags, only_a = self._io_flags(u8, outputs)
         dev = torch.device(device) if device is not None else next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("cfen_vit_dehazing_b200 runs on sm_100a GPUs only: the module lives on %s "
                                "and there is no CPU fallback" % dev)
-        b, _, h, w = input.shape
+        if u8:
+            b, h, w, _ = input.shape
+            in_shape = lambda n: (n, h, w, 3)
+            out_shapes = [lambda n: (n, h, w, 3)] * 3
+            dt = torch.uint8
+        else:
+            b, _, h, w = input.shape
+            in_shape = lambda n: (n, 3, h, w)
+            out_shapes = [lambda n, c=c: (n, c, h, w) for c in (3, 1, 3)]
+            dt = torch.float32
+        which = [2] if only_a else [0, 1, 2]
         if out is None:
-            out = [torch.empty((b, c, h, w), dtype=torch.float32).pin_memory() for c in (3, 1, 3)]
+            out = [torch.empty(out_shapes[i](b), dtype=dt).pin_memory() for i in which]
+        elif len(out) != len(which):
+            raise RuntimeError("forward_host: `out` must hold %d tensors for outputs=%r" % (len(which), outputs))
         with torch.cuda.device(dev):
             plan = self._plan_for(dev, h, w, b)
             if plan.needs_calibration:
                 raise RuntimeError("forward_host needs initialised ActNorm layers: run one forward() first "
                                    "(models/actnorm.py:25-37 initialises from that batch) or load a checkpoint")
             nb = plan.max_batch
-            key = (dev.index, h, w, nb)
-            st = getattr(self, "_host_pipe", {}).get(key)
+            key = (dev.index, h, w, nb, flags)
+            pipes = getattr(self, "_host_pipe", None)
+            if pipes is None:
+                pipes = self._host_pipe = {}
+            st = pipes.get(key)
             if st is None:
-                st = {"in": [torch.empty((nb, 3, h, w), device=dev) for _ in range(2)],
-                      "out": [[torch.empty((nb, c, h, w), device=dev) for c in (3, 1, 3)] for _ in range(2)],
+                for k in [k for k in pipes if k != key]:     # one staging set at a time (device memory)
+                    self._host_sync_one(pipes.pop(k))
+                st = {"in": [torch.empty(in_shape(nb), dtype=dt, device=dev) for _ in range(2)],
+                      "out": [[torch.empty(out_shapes[i](nb), dtype=dt, device=dev) for i in which] for _ in range(2)],
                       "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
                       # per device slot: the kernels that last read "in" / the D2H that last drained "out"; kept
                       # across calls so that deferred calls chain without a stream-wide join
                       "ev_comp": [None, None], "ev_out": [None, None], "next": 0, "dev": dev}
-                self._host_pipe = {key: st}
+                pipes[key] = st
             cur = torch.cuda.current_stream(dev)
             s_in, s_out = st["s_in"], st["s_out"]
             if not defer_sync:
@@ -565,8 +630,13 @@ class dec_ipt(nn.Module):
                 if st["ev_out"][slot] is not None:
                     cur.wait_event(st["ev_out"][slot])           # the D2H that last drained this slot is done
                 o = st["out"][slot]
-                plan.forward(n, st["in"][slot].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
-                             cur.cuda_stream)
+                ptrs = [None, None, None]
+                for j, idx in enumerate(which):
+                    ptrs[idx] = o[j].data_ptr()
+                if flags:
+                    plan.forward_ex(n, st["in"][slot].data_ptr(), ptrs[0], ptrs[1], ptrs[2], flags, cur.cuda_stream)
+                else:
+                    plan.forward(n, st["in"][slot].data_ptr(), ptrs[0], ptrs[1], ptrs[2], cur.cuda_stream)
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 st["ev_comp"][slot] = ev
@@ -581,13 +651,17 @@ class dec_ipt(nn.Module):
                 cur.wait_stream(s_out)
         return out
 
+    @staticmethod
+    def _host_sync_one(st):
+        cur = torch.cuda.current_stream(st["dev"])
+        cur.wait_stream(st["s_out"])
+        cur.synchronize()
+
     def host_sync(self):
         """Completes every forward_host(..., defer_sync=True) issued so far: the current stream of each pipeline's
         device waits for the D2H copies, then the host waits for that stream."""
-        for st in getattr(self, "_host_pipe", {}).values():
-            cur = torch.cuda.current_stream(st["dev"])
-            cur.wait_stream(st["s_out"])
-            cur.synchronize()
+        for st in (getattr(self, "_host_pipe", None) or {}).values():
+            self._host_sync_one(st)
 
 
 def _mark_dirty(module, _incompatible):

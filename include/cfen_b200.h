@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CFEN_ABI_VERSION 2
+#define CFEN_ABI_VERSION 3
 
 typedef struct cfen_plan cfen_plan;
 
@@ -94,10 +94,21 @@ int32_t cfen_forward_calibrate(cfen_plan* plan, int32_t batch, const float* in,
                                float* xr, float* xs, float* xd, void* stream);
 
 /* Fused pre/post-processing variant: uint8 HWC in ([batch,H,W,3]),
- * (x/255-0.5)/0.5 as data/base_dataset.py:44-46; uint8 HWC out, (y+1)/2*255 as
- * util/util.py:22-24 (xs is replicated to 3 channels like tensor2im does). */
+ * (x/255-0.5)/0.5 as data/base_dataset.py:44-46 applied by the head convolution's loader; uint8 HWC out,
+ * (y+1)/2*255 as util/util.py:22-24 applied in the 7x7 tail epilogues (xs is replicated to 3 channels like
+ * tensor2im does).  No extra kernels and no fp32 image ever exists in HBM. */
 int32_t cfen_forward_u8(cfen_plan* plan, int32_t batch, const uint8_t* in_hwc,
                         uint8_t* xr_hwc, uint8_t* xs_hwc, uint8_t* xd_hwc, void* stream);
+
+/* General form.  io_flags:
+ *   CFEN_IO_U8        the four images are uint8 HWC as in cfen_forward_u8 (otherwise fp32 NCHW as in cfen_forward)
+ *   CFEN_ONLY_FAKE_A  only xd ("fake_A", the dehazed image) is produced; xr / xs may be NULL.  The reflectance /
+ *                     shading level-1 blocks, last up-convolutions and tails feed nothing else (v3.py:607-697,
+ *                     709-853) and are skipped - what test.py:47-55 keeps when it drops every visual but fake_A. */
+#define CFEN_IO_U8 1
+#define CFEN_ONLY_FAKE_A 2
+int32_t cfen_forward_ex(cfen_plan* plan, int32_t batch, const void* in, void* xr, void* xs, void* xd,
+                        int32_t io_flags, void* stream);
 
 /* Debug/testing: device pointer + element count of a named internal NHWC stage buffer of the
  * last pass ("xf", "e1", "e2", "e3", "u3r", ...); elements are fp16 when option "maps16" is 2, else fp32. */
@@ -185,7 +196,9 @@ int32_t cfen_tokenize_global(const float* map_nhwc, float* tokens, void* tokens_
  * bit1 tanh, bit2 add `extra` after activation (residual), bit3 output NCHW, bit4 input NCHW,
  * bit5 `extra` is a second input summed (SUM2) / concatenated (skip) before the conv;
  * bit8 `in` is an fp16 NHWC map (single-input NHWC kinds), bit9 `out` is an fp16 NHWC map, bit10 the residual
- * `extra` is an fp16 NHWC map (the storage format of the full-resolution 12-channel maps inside cfen_forward). */
+ * `extra` is an fp16 NHWC map (the storage format of the full-resolution 12-channel maps inside cfen_forward);
+ * bit11 ("head5x5"): `in` is a uint8 HWC image, normalised on load; bit12 (tails, with bit3): `out` is a uint8 HWC
+ * x3 image, tanh -> (y+1)/2*255 -> uint8 in the epilogue. */
 int32_t cfen_conv2d_nhwc(const char* kind, const float* in, const float* extra, const float* weight,
                          const float* bias, const float* an_weight, const float* an_bias,
                          float* out, int32_t B, int32_t H, int32_t W, int32_t flags, void* stream);

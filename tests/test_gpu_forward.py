@@ -239,23 +239,75 @@ def test_reload_state_dict_repacks():
     assert not torch.equal(a, b)
 
 
-def test_uint8_boundary_matches_float_path():
-    """cfen_forward_u8 == float path + tensor2im (util/util.py:12-24)."""
+def _tensor2im_u8(y):
+    """util/util.py:12-24 on a batch: [-1,1] NCHW fp32 -> uint8 HWC, one-channel maps tiled x3, truncation."""
+    y3 = y.expand(-1, 3, -1, -1) if y.shape[1] == 1 else y
+    return ((y3.permute(0, 2, 3, 1).float() + 1) / 2.0 * 255.0).clamp(0, 255).to(torch.uint8)
+
+
+def test_uint8_boundary_vs_oracle_and_float_path():
+    """Fused uint8 boundary: ToTensor + Normalize in the head loader, tensor2im in the tail epilogues.
+    Checked against the ORACLE on the normalised image + the tensor2im formula (gate 1e-2 of [0,1] = 2.55 grey levels),
+    and against the product's own fp32 path + tensor2im (same arithmetic up to the truncation boundary: <= 1 level)."""
     gnet, sd0, sd1, x0 = _gpu_net(2, 128)
     g = torch.Generator().manual_seed(5)
-    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8)
-    x = ((img.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    img = torch.randint(0, 256, (3, 128, 128, 3), generator=g, dtype=torch.uint8)
+    x = ((img.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5          # data/base_dataset.py:44-46
+    ref = orc.forward(sd1, x)
     with torch.no_grad():
-        fr, fs, fd = gnet(x.cuda())
-    plan = gnet._plans[(torch.cuda.current_device(), 128, 128)]
-    outs = [torch.empty(2, 128, 128, 3, dtype=torch.uint8, device="cuda") for _ in range(3)]
-    plan.forward_u8(2, img.cuda().data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
-                    torch.cuda.current_stream().cuda_stream)
+        flt = gnet(x.cuda())
+        outs = gnet.forward_u8(img.cuda())
     torch.cuda.synchronize()
-    for o, f in zip(outs, (fr, fs, fd)):
-        f3 = f.expand(-1, 3, -1, -1) if f.shape[1] == 1 else f
-        ref = ((f3.permute(0, 2, 3, 1) + 1) / 2.0 * 255.0).to(torch.uint8)
-        assert (o.int() - ref.int()).abs().max().item() <= 1
+    assert len(outs) == 3
+    for o, f, r in zip(outs, flt, ref):
+        assert o.dtype == torch.uint8 and tuple(o.shape) == (3, 128, 128, 3)
+        d_ref = (o.cpu().int() - _tensor2im_u8(r).int()).abs()
+        assert d_ref.max().item() <= 3 and d_ref.float().mean().item() <= 0.6, (d_ref.max().item(), d_ref.float().mean().item())
+        assert (o.int() - _tensor2im_u8(f).int()).abs().max().item() <= 1
+    with pytest.raises(RuntimeError):
+        gnet.forward_u8(x.cuda())            # fp32 tensor: wrong entry point
+
+
+def test_fake_a_only_mode_skips_kernels_and_matches():
+    """outputs=("fake_A",) (test.py:47-55): the R / S level-1 blocks, last up-convolutions and tails feed nothing else
+    (v3.py:607-697, 709-853); xd is bit-identical to the full forward and fewer kernels are launched."""
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    g = torch.Generator().manual_seed(6)
+    img = torch.randint(0, 256, (2, 128, 128, 3), generator=g, dtype=torch.uint8).cuda()
+    plan = None
+    with torch.no_grad():
+        full = gnet.forward_u8(img)
+        plan = gnet._plans[(torch.cuda.current_device(), 128, 128)]
+        n_full = plan.launches_per_forward
+        only = gnet.forward_u8(img, outputs=("fake_A",))
+        n_only = plan.launches_per_forward
+    torch.cuda.synchronize()
+    assert len(only) == 1 and torch.equal(only[0], full[2])
+    assert n_only < n_full - 20, (n_only, n_full)
+    with pytest.raises(ValueError):
+        gnet.forward_u8(img, outputs=("fake_R",))
+
+
+def test_forward_host_uint8_and_fake_a_only(monkeypatch):
+    """forward_host on pinned uint8 HWC images (3 passes of 4, the last ragged) == forward_u8; fp32 with
+    outputs=("fake_A",) == xd of forward(); switching modes re-creates the staging buffers."""
+    monkeypatch.setenv("CFEN_CHUNK_IMAGES", "4")
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (10, 128, 128, 3), generator=g, dtype=torch.uint8)
+    x = orc.make_inputs(128, [1, 6])[1]
+    with torch.no_grad():
+        ref8 = [o.cpu() for o in gnet.forward_u8(img.cuda())]
+        out8 = gnet.forward_host(img.pin_memory())
+        torch.cuda.synchronize()
+        a8 = gnet.forward_host(img.pin_memory(), outputs=("fake_A",), defer_sync=True)
+        gnet.host_sync()
+        ref32 = gnet(x.cuda())[2].cpu()
+        a32 = gnet.forward_host(x.pin_memory(), outputs=("fake_A",))
+        torch.cuda.synchronize()
+    assert len(out8) == 3 and all(torch.equal(a, b) for a, b in zip(out8, ref8))
+    assert len(a8) == 1 and torch.equal(a8[0], ref8[2])
+    assert len(a32) == 1 and torch.equal(a32[0], ref32)
 
 
 def test_forward_host_pipeline_matches_forward(monkeypatch):

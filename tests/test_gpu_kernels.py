@@ -519,6 +519,34 @@ def test_conv_tail_reflect_tanh(kind, cout):
     assert (out.double() - ref).abs().max().item() <= TF32_TOL
 
 
+def test_conv_head5x5_uint8_loader():
+    """bit 11: the head convolution reads a uint8 HWC image and applies (u/255 - 0.5)/0.5 on load."""
+    B, H = 2, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.randint(0, 256, (B, H, H, 3), generator=g, device="cuda", dtype=torch.uint8)
+    w, b = dev(12, 3, 5, 5, seed=2, scale=0.2), dev(12, seed=3)
+    out = torch.empty(B, H, H, 12, device="cuda")
+    _conv("head5x5", img, None, w, b, None, None, out, B, H, H, 2048)
+    x = ((img.permute(0, 3, 1, 2).double() / 255.0) - 0.5) / 0.5
+    ref = F.conv2d(x, w.double(), b.double(), padding=2)
+    assert U.rel_err(U.to_nchw(out), ref) <= TF32_TOL
+
+
+@pytest.mark.parametrize("kind,cout", [("tail7x7_3", 3), ("tail7x7_1", 1)])
+def test_conv_tail_uint8_epilogue(kind, cout):
+    """bit 12: reflect 7x7 + tanh + tensor2im ((y+1)/2*255 truncated, one-channel maps tiled x3) -> uint8 HWC."""
+    B, H = 2, 64
+    x, w, b = dev(B, 12, H, H, seed=1), dev(cout, 12, 7, 7, seed=2, scale=0.05), dev(cout, seed=3)
+    out = torch.zeros(B, H, H, 3, device="cuda", dtype=torch.uint8)
+    _conv(kind, U.to_nhwc(x), None, w, b, None, None, out, B, H, H, TANH | ONCHW | 4096)
+    y = torch.tanh(F.conv2d(F.pad(x.double(), (3, 3, 3, 3), mode="reflect"), w.double(), b.double()))
+    y3 = y.expand(-1, 3, -1, -1) if cout == 1 else y
+    ref = ((y3.permute(0, 2, 3, 1) + 1) / 2.0 * 255.0).clamp(0, 255)
+    d = (out.double() - ref.floor()).abs()
+    # the fp16-operand contraction moves y by ~1e-3 -> (y+1)/2*255 by ~0.2: at most one grey level, rarely
+    assert d.max().item() <= 1 and d.mean().item() <= 0.2, (d.max().item(), d.mean().item())
+
+
 @pytest.mark.parametrize("C,H,win", [(24, 64, 8), (48, 32, 8), (96, 16, 8), (24, 256, 32)])
 def test_merge_local_global(C, H, win):
     L = _native.lib()

@@ -90,7 +90,7 @@ def test_library_exports_every_header_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _native.lib().cfen_abi_version() == 2
+    assert _native.lib().cfen_abi_version() == 3
 
 
 def test_missing_library_fails_loudly(monkeypatch):
