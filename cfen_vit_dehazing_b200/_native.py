@@ -19,6 +19,7 @@ _lib = None
 EXPORTED_SYMBOLS = (
     "cfen_abi_version", "cfen_last_error",
     "cfen_plan_create", "cfen_plan_destroy", "cfen_plan_set_weight", "cfen_plan_pack_weights",
+    "cfen_plan_packed_bytes", "cfen_plan_export_packed", "cfen_plan_import_packed",
     "cfen_plan_workspace_bytes", "cfen_plan_launches_per_forward", "cfen_plan_set_option", "cfen_plan_get_option",
     "cfen_plan_profile_json", "cfen_plan_profile_trace",
     "cfen_forward", "cfen_forward_calibrate", "cfen_forward_u8", "cfen_forward_ex",
@@ -56,6 +57,10 @@ def lib():
         L.cfen_plan_destroy.argtypes = [vp]
         L.cfen_plan_set_weight.argtypes = [vp, cp, vp, i64, i32]
         L.cfen_plan_pack_weights.argtypes = [vp, vp]
+        L.cfen_plan_packed_bytes.argtypes = [vp]
+        L.cfen_plan_packed_bytes.restype = i64
+        L.cfen_plan_export_packed.argtypes = [vp, vp, i64, vp]
+        L.cfen_plan_import_packed.argtypes = [vp, vp, i64, vp]
         L.cfen_plan_workspace_bytes.argtypes = [vp]
         L.cfen_plan_workspace_bytes.restype = i64
         L.cfen_plan_launches_per_forward.argtypes = [vp]
@@ -94,6 +99,15 @@ def lib():
             getattr(L, name)  # AttributeError here means the .so is stale: rebuild
         _lib = L
     return _lib
+
+
+def is_dead_key(name):
+    """state_dict entries the forward never reads: the TransformerDecoder stacks and query_embed of
+    every ViT (constructed at v3.py:1116-1123, their use commented out at :1158-1168) and sub_mean / add_mean
+    (v3.py:120-121).  208.6 M of the 479.9 M elements at hidden_dim_ratio=4; they round-trip through state_dict but
+    are never copied to the plan."""
+    return (".decoder." in name or name.endswith(".query_embed.weight") or name.startswith("sub_mean.")
+            or name.startswith("add_mean."))
 
 
 def check(status):
@@ -138,7 +152,7 @@ class Plan:
             if name.endswith(".initialized"):
                 need_cal = need_cal or int(t.item()) == 0
                 continue
-            if not t.is_floating_point():
+            if not t.is_floating_point() or is_dead_key(name):
                 continue
             if t.dtype != torch.float32:
                 # the pack kernels read fp32: after net.half() / .bfloat16() / .double() they would read past the
@@ -151,6 +165,18 @@ class Plan:
                                          t.element_size()))
         check(L.cfen_plan_pack_weights(self._h, ctypes.c_void_p(stream)))
         self.needs_calibration = need_cal
+
+    def export_packed(self, stream):
+        """The packed weight arena as a host uint8 tensor (opaque; tied to this library build and plan configuration)."""
+        n = lib().cfen_plan_packed_bytes(self._h)
+        blob = torch.empty(n, dtype=torch.uint8)
+        check(lib().cfen_plan_export_packed(self._h, ctypes.c_void_p(blob.data_ptr()), n, ctypes.c_void_p(stream)))
+        return blob
+
+    def import_packed(self, blob, stream):
+        blob = blob.contiguous()
+        check(lib().cfen_plan_import_packed(self._h, ctypes.c_void_p(blob.data_ptr()), blob.numel(), ctypes.c_void_p(stream)))
+        self.needs_calibration = False
 
     def forward(self, batch, x, xr, xs, xd, stream):
         check(lib().cfen_forward(self._h, batch, x, xr, xs, xd, ctypes.c_void_p(stream)))

@@ -318,7 +318,7 @@ struct cfen_plan {
   int Hl[4], Cl[4];  // level 1..3 map size / channels
   std::unordered_map<std::string, std::pair<const float*, int64_t>> reg;
   Arena wa, ws;  // packed weights, workspace
-  bool allocated = false, packed = false;
+  bool allocated = false, packed = false, from_blob = false;
   VitW lvit[12], gvit[12];
   std::map<std::string, ConvLayer> conv;
   float* cfsm_w[2] = {nullptr, nullptr};  // d03d (C=48), d02d (C=24): 8 weights concatenated
@@ -575,6 +575,37 @@ extern "C" int32_t cfen_plan_set_weight(cfen_plan* p, const char* key, const voi
     return fail(1, "cfen_plan_set_weight: '%s' has %d-byte elements; the pack kernels read fp32 (4 bytes) only", key, elem_bytes);
   p->reg[key] = std::make_pair(static_cast<const float*>(dev_ptr), numel);
   p->packed = false;
+  p->from_blob = false;
+  return 0;
+}
+
+// ---- packed-weight blob: the weight arena as one opaque byte string.  Its layout is a function of
+// the plan's configuration and of this library build only; the host side stores it next to a header and refuses a
+// blob whose header does not match.
+extern "C" int64_t cfen_plan_packed_bytes(const cfen_plan* p) { return p ? (int64_t)p->wa.cap : 0; }
+extern "C" int32_t cfen_plan_export_packed(cfen_plan* p, void* host_dst, int64_t bytes, void* stream) {
+  if (!p || !host_dst) return fail(1, "cfen_plan_export_packed: null argument");
+  if (!p->packed) return fail(8, "cfen_plan_export_packed: weights not packed");
+  if (bytes != (int64_t)p->wa.cap) return fail(1, "cfen_plan_export_packed: buffer is %lld bytes, the arena %zu", (long long)bytes, p->wa.cap);
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaMemcpyAsync(host_dst, p->wa.base, p->wa.cap, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+extern "C" int32_t cfen_plan_import_packed(cfen_plan* p, const void* host_src, int64_t bytes, void* stream) {
+  if (!p || !host_src) return fail(1, "cfen_plan_import_packed: null argument");
+  if (bytes != (int64_t)p->wa.cap) return fail(1, "cfen_plan_import_packed: blob is %lld bytes, the arena %zu", (long long)bytes, p->wa.cap);
+  DeviceGuard dg(p->cfg.device);
+  CU(dg.err);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaMemcpyAsync(p->wa.base, host_src, p->wa.cap, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  // no reference-layout tensors are registered: calibration (which writes them back) is not available on this plan
+  for (auto& kv : p->conv) { kv.second.bias_src = nullptr; kv.second.an_w = nullptr; kv.second.an_b = nullptr; }
+  p->packed = true;
+  p->from_blob = true;
   return 0;
 }
 
@@ -1300,6 +1331,7 @@ static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void*
   if (batch < 0 || !in || !xd || (!only_d && (!xr || !xs))) return fail(1, "cfen_forward: bad argument");
   if (io & ~(CFEN_IO_U8 | CFEN_ONLY_FAKE_A)) return fail(1, "cfen_forward_ex: unknown io flag bits 0x%x", io);
   if (calibrate && io) return fail(1, "cfen_forward_calibrate takes fp32 tensors and produces all three outputs");
+  if (calibrate && p->from_blob) return fail(8, "cfen_forward_calibrate: this plan was filled from a packed blob (no registered tensors to initialise)");
   if (u8 && !p->conv_path) return fail(3, "the fused uint8 boundary needs the conv16 generation (conv_path 1)");
   if (calibrate && batch > p->nbmax)
     return fail(9, "calibration batch %d exceeds plan max_batch %d (ActNorm statistics span the whole batch)",

@@ -383,6 +383,10 @@ class dec_ipt(nn.Module):
         """Call after mutating parameters in place; the next forward re-packs them."""
         _mark_dirty(self, None)
 
+    def _live_device(self):
+        """Device of the tensors the forward reads (dead tensors may have been left on the host, checkpoint.py)."""
+        return self.head[0][0].weight.device
+
     def _tensors_version(self):
         """In-place updates (optimizer.step(), p.data.mul_(), copy_()) bump the tensors' version counters:
         their sum detects stale packed weights without hooks."""
@@ -410,8 +414,8 @@ class dec_ipt(nn.Module):
             self._plans[key] = plan
         version = (self._weights_version, self._tensors_version())
         if plan.weights_version != version:
-            tensors = {k: v for k, v in self.state_dict(keep_vars=True).items()}
-            master = next(self.parameters()).device
+            tensors = {k: v for k, v in self.state_dict(keep_vars=True).items() if not _native.is_dead_key(k)}
+            master = self._live_device()
             stream = torch.cuda.current_stream(device)
             if master != device:
                 # a plan on another GPU of the box (forward_sharded): pack from a transient copy of the master
@@ -485,7 +489,7 @@ class dec_ipt(nn.Module):
         out_dev = ids[0] if output_device is None else torch.device("cuda", int(output_device)) \
             if not isinstance(output_device, torch.device) else output_device
         b = input.shape[0]
-        master = next(self.parameters()).device
+        master = self._live_device()
         if any(int(m.initialized) == 0 for m in self._actnorm_modules()):
             # data-dependent ActNorm initialisation spans the whole batch: one pass on the master device
             outs = self.forward(input.to(master))
@@ -565,7 +569,7 @@ class dec_ipt(nn.Module):
         elif input.dtype != torch.float32 or not input.is_contiguous():
             input = input.float().contiguous()
         flags, only_a = self._io_flags(u8, outputs)
-        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        dev = torch.device(device) if device is not None else self._live_device()
         if dev.type != "cuda":
             raise RuntimeError("cfen_vit_dehazing_b200 runs on sm_100a GPUs only: the module lives on %s "
                                "and there is no CPU fallback" % dev)

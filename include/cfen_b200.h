@@ -68,6 +68,14 @@ int32_t cfen_plan_set_weight(cfen_plan* plan, const char* key, const void* dev_p
  * after all set_weight calls and again whenever the registered tensors change. */
 int32_t cfen_plan_pack_weights(cfen_plan* plan, void* stream);
 
+/* Packed-weight blob: export the packed arena to host memory / fill a plan of the SAME configuration
+ * from such a blob instead of set_weight + pack_weights (no reference-layout tensor has to exist on the device).
+ * The blob is opaque and tied to this library build; the host stores a header next to it.  Both calls synchronise
+ * `stream`.  A plan filled from a blob cannot run cfen_forward_calibrate. */
+int64_t cfen_plan_packed_bytes(const cfen_plan* plan);
+int32_t cfen_plan_export_packed(cfen_plan* plan, void* host_dst, int64_t bytes, void* stream);
+int32_t cfen_plan_import_packed(cfen_plan* plan, const void* host_src, int64_t bytes, void* stream);
+
 int64_t cfen_plan_workspace_bytes(const cfen_plan* plan);
 int64_t cfen_plan_launches_per_forward(const cfen_plan* plan); /* kernels per max_batch pass */
 /* options: "timing" (0/1): bracket every kernel launch with CUDA events on the launching stream;
