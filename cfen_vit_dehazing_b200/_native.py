@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
 
 
 IO_U8, ONLY_FAKE_A = 1, 2     # cfen_forward_ex io_flags (include/cfen_b200.h)
+VARIANT_CFS = 1                # cfen_config.flags: iid_hlgvit_crs_gd4_cfs graph
 
 
 class cfen_config(ctypes.Structure):
@@ -120,7 +121,7 @@ def chunk_images(height, batch):
     """Images processed per internal pass: bounds the workspace (~90 MB/image at 512x512, 5.8 GB of the 180 GB at
     64 images).  Measured: 16 -> 32 images per pass +16 % throughput, 32 -> 64 another +3.5 % (the small-M
     GEMMs of the global branch and the level-3 kernels fill more of a wave)."""
-    per = 64 if height <= 512 else 16
+    per = 64 if height <= 512 else 16      # (cfs variant: callers pass the level-1 equivalent, 2 * input edge)
     env = os.environ.get("CFEN_CHUNK_IMAGES")
     if env:
         per = max(1, int(env))
@@ -131,12 +132,12 @@ class Plan:
     """Opaque per-(device, H, W) execution plan: packed weights + static workspace."""
 
     def __init__(self, device, height, width, n_feats, hidden_dim_ratio, num_heads, patch_dim,
-                 patch_size, load_size, max_batch):
+                 patch_size, load_size, max_batch, flags=0):
         L = lib()
         cfg = cfen_config(struct_size=ctypes.sizeof(cfen_config), device=device, max_batch=max_batch,
                           height=height, width=width, n_feats=n_feats,
                           hidden_dim_ratio=hidden_dim_ratio, num_heads=num_heads, patch_dim=patch_dim,
-                          patch_size=patch_size, load_size=load_size, flags=0)
+                          patch_size=patch_size, load_size=load_size, flags=flags)
         handle = ctypes.c_void_p()
         check(L.cfen_plan_create(ctypes.byref(cfg), ctypes.byref(handle)))
         self._h = handle

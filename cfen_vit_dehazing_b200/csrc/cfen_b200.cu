@@ -97,6 +97,140 @@ struct DeviceGuard {
   DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+static cudaError_t set_kernel_attributes();
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+// Every conv-family geometry, one row each:
+//   X(kind, ConvSpec, source Cin of the reference weight, C-ABI name, Cout, contraction length per output pixel,
+//     compulsory input values per tile-domain pixel, first generation available)
+#define CFEN_CONV_KINDS(X)                                                                       \
+  X(K_HEAD5, ConvHead5x5, 3, "head5x5", 12, 75, 3.0, 1)                                          \
+  X(K_C3, Conv3x3_12, 12, "conv3x3_12_12", 12, 108, 12.0, 1)                                     \
+  X(K_DS1, ConvDs12_24, 12, "ds_12_24", 24, 108, 48.0, 1)                                        \
+  X(K_DS2, ConvDs24_48, 24, "ds_24_48", 48, 216, 96.0, 1)                                        \
+  X(K_DS3, ConvDs48_96, 48, "ds_48_96", 96, 432, 192.0, 1)                                       \
+  X(K_UP3, ConvUp96_48, 96, "up_96_48", 48, 384, 96.0, 1)                                        \
+  X(K_UP2, ConvUp48_24, 48, "up_48_24", 24, 192, 48.0, 1)                                        \
+  X(K_UP1, ConvUp24_12, 24, "up_24_12", 12, 96, 48.0, 1)                                         \
+  X(K_LG1, ConvLg1, 48, "lg_48_24", 24, 48, 24 + 24 / 16.0, 1)                                   \
+  X(K_LG2, ConvLg2, 96, "lg_96_48", 48, 96, 48 + 48 / 16.0, 1)                                   \
+  X(K_LG3, ConvLg3, 192, "lg_192_96", 96, 192, 96 + 96 / 16.0, 1)                                \
+  X(K_SK3, ConvSk96_48, 96, "skip_96_48", 48, 96, 96.0, 1)                                       \
+  X(K_SK2, ConvSk48_24, 48, "skip_48_24", 24, 48, 48.0, 1)                                       \
+  X(K_T3, ConvTail7_3, 12, "tail7x7_3", 3, 588, 12.0, 1)                                         \
+  X(K_T1, ConvTail7_1, 12, "tail7x7_1", 1, 588, 12.0, 1)                                         \
+  X(K_HEAD5_24, ConvHead5x5_24, 3, "head5x5_24", 24, 75, 3.0, 0)                                 \
+  X(K_C3_24, Conv3x3_24, 24, "conv3x3_24_24", 24, 216, 24.0, 0)                                  \
+  X(K_C3S_24, Conv3x3_24S, 24, "conv3x3_24_24_sum2", 24, 216, 48.0, 0)                           \
+  X(K_T3_24, ConvTail7_3_24, 24, "tail7x7_24_3", 3, 1176, 24.0, 0)                               \
+  X(K_T1_24, ConvTail7_1_24, 24, "tail7x7_24_1", 1, 1176, 24.0, 0)
+
+enum ConvKind {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) K,
+  CFEN_CONV_KINDS(X)
+#undef X
+  K_COUNT
+};
+
+#define CONV_SWITCH_RET(kind, expr_with_S_etc, dflt)                          \
+  switch (kind) {                                                             \
+    CFEN_CONV_KINDS(expr_with_S_etc)                                          \
+  }                                                                           \
+  return dflt;
+
+// first generation (conv_igemm.cuh, TF32): the v3 geometries only
+template <class S, int G1> struct Gen1 {
+  static int wpack_floats() { return S::WPACK_FLOATS; }
+  static cudaError_t set_attr() { return conv_set_attr<S>(); }
+  static cudaError_t pack(const float* src, float* dst, int cs, cudaStream_t st) {
+    conv_pack_kernel<S><<<(S::WPACK_FLOATS + 255) / 256 < 148 * 16 ? (S::WPACK_FLOATS + 255) / 256 : 148 * 16, 256, 0, st>>>(src, dst, cs);
+    return cudaGetLastError();
+  }
+  static cudaError_t launch(const ConvArgs& a, cudaStream_t st) { return launch_conv<S>(a, st); }
+};
+template <class S> struct Gen1<S, 0> {
+  static int wpack_floats() { return 4; }
+  static cudaError_t set_attr() { return cudaSuccess; }
+  static cudaError_t pack(const float*, float*, int, cudaStream_t) { return cudaSuccess; }
+  static cudaError_t launch(const ConvArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+};
+
+static int conv_wpack_floats(int kind) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return Gen1<S, G1>::wpack_floats();
+  CONV_SWITCH_RET(kind, X, 0)
+#undef X
+}
+static int conv_cout(int kind) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return COUT;
+  CONV_SWITCH_RET(kind, X, 0)
+#undef X
+}
+// second generation (conv16.cuh): fp16 packed weights, ldmatrix-fed mma.sync m16n8k16
+static int conv16_wpack_halves(int kind) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return Conv16<S>::WPACK_HALVES;
+  CONV_SWITCH_RET(kind, X, 0)
+#undef X
+}
+static cudaError_t conv16_pack_dispatch(int kind, const float* src, __half* dst, cudaStream_t st) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) \
+  case K: conv16_pack_kernel<S><<<ew_blocks(Conv16<S>::WPACK_HALVES), 256, 0, st>>>(src, dst, CS); return cudaGetLastError();
+  CONV_SWITCH_RET(kind, X, cudaErrorInvalidValue)
+#undef X
+}
+static cudaError_t conv16_launch_dispatch(int kind, const ConvArgs& a, const __half* w, cudaStream_t st) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return launch_conv16<S>(a, w, st);
+  CONV_SWITCH_RET(kind, X, cudaErrorInvalidValue)
+#undef X
+}
+static cudaError_t conv_pack_dispatch(int kind, const float* src, float* dst, cudaStream_t st) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return Gen1<S, G1>::pack(src, dst, CS, st);
+  CONV_SWITCH_RET(kind, X, cudaErrorInvalidValue)
+#undef X
+}
+static cudaError_t conv_launch_dispatch(int kind, const ConvArgs& a, cudaStream_t st) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return Gen1<S, G1>::launch(a, st);
+  CONV_SWITCH_RET(kind, X, cudaErrorInvalidValue)
+#undef X
+}
+static int conv_wpack_k(int kind) {  // contraction length (taps * input channels) per output pixel
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return KLEN;
+  CONV_SWITCH_RET(kind, X, 0)
+#undef X
+}
+static double conv_cin_bytes(int kind) {  // input values read per tile-domain pixel (compulsory)
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return CINB;
+  CONV_SWITCH_RET(kind, X, 0.0)
+#undef X
+}
+static bool conv_is_up(int kind) { return kind == K_UP3 || kind == K_UP2 || kind == K_UP1; }
+static int conv_parts(int kind, int H, int W) {  // H, W = tile domain (first generation: 8 x 16 tiles)
+  const int tiles = (H / 8) * (W / 16);
+  return conv_is_up(kind) ? tiles * 4 : tiles;
+}
+static int conv16_parts(int kind, int H, int W) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return conv16_stat_parts<S>(H, W);
+  CONV_SWITCH_RET(kind, X, 0)
+#undef X
+}
+static const char* conv_kind_name(int kind) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return #S;
+  CONV_SWITCH_RET(kind, X, "?")
+#undef X
+}
+static int conv_kind_from_name(const char* kind) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) if (strcmp(NAME, kind) == 0) return K;
+  CFEN_CONV_KINDS(X)
+#undef X
+  return -1;
+}
+static bool conv_has_gen1(int kind) {
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) case K: return G1 != 0;
+  CONV_SWITCH_RET(kind, X, false)
+#undef X
+}
+
 static cudaError_t set_kernel_attributes() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<128, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -107,16 +241,11 @@ static cudaError_t set_kernel_attributes() {
                                 AttnCfg<24>::SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 AttnCfg<96>::SMEM_BYTES)) != cudaSuccess) return e;
-#define SETC(S) if ((e = conv_set_attr<S>()) != cudaSuccess) return e;
-  SETC(ConvHead5x5) SETC(Conv3x3_12) SETC(ConvDs12_24) SETC(ConvDs24_48) SETC(ConvDs48_96)
-  SETC(ConvUp96_48) SETC(ConvUp48_24) SETC(ConvUp24_12) SETC(ConvLg1) SETC(ConvLg2) SETC(ConvLg3)
-  SETC(ConvSk96_48) SETC(ConvSk48_24) SETC(ConvTail7_3) SETC(ConvTail7_1)
-#undef SETC
-#define SETC(S) if ((e = conv16_set_attr<S>()) != cudaSuccess) return e;
-  SETC(ConvHead5x5) SETC(Conv3x3_12) SETC(ConvDs12_24) SETC(ConvDs24_48) SETC(ConvDs48_96)
-  SETC(ConvUp96_48) SETC(ConvUp48_24) SETC(ConvUp24_12) SETC(ConvLg1) SETC(ConvLg2) SETC(ConvLg3)
-  SETC(ConvSk96_48) SETC(ConvSk48_24) SETC(ConvTail7_3) SETC(ConvTail7_1)
-#undef SETC
+#define X(K, S, CS, NAME, COUT, KLEN, CINB, G1)                               \
+  if ((e = Gen1<S, G1>::set_attr()) != cudaSuccess) return e;                 \
+  if ((e = conv16_set_attr<S>()) != cudaSuccess) return e;
+  CFEN_CONV_KINDS(X)
+#undef X
   if ((e = gemm_tc_set_attr()) != cudaSuccess) return e;
   if ((e = mlp_tc_set_attr()) != cudaSuccess) return e;
   if ((e = gemm16_set_attr()) != cudaSuccess) return e;
@@ -129,140 +258,6 @@ static cudaError_t set_kernel_attributes() {
   return cudaSuccess;
 }
 
-// ------------------------------------------------------------------------------------------
-// plan
-// ------------------------------------------------------------------------------------------
-enum ConvKind { K_HEAD5, K_C3, K_DS1, K_DS2, K_DS3, K_UP3, K_UP2, K_UP1, K_LG1, K_LG2, K_LG3,
-                K_SK3, K_SK2, K_T3, K_T1, K_COUNT };
-
-static int conv_wpack_floats(int kind) {
-  switch (kind) {
-    case K_HEAD5: return ConvHead5x5::WPACK_FLOATS; case K_C3: return Conv3x3_12::WPACK_FLOATS;
-    case K_DS1: return ConvDs12_24::WPACK_FLOATS;   case K_DS2: return ConvDs24_48::WPACK_FLOATS;
-    case K_DS3: return ConvDs48_96::WPACK_FLOATS;   case K_UP3: return ConvUp96_48::WPACK_FLOATS;
-    case K_UP2: return ConvUp48_24::WPACK_FLOATS;   case K_UP1: return ConvUp24_12::WPACK_FLOATS;
-    case K_LG1: return ConvLg1::WPACK_FLOATS;       case K_LG2: return ConvLg2::WPACK_FLOATS;
-    case K_LG3: return ConvLg3::WPACK_FLOATS;       case K_SK3: return ConvSk96_48::WPACK_FLOATS;
-    case K_SK2: return ConvSk48_24::WPACK_FLOATS;   case K_T3: return ConvTail7_3::WPACK_FLOATS;
-    case K_T1: return ConvTail7_1::WPACK_FLOATS;
-  }
-  return 0;
-}
-static int conv_cout(int kind) {
-  switch (kind) {
-    case K_HEAD5: case K_C3: case K_UP1: return 12;
-    case K_DS1: case K_UP2: case K_LG1: case K_SK2: return 24;
-    case K_DS2: case K_UP3: case K_LG2: case K_SK3: return 48;
-    case K_DS3: case K_LG3: return 96;
-    case K_T3: return 3; case K_T1: return 1;
-  }
-  return 0;
-}
-
-// second generation (conv16.cuh): fp16 packed weights, ldmatrix-fed mma.sync m16n8k16
-static int conv16_wpack_halves(int kind) {
-  switch (kind) {
-    case K_HEAD5: return Conv16<ConvHead5x5>::WPACK_HALVES; case K_C3: return Conv16<Conv3x3_12>::WPACK_HALVES;
-    case K_DS1: return Conv16<ConvDs12_24>::WPACK_HALVES;   case K_DS2: return Conv16<ConvDs24_48>::WPACK_HALVES;
-    case K_DS3: return Conv16<ConvDs48_96>::WPACK_HALVES;   case K_UP3: return Conv16<ConvUp96_48>::WPACK_HALVES;
-    case K_UP2: return Conv16<ConvUp48_24>::WPACK_HALVES;   case K_UP1: return Conv16<ConvUp24_12>::WPACK_HALVES;
-    case K_LG1: return Conv16<ConvLg1>::WPACK_HALVES;       case K_LG2: return Conv16<ConvLg2>::WPACK_HALVES;
-    case K_LG3: return Conv16<ConvLg3>::WPACK_HALVES;       case K_SK3: return Conv16<ConvSk96_48>::WPACK_HALVES;
-    case K_SK2: return Conv16<ConvSk48_24>::WPACK_HALVES;   case K_T3: return Conv16<ConvTail7_3>::WPACK_HALVES;
-    case K_T1: return Conv16<ConvTail7_1>::WPACK_HALVES;
-  }
-  return 0;
-}
-static cudaError_t conv16_pack_dispatch(int kind, const float* src, __half* dst, cudaStream_t st) {
-#define PK(S, CS) conv16_pack_kernel<S><<<ew_blocks(Conv16<S>::WPACK_HALVES), 256, 0, st>>>(src, dst, CS); break;
-  switch (kind) {
-    case K_HEAD5: PK(ConvHead5x5, 3) case K_C3: PK(Conv3x3_12, 12) case K_DS1: PK(ConvDs12_24, 12)
-    case K_DS2: PK(ConvDs24_48, 24) case K_DS3: PK(ConvDs48_96, 48) case K_UP3: PK(ConvUp96_48, 96)
-    case K_UP2: PK(ConvUp48_24, 48) case K_UP1: PK(ConvUp24_12, 24) case K_LG1: PK(ConvLg1, 48)
-    case K_LG2: PK(ConvLg2, 96) case K_LG3: PK(ConvLg3, 192) case K_SK3: PK(ConvSk96_48, 96)
-    case K_SK2: PK(ConvSk48_24, 48) case K_T3: PK(ConvTail7_3, 12) case K_T1: PK(ConvTail7_1, 12)
-    default: return cudaErrorInvalidValue;
-  }
-#undef PK
-  return cudaGetLastError();
-}
-static cudaError_t conv16_launch_dispatch(int kind, const ConvArgs& a, const __half* w, cudaStream_t st) {
-  switch (kind) {
-    case K_HEAD5: return launch_conv16<ConvHead5x5>(a, w, st); case K_C3: return launch_conv16<Conv3x3_12>(a, w, st);
-    case K_DS1: return launch_conv16<ConvDs12_24>(a, w, st);   case K_DS2: return launch_conv16<ConvDs24_48>(a, w, st);
-    case K_DS3: return launch_conv16<ConvDs48_96>(a, w, st);   case K_UP3: return launch_conv16<ConvUp96_48>(a, w, st);
-    case K_UP2: return launch_conv16<ConvUp48_24>(a, w, st);   case K_UP1: return launch_conv16<ConvUp24_12>(a, w, st);
-    case K_LG1: return launch_conv16<ConvLg1>(a, w, st);       case K_LG2: return launch_conv16<ConvLg2>(a, w, st);
-    case K_LG3: return launch_conv16<ConvLg3>(a, w, st);       case K_SK3: return launch_conv16<ConvSk96_48>(a, w, st);
-    case K_SK2: return launch_conv16<ConvSk48_24>(a, w, st);   case K_T3: return launch_conv16<ConvTail7_3>(a, w, st);
-    case K_T1: return launch_conv16<ConvTail7_1>(a, w, st);
-  }
-  return cudaErrorInvalidValue;
-}
-
-static cudaError_t conv_pack_dispatch(int kind, const float* src, float* dst, cudaStream_t st) {
-#define PK(S, CS) conv_pack_kernel<S><<<ew_blocks(S::WPACK_FLOATS), 256, 0, st>>>(src, dst, CS); break;
-  switch (kind) {
-    case K_HEAD5: PK(ConvHead5x5, 3) case K_C3: PK(Conv3x3_12, 12) case K_DS1: PK(ConvDs12_24, 12)
-    case K_DS2: PK(ConvDs24_48, 24) case K_DS3: PK(ConvDs48_96, 48) case K_UP3: PK(ConvUp96_48, 96)
-    case K_UP2: PK(ConvUp48_24, 48) case K_UP1: PK(ConvUp24_12, 24) case K_LG1: PK(ConvLg1, 48)
-    case K_LG2: PK(ConvLg2, 96) case K_LG3: PK(ConvLg3, 192) case K_SK3: PK(ConvSk96_48, 96)
-    case K_SK2: PK(ConvSk48_24, 48) case K_T3: PK(ConvTail7_3, 12) case K_T1: PK(ConvTail7_1, 12)
-    default: return cudaErrorInvalidValue;
-  }
-#undef PK
-  return cudaGetLastError();
-}
-
-static cudaError_t conv_launch_dispatch(int kind, const ConvArgs& a, cudaStream_t st) {
-  switch (kind) {
-    case K_HEAD5: return launch_conv<ConvHead5x5>(a, st); case K_C3: return launch_conv<Conv3x3_12>(a, st);
-    case K_DS1: return launch_conv<ConvDs12_24>(a, st);   case K_DS2: return launch_conv<ConvDs24_48>(a, st);
-    case K_DS3: return launch_conv<ConvDs48_96>(a, st);   case K_UP3: return launch_conv<ConvUp96_48>(a, st);
-    case K_UP2: return launch_conv<ConvUp48_24>(a, st);   case K_UP1: return launch_conv<ConvUp24_12>(a, st);
-    case K_LG1: return launch_conv<ConvLg1>(a, st);       case K_LG2: return launch_conv<ConvLg2>(a, st);
-    case K_LG3: return launch_conv<ConvLg3>(a, st);       case K_SK3: return launch_conv<ConvSk96_48>(a, st);
-    case K_SK2: return launch_conv<ConvSk48_24>(a, st);   case K_T3: return launch_conv<ConvTail7_3>(a, st);
-    case K_T1: return launch_conv<ConvTail7_1>(a, st);
-  }
-  return cudaErrorInvalidValue;
-}
-static int conv_wpack_k(int kind) {  // contraction length (taps * input channels) per output pixel
-  switch (kind) {
-    case K_HEAD5: return 75; case K_C3: return 108; case K_DS1: return 108; case K_DS2: return 216;
-    case K_DS3: return 432; case K_UP3: return 384; case K_UP2: return 192; case K_UP1: return 96;
-    case K_LG1: return 48; case K_LG2: return 96; case K_LG3: return 192; case K_SK3: return 96;
-    case K_SK2: return 48; case K_T3: case K_T1: return 588;
-  }
-  return 0;
-}
-static double conv_cin_bytes(int kind) {  // input floats read per tile-domain pixel (compulsory)
-  switch (kind) {
-    case K_HEAD5: return 3; case K_C3: return 12; case K_DS1: return 12 * 4; case K_DS2: return 24 * 4;
-    case K_DS3: return 48 * 4; case K_UP3: return 96; case K_UP2: return 48; case K_UP1: return 48;
-    case K_LG1: return 24 + 24 / 16.0; case K_LG2: return 48 + 48 / 16.0; case K_LG3: return 96 + 96 / 16.0;
-    case K_SK3: return 96; case K_SK2: return 48; case K_T3: case K_T1: return 12;
-  }
-  return 0;
-}
-static int conv_parts(int kind, int H, int W) {  // H, W = tile domain (first generation: 8 x 16 tiles)
-  const int tiles = (H / 8) * (W / 16);
-  return (kind == K_UP3 || kind == K_UP2 || kind == K_UP1) ? tiles * 4 : tiles;
-}
-static int conv16_parts(int kind, int H, int W) {
-  switch (kind) {
-    case K_HEAD5: return conv16_stat_parts<ConvHead5x5>(H, W); case K_C3: return conv16_stat_parts<Conv3x3_12>(H, W);
-    case K_DS1: return conv16_stat_parts<ConvDs12_24>(H, W);   case K_DS2: return conv16_stat_parts<ConvDs24_48>(H, W);
-    case K_DS3: return conv16_stat_parts<ConvDs48_96>(H, W);   case K_UP3: return conv16_stat_parts<ConvUp96_48>(H, W);
-    case K_UP2: return conv16_stat_parts<ConvUp48_24>(H, W);   case K_UP1: return conv16_stat_parts<ConvUp24_12>(H, W);
-    case K_LG1: return conv16_stat_parts<ConvLg1>(H, W);       case K_LG2: return conv16_stat_parts<ConvLg2>(H, W);
-    case K_LG3: return conv16_stat_parts<ConvLg3>(H, W);       case K_SK3: return conv16_stat_parts<ConvSk96_48>(H, W);
-    case K_SK2: return conv16_stat_parts<ConvSk48_24>(H, W);   case K_T3: return conv16_stat_parts<ConvTail7_3>(H, W);
-    case K_T1: return conv16_stat_parts<ConvTail7_1>(H, W);
-  }
-  return 0;
-}
-
 enum ProfClass { PC_GEMM, PC_MLP, PC_ATTN, PC_LN, PC_TOKENIZE, PC_CONV, PC_MERGE, PC_NORM, PC_CFSM, PC_MISC, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"linear_gemm", "fused_mlp", "attention", "layernorm", "tokenize", "conv",
                                            "merge_lg", "instnorm", "cfsm", "misc"};
@@ -271,6 +266,7 @@ struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; char tag[56]; c
 struct ConvLayer {
   int kind = 0;
   std::string wkey, bkey, ankey;  // ankey: ActNorm module prefix ("" = none)
+  bool calibrated = false;        // set by the first use inside a calibrating pass (tail_color is shared by R and D)
   float *wpack = nullptr, *scale = nullptr, *shift = nullptr;
   __half* wpack16 = nullptr;        // second-generation packing (conv16.cuh)
   const float* bias_src = nullptr;  // registered tensors (reference layout)
@@ -315,6 +311,8 @@ struct Lane {
 struct cfen_plan {
   cfen_config cfg;
   int H, W, nbmax, hr, win;
+  int variant = 0;     // 0: iid_hlgvit_crs_gd4_cfs_v3; 1: iid_hlgvit_crs_gd4_cfs (no half-resolution stem)
+  int H1 = 0, Cf = 12; // level-1 map edge; channels of the input-resolution maps (head / tails)
   int Hl[4], Cl[4];  // level 1..3 map size / channels
   std::unordered_map<std::string, std::pair<const float*, int64_t>> reg;
   Arena wa, ws;  // packed weights, workspace
@@ -412,10 +410,10 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
   if (workspace) {
     Arena& a = p->ws;
     a.off = 0;
-    const size_t HH = (size_t)H * H;
-    // token workspaces per lane (local: M*E is largest on level 1, 6*H*H floats per image; global: Lg*E)
-    const size_t lt = 6 * HH * nb;
-    const size_t gt = (size_t)(H / 32) * (H / 32) * 384 * nb;
+    const size_t HH = (size_t)H * H, H1 = (size_t)p->H1;
+    // token workspaces per lane (local: M*E is largest on level 1, 24*H1*H1 floats per image; global: Lg*E)
+    const size_t lt = 24 * H1 * H1 * nb;
+    const size_t gt = (H1 / 16) * (H1 / 16) * 384 * nb;
     for (int li = 0; li < 3; ++li) {
       Lane& L = p->lane[li];
       L.lws.t0 = a.take(lt); L.lws.t1 = a.take(lt); L.lws.h = a.take(lt); L.lws.o = a.take(lt);
@@ -427,18 +425,18 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
       L.gws.qkv = a.take(3 * gt); L.gws.f = a.take(gt * hr);
       L.gws.x16 = a.take16(gt); L.gws.h16 = a.take16(gt); L.gws.o16 = a.take16(gt);
       L.gws.qkv16 = a.take16(3 * gt); L.gws.f16 = a.take16(gt * hr);
-      const size_t parts_max = (size_t)(H / 8) * (H / 16) * 2 * 12;  // tail conv / up_24_12 (4 phases on H/2)
+      const size_t parts_max = (size_t)(H / 8) * (H / 16) * 2 * 24;  // tail conv / up_24_12 (4 phases on H/2)
       L.partials = a.take(parts_max * nb * 2);
       L.mean_rstd = a.take((size_t)nb * 2 * 96);
       L.gates = a.take((size_t)nb * 2 * 48);
       L.cfsm_part = a.take((size_t)nb * 64 * 2 * 48);
-      L.f0 = a.take(HH * 12 * nb);
-      L.f1 = a.take(HH * 12 * nb);
+      L.f0 = a.take(HH * p->Cf * nb);
+      L.f1 = a.take(HH * p->Cf * nb);
     }
     auto add = [&](const char* name, size_t per_image) {
       p->stage[name] = std::make_pair(a.take(per_image * nb), (int64_t)per_image);
     };
-    const size_t F = HH * 12, M1 = (size_t)p->Hl[1] * p->Hl[1] * 24, M2 = (size_t)p->Hl[2] * p->Hl[2] * 48,
+    const size_t F = HH * p->Cf, M1 = (size_t)p->Hl[1] * p->Hl[1] * 24, M2 = (size_t)p->Hl[2] * p->Hl[2] * 48,
                  M3 = (size_t)p->Hl[3] * p->Hl[3] * 96;
     add("f2", F);
     add("xf", M1); add("e1", M1); add("e1d", M2); add("e2", M2); add("e2d", M3); add("e3", M3);
@@ -460,10 +458,11 @@ static void plan_declare_convs(cfen_plan* p) {
     c.ankey = an;
     p->conv[name] = c;
   };
-  add("head.0.0", K_HEAD5, "head.0.0", true, "");
-  add("head.0.1.body.0", K_C3, "head.0.1.body.0", true, "");
-  add("head.0.1.body.2", K_C3, "head.0.1.body.2", true, "");
-  add("ds_conv_e01", K_DS1, "ds_conv_e01.0", true, "");
+  const bool cfs = p->variant == 1;
+  add("head.0.0", cfs ? K_HEAD5_24 : K_HEAD5, "head.0.0", true, "");
+  add("head.0.1.body.0", cfs ? K_C3_24 : K_C3, "head.0.1.body.0", true, "");
+  add("head.0.1.body.2", cfs ? K_C3_24 : K_C3, "head.0.1.body.2", true, "");
+  if (!cfs) add("ds_conv_e01", K_DS1, "ds_conv_e01.0", true, "");
   add("ds_conv_e02", K_DS2, "ds_conv_e02.0", true, "");
   add("ds_conv_e03", K_DS3, "ds_conv_e03.0", true, "");
   for (int i = 0; i < 12; ++i) {
@@ -475,12 +474,19 @@ static void plan_declare_convs(cfen_plan* p) {
     std::string b(br);
     add("us_conv_d03" + b, K_UP3, "us_conv_d03" + b + ".0", true, "");
     add("us_conv_d02" + b, K_UP2, "us_conv_d02" + b + ".0", true, "us_conv_d02" + b + ".1");
-    add("us_conv_d01" + b, K_UP1, "us_conv_d01" + b + ".0", true, "us_conv_d01" + b + ".1");
+    if (!cfs) add("us_conv_d01" + b, K_UP1, "us_conv_d01" + b + ".0", true, "us_conv_d01" + b + ".1");
   }
   for (const char* br : {"r", "s"}) {
     std::string b(br);
     add("sk_conv_d03" + b, K_SK3, "sk_conv_d03" + b + ".0", true, "sk_conv_d03" + b + ".1");
     add("sk_conv_d02" + b, K_SK2, "sk_conv_d02" + b + ".0", true, "sk_conv_d02" + b + ".1");
+  }
+  if (cfs) {   // tail_color serves R and D (cfs.py:334-345, 669, 977), tail_gray S (:346-358, 823)
+    add("tail_color.c1", K_C3S_24, "tail_color.0.1", true, "tail_color.0.2");
+    add("tail_color.c2", K_T3_24, "tail_color.0.5", true, "");
+    add("tail_gray.c1", K_C3S_24, "tail_gray.0.1", true, "");
+    add("tail_gray.c2", K_T1_24, "tail_gray.0.4", true, "");
+    return;
   }
   add("tail_R.c1", K_C3, "tail_R.0.1", true, "tail_R.0.2");
   add("tail_R.c2", K_T3, "tail_R.0.5", true, "");
@@ -500,10 +506,16 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (cfg->hidden_dim_ratio != 2 && cfg->hidden_dim_ratio != 4)
     return fail(3, "unsupported hidden_dim_ratio=%d (2 or 4)", cfg->hidden_dim_ratio);
   if (cfg->num_heads != 4 || cfg->patch_dim != 2) return fail(3, "num_heads/patch_dim must be 4/2");
-  if (cfg->height != cfg->width || cfg->height % 128 != 0 || cfg->height < 128)
-    return fail(3, "input must be square with edge a multiple of 128 (got %dx%d)", cfg->height, cfg->width);
-  if (cfg->load_size * 2 != cfg->height || cfg->patch_size * 16 != cfg->height)
+  if (cfg->flags & ~CFEN_VARIANT_CFS) return fail(3, "unknown cfen_config.flags bits 0x%x", cfg->flags);
+  const bool cfs = (cfg->flags & CFEN_VARIANT_CFS) != 0;
+  const int edge = cfs ? 64 : 128;   // level-1 map edge must be a multiple of 64 (8 windows of >= 8 px; 16x pooling)
+  if (cfg->height != cfg->width || cfg->height % edge != 0 || cfg->height < edge)
+    return fail(3, "input must be square with edge a multiple of %d (got %dx%d)", edge, cfg->height, cfg->width);
+  if (!cfs && (cfg->load_size * 2 != cfg->height || cfg->patch_size * 16 != cfg->height))
     return fail(3, "loadSize must be H/2 and patch_size H/16 (got %d, %d for H=%d)", cfg->load_size,
+                cfg->patch_size, cfg->height);
+  if (cfs && (cfg->load_size != cfg->height || cfg->patch_size * 8 != cfg->height))
+    return fail(3, "iid_hlgvit_crs_gd4_cfs: loadSize must be H and patch_size H/8 (got %d, %d for H=%d)", cfg->load_size,
                 cfg->patch_size, cfg->height);
   if (cfg->max_batch < 1) return fail(1, "max_batch must be >= 1");
   DeviceGuard dg(cfg->device);
@@ -517,6 +529,9 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->cfg = *cfg;
   p->H = cfg->height; p->W = cfg->width; p->nbmax = cfg->max_batch; p->hr = cfg->hidden_dim_ratio;
   p->win = cfg->patch_size;
+  p->variant = cfs ? 1 : 0;
+  p->H1 = cfs ? p->H : p->H / 2;
+  p->Cf = cfs ? 24 : 12;
   if (const char* gp = getenv("CFEN_GEMM_PATH")) {
     const int v = atoi(gp);
     p->gemm_path = (v >= 0 && v <= 2) ? v : 2;
@@ -530,7 +545,11 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
   if (const char* cp = getenv("CFEN_CONV_PATH")) p->conv_path = atoi(cp) != 0;
-  for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H >> l; p->Cl[l] = 24 << (l - 1); }
+  for (int l = 1; l <= 3; ++l) { p->Hl[l] = p->H1 >> (l - 1); p->Cl[l] = 24 << (l - 1); }
+  if (p->variant && !p->conv_path) {
+    delete p;
+    return fail(3, "iid_hlgvit_crs_gd4_cfs needs the conv16 generation (conv_path 1)");
+  }
   plan_declare_convs(p);
   plan_layout(p, true, true);  // dry run: sizes
   const size_t wbytes = p->wa.off, sbytes = p->ws.off;
@@ -1094,13 +1113,6 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
   return 0;
 }
 
-static const char* conv_kind_name(int kind) {
-  static const char* names[K_COUNT] = {"ConvHead5x5", "Conv3x3_12", "ConvDs12_24", "ConvDs24_48", "ConvDs48_96",
-                                       "ConvUp96_48", "ConvUp48_24", "ConvUp24_12", "ConvLg1", "ConvLg2", "ConvLg3",
-                                       "ConvSk96_48", "ConvSk48_24", "ConvTail7_3", "ConvTail7_1"};
-  return (kind >= 0 && kind < K_COUNT) ? names[kind] : "?";
-}
-
 // One conv-family layer; handles ActNorm calibration (two-pass) when the plan is calibrating.
 static int run_conv(Run& r, const std::string& name, const float* in0, const float* in1, const float* res,
                     float* out, int H, int W, int flags, float* stats = nullptr) {
@@ -1114,7 +1126,10 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   const bool is_lg = c.kind == K_LG1 || c.kind == K_LG2 || c.kind == K_LG3;
   // every stage map is fp16 (maps16 level 2): the map operands of every conv-family layer; loaders / epilogues that
   // do not touch a map of that role ignore the bit (token-matrix inputs of the merges, NCHW network input / outputs)
-  if (all_maps16(p)) flags |= CF_IN16 | CF_OUT16 | ((flags & CF_RES) ? CF_RES16 : 0);
+  // (CF_KEEP_FMT: the caller has spelled out the storage format of every operand - layers that mix scratch and
+  //  stage maps)
+  if (flags & CF_KEEP_FMT) flags &= ~CF_KEEP_FMT;
+  else if (all_maps16(p)) flags |= CF_IN16 | CF_OUT16 | ((flags & CF_RES) ? CF_RES16 : 0);
   const bool is_up = c.kind == K_UP3 || c.kind == K_UP2 || c.kind == K_UP1;
   const int cout_ = conv_cout(c.kind);
   const double kelems = (double)conv_wpack_k(c.kind);           // contraction length per output pixel
@@ -1124,7 +1139,8 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   const double res_b = (flags & CF_RES) ? ((flags & CF_RES16) ? 2.0 : 4.0) : 0.0;
   const double cbytes = opix * cout_ * (out_b + res_b) + in_b * (double)r.nb * H * W * conv_cin_bytes(c.kind);
   const int pcls = is_lg ? PC_MERGE : PC_CONV;
-  if (p->calibrating && !c.ankey.empty()) {
+  if (p->calibrating && !c.ankey.empty() && !c.calibrated) {
+    c.calibrated = true;
     // pass 1: conv + bias only, per-CTA statistics (models/actnorm.py:25-37)
     const int cout = conv_cout(c.kind);
     const int parts = p->conv_path ? conv16_parts(c.kind, H, W) : conv_parts(c.kind, H, W);
@@ -1323,6 +1339,87 @@ static int forward_chunk(cfen_plan* p, int nb, const float* in, float* xr, float
   return 0;
 }
 
+// iid_hlgvit_crs_gd4_cfs (models/networks_iid_hlgvit_crs_gd4_cfs.py:366-985): the same encoder / decoder graph on a level-1
+// map at the INPUT resolution - head = conv5x5 3->24 + ResBlock(24) (:117-121), no ds_conv_e01 / us_conv_d01, and the
+// tails (conv3x3 24->24 [+ActNorm] + ReLU + reflect 7x7 + tanh; tail_color shared by R and D, :334-358) consume
+// block_out + xf directly (:669, 823, 977).
+static int forward_chunk_cfs(cfen_plan* p, int nb, const float* in, float* xr, float* xs, float* xd, cudaStream_t st,
+                             int io) {
+  const bool u8 = (io & CFEN_IO_U8) != 0, only_d = (io & CFEN_ONLY_FAKE_A) != 0;
+  const int H1 = p->Hl[1], H2 = p->Hl[2], H3 = p->Hl[3];
+  auto S = [&](const std::string& n) { return p->stage[n].first; };
+  const bool multi = p->streams && !p->timing && !p->calibrating;
+  p->lane[0].st = st;
+  p->lane[0].gst = multi ? p->side[0] : st;
+  p->lane[1].st = multi ? p->side[1] : st;
+  p->lane[1].gst = multi ? p->side[2] : st;
+  p->lane[2].st = multi ? p->side[3] : st;
+  p->lane[2].gst = multi ? p->side[4] : st;
+  p->sync_used = 0;
+  const bool m16 = p->maps16 >= 1;      // input-resolution scratch maps f0 / f1 follow the full-resolution rule
+  const int I16 = m16 ? CF_IN16 : 0, O16 = m16 ? CF_OUT16 : 0, R16 = m16 ? CF_RES16 : 0;
+  Run r0{p, st, nb, &p->lane[0]};
+  {
+    Run& r = r0;
+    float *f0 = r.ln->f0, *f1 = r.ln->f1;
+    RET(run_conv(r, "head.0.0", in, nullptr, nullptr, f0, H1, H1, O16 | (u8 ? CF_IN_U8 : 0)));
+    RET(run_conv(r, "head.0.1.body.0", f0, nullptr, nullptr, f1, H1, H1, CF_RELU | I16 | O16));
+    // xf is a stage map (fp16 when every stage map is): the ResBlock's residual f0 keeps the scratch format
+    RET(run_conv(r, "head.0.1.body.2", f1, nullptr, f0, S("xf"), H1, H1,
+                 CF_RES | I16 | R16 | (all_maps16(p) ? CF_OUT16 : 0) | CF_KEEP_FMT));
+    RET(run_block(r, 0, S("xf"), S("e1")));
+    RET(run_conv_in_relu(r, "ds_conv_e02", S("e1"), S("e1d"), H2, H2, H2, H2, 48));
+    RET(run_block(r, 1, S("e1d"), S("e2")));
+    RET(run_conv_in_relu(r, "ds_conv_e03", S("e2"), S("e2d"), H3, H3, H3, H3, 96));
+    RET(run_block(r, 2, S("e2d"), S("e3")));
+  }
+  const char* brs[3] = {"r", "s", "d"};
+  float* outs[3] = {xr, xs, xd};
+  const char* tails[3] = {"tail_color", "tail_gray", "tail_color"};
+  Run rr[3] = {r0, Run{p, p->lane[1].st, nb, &p->lane[1]}, Run{p, p->lane[2].st, nb, &p->lane[2]}};
+  for (int bi = 1; bi < 3; ++bi) RET(stream_edge(p, st, rr[bi].st));
+  cudaEvent_t up_done[2] = {nullptr, nullptr};
+  for (int bi = 0; bi < 3; ++bi) {
+    Run& r = rr[bi];
+    const std::string b(brs[bi]);
+    RET(run_block(r, 3 + bi * 3, S("e3"), S("d3" + b)));
+    RET(run_conv_in_relu(r, "us_conv_d03" + b, S("d3" + b), S("u3" + b), H3, H3, H2, H2, 48));
+    if (bi < 2 && multi) RET(stream_mark(p, r.st, &up_done[bi]));
+  }
+  for (int bi = 0; bi < 3; ++bi) {
+    Run& r = rr[bi];
+    const std::string b(brs[bi]);
+    if (bi < 2) {
+      RET(run_conv(r, "sk_conv_d03" + b, S("u3" + b), S("e2"), nullptr, S("d2in" + b), H2, H2, CF_RELU));
+    } else {
+      if (multi) { CU(cudaStreamWaitEvent(r.st, up_done[0], 0)); CU(cudaStreamWaitEvent(r.st, up_done[1], 0)); }
+      RET(run_cfsm(r, 0, S("u3d"), S("u3r"), S("u3s"), S("d2ind"), H2, H2));
+    }
+    RET(run_block(r, 3 + bi * 3 + 1, S("d2in" + b), S("d2" + b)));
+    RET(run_conv(r, "us_conv_d02" + b, S("d2" + b), nullptr, nullptr, S("u2" + b), H2, H2, CF_RELU));
+    if (bi < 2 && multi) RET(stream_mark(p, r.st, &up_done[bi]));
+  }
+  for (int bi = 0; bi < 3; ++bi) {
+    Run& r = rr[bi];
+    const std::string b(brs[bi]);
+    if (bi < 2 && only_d) continue;
+    if (bi < 2) {
+      RET(run_conv(r, "sk_conv_d02" + b, S("u2" + b), S("e1"), nullptr, S("d1in" + b), H1, H1, CF_RELU));
+    } else {
+      if (multi) { CU(cudaStreamWaitEvent(r.st, up_done[0], 0)); CU(cudaStreamWaitEvent(r.st, up_done[1], 0)); }
+      RET(run_cfsm(r, 1, S("u2d"), S("u2r"), S("u2s"), S("d1ind"), H1, H1));
+    }
+    RET(run_block(r, 3 + bi * 3 + 2, S("d1in" + b), S("d1" + b)));
+    float* f1 = r.ln->f1;
+    RET(run_conv(r, std::string(tails[bi]) + ".c1", S("d1" + b), S("xf"), nullptr, f1, H1, H1,
+                 CF_RELU | O16 | (all_maps16(p) ? CF_IN16 : 0) | CF_KEEP_FMT));
+    RET(run_conv(r, std::string(tails[bi]) + ".c2", f1, nullptr, nullptr, outs[bi], H1, H1,
+                 CF_TANH | CF_OUT_NCHW | I16 | (u8 ? CF_OUT_U8 : 0) | CF_KEEP_FMT));
+  }
+  for (int bi = 1; bi < 3; ++bi) RET(stream_edge(p, rr[bi].st, st));
+  return 0;
+}
+
 static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void* xs, void* xd, void* stream,
                         bool calibrate, int io) {
   if (!p) return fail(1, "cfen_forward: null plan");
@@ -1344,6 +1441,8 @@ static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void*
   const size_t in_b = u8 ? 3 * HW : 12 * HW, o3_b = u8 ? 3 * HW : 12 * HW, o1_b = u8 ? 3 * HW : 4 * HW;
   p->launches = 0;
   p->calibrating = calibrate;
+  if (calibrate)
+    for (auto& kv : p->conv) kv.second.calibrated = false;
 
   int rc = 0;
   for (int b0 = 0; b0 < batch && rc == 0; b0 += p->nbmax) {
@@ -1351,7 +1450,7 @@ static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void*
     auto at = [&](const void* base, size_t per) {
       return base ? reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(base)) + (size_t)b0 * per) : nullptr;
     };
-    rc = forward_chunk(p, nb, at(in, in_b), at(xr, o3_b), at(xs, o1_b), at(xd, o3_b), st, io);
+    rc = (p->variant ? forward_chunk_cfs : forward_chunk)(p, nb, at(in, in_b), at(xr, o3_b), at(xs, o1_b), at(xd, o3_b), st, io);
     if (b0 == 0) p->launches_last = p->launches;
   }
   p->calibrating = false;
@@ -1384,8 +1483,8 @@ extern "C" int32_t cfen_plan_stage_ptr(cfen_plan* p, const char* name, void** de
     *numel = it->second.second;
     return 0;
   }
-  if (n == "local_tokens") { *dev_ptr = p->lane[0].lws.t1; *numel = 6LL * p->H * p->H; return 0; }
-  if (n == "global_tokens") { *dev_ptr = p->lane[0].gws.t1; *numel = (int64_t)(p->H / 32) * (p->H / 32) * 384; return 0; }
+  if (n == "local_tokens") { *dev_ptr = p->lane[0].lws.t1; *numel = 24LL * p->H1 * p->H1; return 0; }
+  if (n == "global_tokens") { *dev_ptr = p->lane[0].gws.t1; *numel = (int64_t)(p->H1 / 16) * (p->H1 / 16) * 384; return 0; }
   return fail(5, "unknown stage '%s'", name);
 }
 
@@ -1612,17 +1711,6 @@ extern "C" int32_t cfen_tokenize_global(const float* map, float* tokens, void* t
       map, tokens, static_cast<__half*>(tokens16), B, H, W, C);
   CU(cudaGetLastError());
   return 0;
-}
-
-static int conv_kind_from_name(const char* kind) {
-  static const std::pair<const char*, int> tab[] = {
-      {"head5x5", K_HEAD5}, {"conv3x3_12_12", K_C3}, {"ds_12_24", K_DS1}, {"ds_24_48", K_DS2},
-      {"ds_48_96", K_DS3}, {"up_96_48", K_UP3}, {"up_48_24", K_UP2}, {"up_24_12", K_UP1},
-      {"skip_96_48", K_SK3}, {"skip_48_24", K_SK2}, {"tail7x7_3", K_T3}, {"tail7x7_1", K_T1},
-      {"lg_48_24", K_LG1}, {"lg_96_48", K_LG2}, {"lg_192_96", K_LG3}};
-  for (auto& e : tab)
-    if (strcmp(e.first, kind) == 0) return e.second;
-  return -1;
 }
 
 // Test-only convenience: packs the weights into temporaries (cudaMalloc + sync), runs, frees.

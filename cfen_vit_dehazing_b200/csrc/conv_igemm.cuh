@@ -28,7 +28,8 @@ enum ConvFlags {
   //             (data/base_dataset.py:44-46): (u / 255 - 0.5) / 0.5
   //   CF_OUT_U8 (with CF_OUT_NCHW staging): out is a uint8 HWC image [B,H,W,3] = tensor2im (util/util.py:12-24):
   //             (y + 1) / 2 * 255 truncated to uint8, one-channel maps tiled to three channels
-  CF_IN_U8 = 128, CF_OUT_U8 = 256
+  CF_IN_U8 = 128, CF_OUT_U8 = 256,
+  CF_KEEP_FMT = 1 << 20   // host-side only (run_conv): do not apply the plan-wide fp16-map format bits
 };
 
 struct ConvArgs {
@@ -407,5 +408,13 @@ using ConvSk96_48 = ConvSpec<96, 48, 1, 1, 0, false, false, LD_CAT2>;
 using ConvSk48_24 = ConvSpec<48, 24, 1, 1, 0, false, false, LD_CAT2>;
 using ConvTail7_3 = ConvSpec<12, 3, 7, 1, 3, true, false, LD_NHWC>;
 using ConvTail7_1 = ConvSpec<12, 1, 7, 1, 3, true, false, LD_NHWC>;
+// sibling generator iid_hlgvit_crs_gd4_cfs (models/networks_iid_hlgvit_crs_gd4_cfs.py): no half-resolution stem, the head
+// and the tails work on 24 channels at the input resolution (:117-121, 334-358); the tails consume block_out + xf
+// (:669, 823, 977).  conv16 generation only.
+using ConvHead5x5_24 = ConvSpec<4, 24, 5, 1, 2, false, false, LD_NCHW3>;
+using Conv3x3_24 = ConvSpec<24, 24, 3, 1, 1, false, false, LD_NHWC>;
+using Conv3x3_24S = ConvSpec<24, 24, 3, 1, 1, false, false, LD_SUM2>;
+using ConvTail7_3_24 = ConvSpec<24, 3, 7, 1, 3, true, false, LD_NHWC>;
+using ConvTail7_1_24 = ConvSpec<24, 1, 7, 1, 3, true, false, LD_NHWC>;
 
 }  // namespace cfen

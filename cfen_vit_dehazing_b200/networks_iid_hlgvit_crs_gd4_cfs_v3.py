@@ -246,23 +246,30 @@ def _level_of(stage):
 
 
 class dec_ipt(nn.Module):
+    # "v3": iid_hlgvit_crs_gd4_cfs_v3 (this file's reference); "cfs": the sibling iid_hlgvit_crs_gd4_cfs without the
+    # half-resolution stem (networks_iid_hlgvit_crs_gd4_cfs.py subclasses and flips this)
+    VARIANT = "v3"
+
     def __init__(self, opt, conv=common.default_conv):
         super().__init__()
         self._check_supported(opt)
+        cfs = self.VARIANT == "cfs"
         self.scale_idx = 0
         self.opt = opt
         nf = opt.n_feats
         p = opt.patch_dim
         act = nn.ReLU(True)
 
-        self.ave_pool2 = nn.Sequential(nn.AvgPool2d(2, stride=2))
-        self.upsam = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear"))
+        if not cfs:
+            self.ave_pool2 = nn.Sequential(nn.AvgPool2d(2, stride=2))
+            self.upsam = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear"))
         self.sub_mean = common.MeanShift(opt.rgb_range)
         self.add_mean = common.MeanShift(opt.rgb_range, sign=1)
 
+        nh = nf if cfs else int(nf / 2)      # channels of the input-resolution maps (cfs.py:117-121 / v3.py:123-127)
         self.head = nn.ModuleList([nn.Sequential(
-            conv(opt.n_colors, int(nf / 2), 5),
-            common.ResBlock(conv, int(nf / 2), 3, act=act))])
+            conv(opt.n_colors, nh, 5),
+            common.ResBlock(conv, nh, 3, act=act))])
 
         vit_kw = dict(num_layers=opt.num_layers, num_queries=opt.num_queries,
                       dropout_rate=opt.dropout_rate, mlp=opt.no_mlp, pos_every=opt.pos_every,
@@ -303,14 +310,14 @@ class dec_ipt(nn.Module):
                 nn.Conv2d(2 * ch, ch, kernel_size=1, stride=1, padding=0), ActNorm2d(ch), nn.ReLU(True)))
 
         # ---- strided down convs (v3.py:292-298); note the e02, e03, e01 registration order
-        for tag, cin, cout in (("e02", nf, 2 * nf), ("e03", 2 * nf, 4 * nf), ("e01", int(nf / 2), nf)):
+        for tag, cin, cout in (("e02", nf, 2 * nf), ("e03", 2 * nf, 4 * nf), ("e01", int(nf / 2), nf))[:2 if cfs else 3]:
             self.add_module("ds_conv_" + tag, nn.Sequential(
                 nn.Conv2d(int(cin), int(cout), kernel_size=3, stride=2, padding=1),
                 nn.InstanceNorm2d(int(cout)), nn.ReLU(True)))
 
         # ---- transposed up convs (v3.py:301-322)
         for branch in "rsd":
-            for lvl, cin, cout in ((3, 4 * nf, 2 * nf), (2, 2 * nf, nf), (1, nf, int(nf / 2))):
+            for lvl, cin, cout in ((3, 4 * nf, 2 * nf), (2, 2 * nf, nf), (1, nf, int(nf / 2)))[:2 if cfs else 3]:
                 norm = nn.InstanceNorm2d(int(cout)) if lvl == 3 else ActNorm2d(int(cout))
                 self.add_module("us_conv_d0%d%s" % (lvl, branch), nn.Sequential(
                     nn.ConvTranspose2d(int(cin), int(cout), kernel_size=4, stride=2, padding=1),
@@ -327,17 +334,21 @@ class dec_ipt(nn.Module):
 
         # ---- tails (v3.py:348-383)
         def tail(out_ch, with_actnorm):
-            mods = [common.Upsampler(conv, int(nf / 2), act=False),
-                    nn.Conv2d(int(nf / 2), int(nf / 2), kernel_size=3, stride=1, padding=1)]
+            mods = [common.Upsampler(conv, nh, act=False),
+                    nn.Conv2d(nh, nh, kernel_size=3, stride=1, padding=1)]
             if with_actnorm:
-                mods.append(ActNorm2d(int(nf / 2)))
+                mods.append(ActNorm2d(nh))
             mods += [nn.ReLU(True), nn.ReflectionPad2d(3),
-                     nn.Conv2d(int(nf / 2), out_ch, kernel_size=7, padding=0), nn.Tanh()]
+                     nn.Conv2d(nh, out_ch, kernel_size=7, padding=0), nn.Tanh()]
             return nn.ModuleList([nn.Sequential(*mods)])
 
-        self.tail_R = tail(opt.n_colors, True)
-        self.tail_D = tail(opt.n_colors, True)
-        self.tail_S = tail(1, False)
+        if cfs:      # one colour tail serves R and D (cfs.py:334-358, 669, 977)
+            self.tail_color = tail(opt.n_colors, True)
+            self.tail_gray = tail(1, False)
+        else:
+            self.tail_R = tail(opt.n_colors, True)
+            self.tail_D = tail(opt.n_colors, True)
+            self.tail_S = tail(1, False)
 
         self.crop2x2 = _NoParams()
         self.join2x2 = _NoParams()
@@ -394,11 +405,13 @@ class dec_ipt(nn.Module):
 
     def _plan_for(self, device, height, width, batch, exact_batch=False):
         opt = self.opt
-        if height != width or height != 2 * int(opt.loadSize):
+        cfs = self.VARIANT == "cfs"
+        baked = int(opt.loadSize) * (1 if cfs else 2)
+        if height != width or height != baked:
             raise RuntimeError(
-                "input %dx%d does not match the size baked into the network (%d = 2*loadSize); "
+                "input %dx%d does not match the size baked into the network (%d = %sloadSize); "
                 "the reference fails the same way (pos-embedding / fold shape mismatch)"
-                % (height, width, 2 * int(opt.loadSize)))
+                % (height, width, baked, "" if cfs else "2*"))
         key = (device.index, height, width)
         plan = self._plans.get(key)
         need = batch if exact_batch else _native.chunk_images(height, batch)
@@ -410,7 +423,7 @@ class dec_ipt(nn.Module):
                                 n_feats=opt.n_feats, hidden_dim_ratio=opt.hidden_dim_ratio,
                                 num_heads=opt.num_heads, patch_dim=opt.patch_dim,
                                 patch_size=int(opt.patch_size), load_size=int(opt.loadSize),
-                                max_batch=need)
+                                max_batch=need, flags=_native.VARIANT_CFS if cfs else 0)
             self._plans[key] = plan
         version = (self._weights_version, self._tensors_version())
         if plan.weights_version != version:

@@ -47,8 +47,16 @@ typedef struct cfen_config {
   int32_t patch_dim;         /* --patch_dim                                                 */
   int32_t patch_size;        /* --patch_size  (window edge in pixels of every level)       */
   int32_t load_size;         /* --loadSize                                                  */
-  int32_t flags;             /* reserved, 0                                                 */
+  int32_t flags;             /* CFEN_VARIANT_* bits                                         */
 } cfen_config;
+
+/* cfen_config.flags: 0 = iid_hlgvit_crs_gd4_cfs_v3 (the north-star generator).
+ * CFEN_VARIANT_CFS = the sibling generator iid_hlgvit_crs_gd4_cfs (models/networks_iid_hlgvit_crs_gd4_cfs.py, selected by
+ * models/model_iid_dehazing.py:84-86): same blocks, no half-resolution stem - head and tails run on 24 channels at the
+ * input resolution, the level-1 map is the input size.  Constraints: load_size = height, patch_size = height/8,
+ * height == width, height % 64 == 0.  State_dict keys: tail_color / tail_gray instead of tail_R / tail_D / tail_S, no
+ * ds_conv_e01 / us_conv_d01*. */
+#define CFEN_VARIANT_CFS 1
 
 int32_t     cfen_abi_version(void);
 const char* cfen_last_error(void);

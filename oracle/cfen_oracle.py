@@ -8,6 +8,7 @@ It restates, as one functional fp32 PyTorch-CPU program over a plain ``state_dic
 reference computes in ``models/networks_iid_hlgvit_crs_gd4_cfs_v3.py`` (``v3.py`` below):
 
 * orchestration of the 12 local/global blocks, skips, CFS gates, tails   v3.py:392-1020
+  (and of the sibling generator iid_hlgvit_crs_gd4_cfs: models/networks_iid_hlgvit_crs_gd4_cfs.py:366-985, ``forward_cfs``)
 * recursive Crop2x2/Join2x2 == one batched window partition/merge          v3.py:1025-1056
 * LViT / GViT token algebra (unfold, Linear+res, +pos, encoder, MLP, fold) v3.py:1136-1189, 1272-1325
 * pre-norm encoder layer with bias-free MultiheadAttention                 v3.py:1359-1390
@@ -26,7 +27,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-__all__ = ["forward", "prime", "default_opt", "make_inputs", "vit_block", "local_vit", "global_vit",
+__all__ = ["forward", "forward_cfs", "is_cfs", "cfs_opt", "prime", "default_opt", "make_inputs", "vit_block", "local_vit", "global_vit",
            "cfsm", "actnorm", "psnr01", "STAGES"]
 
 STAGES = ("encoder_01", "encoder_02", "encoder_03",
@@ -45,6 +46,12 @@ def default_opt(hidden_dim_ratio=4, size=512, **over):
               init_type="kaiming", gpu_ids=[])
     kw.update(over)
     return argparse.Namespace(**kw)
+
+
+def cfs_opt(hidden_dim_ratio=4, size=256, **over):
+    """Options of the sibling generator iid_hlgvit_crs_gd4_cfs for ``size`` x ``size`` inputs: no half-resolution stem,
+    so loadSize is the input edge and the windows are size/8 px."""
+    return default_opt(hidden_dim_ratio, size, loadSize=size, patch_size=size // 8, **over)
 
 
 def make_inputs(size, batches, seed=123):
@@ -183,10 +190,65 @@ def _tail(sd, name, x, with_actnorm):
     return torch.tanh(_conv(sd, name + (".0.5" if with_actnorm else ".0.4"), y))
 
 
+def is_cfs(sd):
+    """The sibling generator iid_hlgvit_crs_gd4_cfs is recognised by its shared colour tail."""
+    return "tail_color.0.1.weight" in sd
+
+
+def forward_cfs(sd, x, num_heads=4, taps=None):
+    """[xr, xs, xd] = dec_ipt.forward(x) of models/networks_iid_hlgvit_crs_gd4_cfs.py:366-985 (== ..._cfs_v2.py): the
+    v3 graph without the half-resolution stem - xf = head(x) has 24 channels at the input size (:368-369), the level-1
+    windows are size/8 px, there is no ds_conv_e01 / us_conv_d01, and the tails (tail_color for R and D, tail_gray for
+    S, :334-358) take block_out + xf (:669, 823, 977).  tail_color's ActNorm initialises on its FIRST use, the
+    reflectance branch."""
+    x = x.float()
+    size = x.shape[-1]
+    window = size // 8
+    hds = {1: num_heads, 2: 2 * num_heads, 3: 4 * num_heads}
+
+    def blk(stage, z):
+        lvl = int(stage[-1]) if stage[-1].isdigit() else int(stage[-2])
+        return _block(sd, stage, z, hds[lvl], window, taps)
+
+    with torch.no_grad():
+        y = _conv(sd, "head.0.0", x, padding=2)
+        xf = _conv(sd, "head.0.1.body.2", F.relu(_conv(sd, "head.0.1.body.0", y, padding=1)), padding=1) + y
+        e1 = blk("encoder_01", xf)
+        e1d = _down(sd, "ds_conv_e02", e1)
+        e2 = blk("encoder_02", e1d)
+        e2d = _down(sd, "ds_conv_e03", e2)
+        e3 = blk("encoder_03", e2d)
+        if taps is not None:
+            taps.update(xf=xf, e1=e1, e1d=e1d, e2=e2, e2d=e2d, e3=e3)
+        ups, outs = {}, {}
+        for br, tail_name, with_an in (("r", "tail_color", True), ("s", "tail_gray", False)):
+            d3 = blk("decoder_03" + br, e3)
+            u3 = _up(sd, "us_conv_d03" + br, d3, "in")
+            d2 = blk("decoder_02" + br, _skip(sd, "sk_conv_d03" + br, u3, e2))
+            u2 = _up(sd, "us_conv_d02" + br, d2, "an")
+            d1 = blk("decoder_01" + br, _skip(sd, "sk_conv_d02" + br, u2, e1))
+            outs[br] = _tail(sd, tail_name, d1 + xf, with_an)
+            ups[br] = (u3, u2)
+            if taps is not None:
+                taps.update({"u3" + br: u3, "u2" + br: u2})
+        d3 = blk("decoder_03d", e3)
+        u3 = _up(sd, "us_conv_d03d", d3, "in")
+        d2 = blk("decoder_02d", cfsm(sd, "cfsm2g_d03d.0", u3, ups["r"][0], ups["s"][0]))
+        u2 = _up(sd, "us_conv_d02d", d2, "an")
+        d1 = blk("decoder_01d", cfsm(sd, "cfsm2g_d02d.0", u2, ups["r"][1], ups["s"][1]))
+        outs["d"] = _tail(sd, "tail_color", d1 + xf, True)
+        if taps is not None:
+            taps.update(u3d=u3, u2d=u2)
+    return [outs["r"], outs["s"], outs["d"]]
+
+
 def forward(sd, x, num_heads=4, taps=None):
     """[xr, xs, xd] = dec_ipt.forward(x) (v3.py:392-1020).  ``sd`` is a (primed or un-primed)
     state_dict; un-primed ActNorm entries are initialised in place, like the reference's first
-    forward.  ``taps`` (optional dict) receives intermediate maps for per-stage parity tests."""
+    forward.  ``taps`` (optional dict) receives intermediate maps for per-stage parity tests.
+    A state_dict of the sibling generator iid_hlgvit_crs_gd4_cfs is dispatched to ``forward_cfs``."""
+    if is_cfs(sd):
+        return forward_cfs(sd, x, num_heads, taps)
     x = x.float()
     size = x.shape[-1]
     window = size // 16          # == opt.patch_size; the same window size on every level

@@ -32,6 +32,20 @@ def seeded_state(hr, size, seed=1):
     return net, sd0, sd1, x0, opt
 
 
+@functools.lru_cache(maxsize=2)
+def seeded_state_cfs(hr, size, seed=1):
+    """Same for the sibling generator iid_hlgvit_crs_gd4_cfs (input edge = loadSize = ``size``)."""
+    from cfen_vit_dehazing_b200 import common, networks_iid_hlgvit_crs_gd4_cfs as cfs
+    opt = orc.cfs_opt(hr, size)
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = cfs.define_G(opt, common.default_conv)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x0 = orc.make_inputs(size, [1])[0]
+    sd1 = orc.prime(sd0, x0)
+    return net, sd0, sd1, x0, opt
+
+
 def to_nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 

@@ -34,6 +34,11 @@ CONFIGS = {
     "v3_hr2_512_b1": (2, 512, 1, 8),
     "v3_hr4_1024_b1": (4, 1024, 1, 16),
 }
+# sibling generator iid_hlgvit_crs_gd4_cfs (models/networks_iid_hlgvit_crs_gd4_cfs.py): name -> (hr, size, batch, stride)
+CFS_CONFIGS = {
+    "cfs_hr2_128_b2": (2, 128, 2, 2),
+    "cfs_hr4_256_b1": (4, 256, 1, 4),
+}
 SEED = 1
 WEIGHT_KEYS = (
     "head.0.0.weight", "localvit_encoder_01.linear_encoding.weight",
@@ -42,29 +47,39 @@ WEIGHT_KEYS = (
     "lgcat_conv_d01d.0.weight", "us_conv_d02r.0.weight", "cfsm2g_d03d.0.fc_max_cf2.2.weight",
     "tail_S.0.4.weight",
 )
+CFS_WEIGHT_KEYS = ("head.0.0.weight", "head.0.1.body.2.weight", "localvit_encoder_01.linear_encoding.weight",
+                   "globalvit_decoder_03d.position_encoding.pe.weight", "us_conv_d02r.0.weight",
+                   "tail_color.0.1.weight", "tail_color.0.5.weight", "tail_gray.0.4.weight")
+CFS_ACTNORM_KEYS = ("lgcat_conv_e01.1.weight", "lgcat_conv_e01.1.bias", "sk_conv_d03s.1.bias", "tail_color.0.2.weight",
+                    "tail_color.0.2.bias")
 ACTNORM_KEYS = ("lgcat_conv_e01.1.weight", "lgcat_conv_e01.1.bias", "us_conv_d01d.1.weight",
                 "sk_conv_d03s.1.bias", "tail_D.0.2.weight", "tail_R.0.2.bias")
 
 
-def main():
+def main(only=None):
     from models import common as rcommon
     from models import networks_iid_hlgvit_crs_gd4_cfs_v3 as rv3
-    for name, (hr, size, batch, stride) in CONFIGS.items():
+    from models import networks_iid_hlgvit_crs_gd4_cfs as rcfs
+    jobs = [(n, c, rv3, orc.default_opt, WEIGHT_KEYS, ACTNORM_KEYS) for n, c in CONFIGS.items()] + \
+           [(n, c, rcfs, orc.cfs_opt, CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) for n, c in CFS_CONFIGS.items()]
+    for name, (hr, size, batch, stride), ref_mod, make_opt, WEIGHT_KEYS_, ACTNORM_KEYS_ in jobs:
+        if only and name not in only:
+            continue
         t0 = time.time()
-        opt = orc.default_opt(hr, size)
+        opt = make_opt(hr, size)
         torch.manual_seed(SEED)
-        net = rv3.define_G(opt, rcommon.default_conv)
+        net = ref_mod.define_G(opt, rcommon.default_conv)
         x0, x1 = orc.make_inputs(size, [1, batch])
         sd0 = net.state_dict()
         blob = {"seed": SEED, "hr": hr, "size": size, "batch": batch, "stride": stride}
-        for k in WEIGHT_KEYS:
+        for k in WEIGHT_KEYS_:
             blob["w_sum/" + k] = sd0[k].double().sum().item()
             blob["w_abs/" + k] = sd0[k].double().abs().sum().item()
         with torch.no_grad():
             net(x0)
             outs = net(x1)
         sd1 = net.state_dict()
-        for k in ACTNORM_KEYS:
+        for k in ACTNORM_KEYS_:
             blob["an/" + k] = sd1[k].numpy().copy()
         blob["x_sample"] = x1[:, :, ::stride, ::stride].numpy().copy()
         for tag, y in zip(("xr", "xs", "xd"), outs):
@@ -77,4 +92,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=sys.argv[1:] or None)

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 from oracle import cfen_oracle as orc  # noqa: E402
 from tests import _gpu as G  # noqa: E402
 from tests import _util as U  # noqa: E402
-from tests.golden.make_goldens import CONFIGS  # noqa: E402
+from tests.golden.make_goldens import CFS_CONFIGS, CONFIGS  # noqa: E402
 
 MAX_ABS_01 = 1e-2
 MIN_PSNR = 45.0
@@ -183,6 +183,67 @@ def test_forward_parity_option_paths(monkeypatch, env):
     for tag, a, b in zip(("xr", "xs", "xd"), out, ref):
         mx, ps = U.err01(a, b)
         assert mx <= MAX_ABS_01 and ps >= MIN_PSNR and bool(torch.isfinite(a).all()), (env, tag, mx, ps)
+
+
+# ---- sibling generator iid_hlgvit_crs_gd4_cfs: second plan graph over the same kernels
+def _gpu_net_cfs(hr, size, primed=True):
+    net, sd0, sd1, x0, opt = U.seeded_state_cfs(hr, size)
+    from cfen_vit_dehazing_b200 import common, networks_iid_hlgvit_crs_gd4_cfs as cfs
+    with contextlib.redirect_stdout(io.StringIO()):
+        gnet = cfs.dec_ipt(opt, common.default_conv)
+    gnet.load_state_dict(sd1 if primed else sd0, strict=True)
+    return gnet.cuda(), sd0, sd1, x0
+
+
+@pytest.mark.parametrize("name", ["cfs_hr2_128_b2", "cfs_hr4_256_b1"])
+def test_cfs_sibling_parity_vs_oracle_and_goldens(name):
+    hr, size, batch, stride = CFS_CONFIGS[name]
+    gnet, sd0, sd1, x0 = _gpu_net_cfs(hr, size)
+    x1 = orc.make_inputs(size, [1, batch])[1]
+    ref = orc.forward(sd1, x1)
+    with torch.no_grad():
+        out = gnet(x1.cuda())
+    torch.cuda.synchronize()
+    g = U.load_golden(name)
+    for tag, a, b in zip(("xr", "xs", "xd"), out, ref):
+        assert a.shape == b.shape
+        mx, ps = U.err01(a, b)
+        assert mx <= MAX_ABS_01 and ps >= MIN_PSNR and bool(torch.isfinite(a).all()), (tag, mx, ps)
+        d = np.abs(a[:, :, ::stride, ::stride].cpu().numpy() - g[tag]).max() / 2.0     # the real reference's outputs
+        assert d <= MAX_ABS_01, (tag, d)
+
+
+def test_cfs_sibling_batch16_fused_kernels_uint8_and_calibration():
+    """256x256 batch 16 (level-1 tokens 16 x 64 windows x 256: the fused token kernels and attention_tc are selected),
+    the uint8 boundary, and the first-forward ActNorm initialisation with the colour tail shared by R and D
+    (initialised by its first use, the reflectance branch: cfs.py:669)."""
+    gnet, sd0, sd1, x0 = _gpu_net_cfs(2, 256)
+    x = orc.make_inputs(256, [1, 16])[1]
+    with torch.no_grad():
+        out = gnet(x.cuda())
+    for i in (0, 15):
+        ref = orc.forward(sd1, x[i:i + 1])
+        for a, b in zip(out, ref):
+            mx, ps = U.err01(a[i:i + 1], b)
+            assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (i, mx, ps)
+    img = ((x[:2] + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    xn = ((img.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    with torch.no_grad():
+        u8 = gnet.forward_u8(img.cuda())
+        only = gnet.forward_u8(img.cuda(), outputs=("fake_A",))
+    ref = orc.forward(sd1, xn)
+    for o, r in zip(u8, ref):
+        assert (o.cpu().int() - _tensor2im_u8(r).int()).abs().max().item() <= 3
+    assert torch.equal(only[0], u8[2])
+    # un-primed: calibration on the GPU reproduces the oracle's priming
+    gnet2, sd0, sd1, x0 = _gpu_net_cfs(2, 256, primed=False)
+    with torch.no_grad():
+        gnet2(x0.cuda())
+    got = gnet2.state_dict()
+    worst = max((got[k].cpu() - v).abs().max().item() for k, v in sd1.items()
+                if (k.rsplit(".", 1)[0] + ".initialized") in sd1 and not k.endswith(".initialized"))
+    assert worst <= 2e-2, worst
+    assert all(int(got[k]) == 1 for k in sd1 if k.endswith(".initialized"))
 
 
 def test_batch_chunking_and_batch_invariance(monkeypatch):

@@ -11,15 +11,18 @@ import torch
 
 from oracle import cfen_oracle as orc
 from tests import _util as U
-from tests.golden.make_goldens import ACTNORM_KEYS, CONFIGS, WEIGHT_KEYS
+from tests.golden.make_goldens import (ACTNORM_KEYS, CFS_ACTNORM_KEYS, CFS_CONFIGS, CFS_WEIGHT_KEYS, CONFIGS,
+                                       WEIGHT_KEYS)
 
 TOL = 1e-4
 
 
 def _check(name):
-    hr, size, batch, stride = CONFIGS[name]
+    cfs = name in CFS_CONFIGS
+    hr, size, batch, stride = (CFS_CONFIGS if cfs else CONFIGS)[name]
     g = U.load_golden(name)
-    net, sd0, sd1, x0, opt = U.seeded_state(hr, size)
+    net, sd0, sd1, x0, opt = (U.seeded_state_cfs if cfs else U.seeded_state)(hr, size)
+    WEIGHT_KEYS, ACTNORM_KEYS = (CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) if cfs else (globals()["WEIGHT_KEYS"], globals()["ACTNORM_KEYS"])
     # 1) init-stream mirror: seeded weights equal the reference's
     for k in WEIGHT_KEYS:
         assert abs(sd0[k].double().sum().item() - float(g["w_sum/" + k])) <= 1e-6 * max(1.0, abs(float(g["w_abs/" + k]))), k
@@ -48,6 +51,15 @@ def test_oracle_matches_reference_512_hr4():
 
 def test_oracle_matches_reference_512_hr2():
     _check("v3_hr2_512_b1")
+
+
+def test_oracle_matches_reference_cfs_sibling_128_hr2():
+    """iid_hlgvit_crs_gd4_cfs (models/networks_iid_hlgvit_crs_gd4_cfs.py): 934-key module, RNG stream and forward_cfs."""
+    _check("cfs_hr2_128_b2")
+
+
+def test_oracle_matches_reference_cfs_sibling_256_hr4():
+    _check("cfs_hr4_256_b1")
 
 
 @pytest.mark.slow
