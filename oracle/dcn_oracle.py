@@ -15,8 +15,10 @@ APIs, SURVEY.md section 2.1 - and refuses CPU tensors, dcn/deform_conv.py:36-37)
 Pinning: the reference ships no tests or vectors for dcn.  The oracle is pinned (a) against
 ``torchvision.ops.deform_conv2d`` - an independent implementation of the same mmdetection
 algorithm with the same offset/mask channel convention - in tests/test_dcn_oracle.py, and (b) by
-the identity "zero offsets, unit mask == F.conv2d".  Parity with the reference binary itself is
-unpinned (it does not build here).
+the identity "zero offsets, unit mask == F.conv2d", and (c) against THE REFERENCE'S OWN KERNELS: the kernel file
+dcn/src/deform_conv_cuda_kernel.cu compiles unmodified with a three-name ATen shim (oracle/build_dcn_ref.py ->
+oracle/_ref/libdcn_ref.so); tests/test_gpu_dcn.py::test_*_vs_reference_kernels runs it on the GPU, applies the
+reference's weight x columns product, and checks both this oracle and the product against the result.
 """
 import torch
 
