@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "conv16.cuh"
 #include "conv_igemm.cuh"
+#include "conv_tc.cuh"
 #include "dcn.cuh"
 #include "attn16.cuh"
 #include "attn_tc.cuh"
@@ -231,6 +232,52 @@ static bool conv_has_gen1(int kind) {
 #undef X
 }
 
+// third generation (conv_tc.cuh): tcgen05 shifted-view implicit GEMM for the 3x3 12->12 layers and the two thin
+// up-convolutions, on fp16 maps whose rows are multiples of 128 pixels
+static bool conv_tc_kind(int kind) { return kind == K_C3 || kind == K_UP1 || kind == K_UP2; }
+static ConvTcProg conv_tc_prog(int kind) {
+  switch (kind) {
+    case K_C3: return conv_tc_prog_s1(12, 12, 3, CTC_S3, 2);
+    case K_UP1: return conv_tc_prog_t(24, 12, 4, 2);
+    case K_UP2: return conv_tc_prog_t(48, 24, 2);
+  }
+  return ConvTcProg{};
+}
+static cudaError_t conv_tc_pack_dispatch(int kind, const float* src, __half* dst, cudaStream_t st) {
+  const ConvTcProg pg = conv_tc_prog(kind);
+  const int n = conv_tc_wpack_halves(pg);
+  switch (kind) {
+    case K_C3: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 12, 12, 3, CTC_S3, 0, 1); break;
+    case K_UP1: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 24, 12, 4, 1, 1, 2); break;
+    case K_UP2: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 48, 24, 4, 1, 1, 1); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+static bool conv_tc_eligible(int kind, const ConvArgs& a) {
+  if (!conv_tc_kind(kind) || a.stats) return false;
+  const ConvTcProg pg = conv_tc_prog(kind);
+  if (a.W % 128 != 0 || a.H % (pg.groups * pg.rows_per_group) != 0) return false;
+  const int f = a.flags;
+  if (!(f & CF_IN16) || !(f & CF_OUT16) || (f & (CF_TANH | CF_OUT_NCHW | CF_IN_U8 | CF_OUT_U8))) return false;
+  if (f & CF_RES) return kind == K_C3 && (f & CF_RES16);
+  return true;
+}
+static cudaError_t conv_tc_launch_dispatch(int kind, const ConvArgs& a, const __half* wpack_tc, cudaStream_t st) {
+  ConvTcArgs t;
+  t.in0 = reinterpret_cast<const __half*>(a.in0); t.in1 = reinterpret_cast<const __half*>(a.in1);
+  t.res = (a.flags & CF_RES) ? reinterpret_cast<const __half*>(a.res) : nullptr;
+  t.wpack = wpack_tc; t.scale = a.scale; t.shift = a.shift; t.out = reinterpret_cast<__half*>(a.out);
+  t.B = a.B; t.H = a.H; t.W = a.W; t.relu = (a.flags & CF_RELU) != 0;
+  t.prog = conv_tc_prog(kind);
+  switch (kind) {
+    case K_C3: return launch_conv_tc<12, 12, false, false, CTC_S3, 2>(t, st);
+    case K_UP1: return launch_conv_tc<24, 12, true, true, 1, 4>(t, st);
+    case K_UP2: return launch_conv_tc<48, 24, true, false, 1, 2>(t, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
 static cudaError_t set_kernel_attributes() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(gemm_tf32_kernel<128, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -252,6 +299,7 @@ static cudaError_t set_kernel_attributes() {
   if ((e = mlp16_set_attr()) != cudaSuccess) return e;
   if ((e = attention16_set_attr()) != cudaSuccess) return e;
   if ((e = attention_tc_set_attr()) != cudaSuccess) return e;
+  if ((e = conv_tc_set_attr()) != cudaSuccess) return e;
   if ((e = tail16_set_attr()) != cudaSuccess) return e;
   if ((e = tail16r_set_attr()) != cudaSuccess) return e;
   if ((e = front16_set_attr()) != cudaSuccess) return e;
@@ -269,6 +317,7 @@ struct ConvLayer {
   bool calibrated = false;        // set by the first use inside a calibrating pass (tail_color is shared by R and D)
   float *wpack = nullptr, *scale = nullptr, *shift = nullptr;
   __half* wpack16 = nullptr;        // second-generation packing (conv16.cuh)
+  __half* wpack_tc = nullptr;       // third-generation packing (conv_tc.cuh), eligible kinds only
   const float* bias_src = nullptr;  // registered tensors (reference layout)
   float *an_w = nullptr, *an_b = nullptr;
 };
@@ -341,6 +390,7 @@ struct cfen_plan {
                              // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
   int maps16 = 2;      // 0: fp32 maps; 1: fp16 full-resolution maps only; 2: every stage map is fp16
   //     // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
+  int conv_tc = 1;     // conv_path 1: tcgen05 convolutions where eligible (conv_tc.cuh), else conv16
   int attn_tc = 1;     // gemm_path 2, 256-token windows with 24-wide heads: tcgen05 / TMEM attention (attn_tc.cuh)
   int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
                        // as one kernel reading the NHWC map (vit_front16.cuh); tokenize_local is not launched
@@ -400,6 +450,7 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
       ConvLayer& c = kv.second;
       c.wpack = a.take(conv_wpack_floats(c.kind));
       c.wpack16 = a.take16(conv16_wpack_halves(c.kind));
+      c.wpack_tc = conv_tc_kind(c.kind) ? a.take16(conv_tc_wpack_halves(conv_tc_prog(c.kind))) : nullptr;
       c.scale = a.take(96);
       c.shift = a.take(96);
     }
@@ -541,6 +592,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->tail_variant = default_tail_variant();
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
   if (const char* at = getenv("CFEN_ATTN_TC")) p->attn_tc = atoi(at) != 0;
+  if (const char* ct = getenv("CFEN_CONV_TC")) p->conv_tc = atoi(ct) != 0;
   if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm);
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
@@ -637,6 +689,7 @@ extern "C" int32_t cfen_plan_get_option(const cfen_plan* p, const char* name, in
   if (strcmp(name, "conv_path") == 0) { *value = p->conv_path; return 0; }
   if (strcmp(name, "fuse_front") == 0) { *value = p->fuse_front; return 0; }
   if (strcmp(name, "attn_tc") == 0) { *value = p->attn_tc; return 0; }
+  if (strcmp(name, "conv_tc") == 0) { *value = p->conv_tc; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { *value = p->fuse_tail; return 0; }
   if (strcmp(name, "split_k") == 0) { *value = p->split_k; return 0; }
   return fail(5, "unknown option '%s'", name);
@@ -659,6 +712,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
   if (strcmp(name, "attn_tc") == 0) { p->attn_tc = value != 0; return 0; }
+  if (strcmp(name, "conv_tc") == 0) { p->conv_tc = value != 0; return 0; }
   if (strcmp(name, "maps16") == 0) { p->maps16 = (int)value; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
@@ -776,6 +830,7 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
     if (it == p->reg.end()) return fail(6, "weight '%s' was not registered", c.wkey.c_str());
     CU(conv_pack_dispatch(c.kind, it->second.first, c.wpack, st));
     CU(conv16_pack_dispatch(c.kind, it->second.first, c.wpack16, st));
+    if (c.wpack_tc) CU(conv_tc_pack_dispatch(c.kind, it->second.first, c.wpack_tc, st));
     c.bias_src = nullptr; c.an_w = nullptr; c.an_b = nullptr;
     if (!c.bkey.empty()) RET(lookup(p, c.bkey, cout, &c.bias_src));
     if (!c.ankey.empty()) {
@@ -1159,6 +1214,11 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   }
   a.scale = c.scale; a.shift = c.shift; a.flags = flags; a.stats = stats;
   Launch l(r, pcls, cflops, cbytes, "%s %dx%d b%d", name.c_str(), H, W, r.nb);
+  if (p->conv_path && p->conv_tc && c.wpack_tc && conv_tc_eligible(c.kind, a)) {
+    l.sym("conv_tc_kernel<%s>", conv_kind_name(c.kind));
+    CU(conv_tc_launch_dispatch(c.kind, a, c.wpack_tc, r.st));
+    return 0;
+  }
   l.sym("%s<%s>", p->conv_path ? "conv16_kernel" : "conv_igemm_kernel", conv_kind_name(c.kind));
   CU(p->conv_path ? conv16_launch_dispatch(c.kind, a, c.wpack16, r.st) : conv_launch_dispatch(c.kind, a, r.st));
   return 0;
@@ -1734,6 +1794,18 @@ static int conv_oneoff(int kind, const float* in0, const float* in1, const float
     ConvArgs a;
     a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = tmp; a.scale = scale; a.shift = shift; a.out = out;
     a.stats = stats; a.B = B; a.H = H; a.W = W; a.flags = flags; a.win = win;
+    const char* cte = getenv("CFEN_CONV_TC");   // same selection as the plan (option "conv_tc")
+    if (gen2 && (!cte || atoi(cte) != 0) && conv_tc_eligible(kind, a)) {
+      __half* wtc = nullptr;
+      e = cudaMalloc(&wtc, (size_t)conv_tc_wpack_halves(conv_tc_prog(kind)) * 2);
+      if (e == cudaSuccess) e = conv_tc_pack_dispatch(kind, weight, wtc, st);
+      if (e == cudaSuccess) e = conv_tc_launch_dispatch(kind, a, wtc, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (wtc) cudaFree(wtc);
+      cudaFree(tmp);
+      if (e != cudaSuccess) return fail(2, "conv one-off (tcgen05) failed: %s", cudaGetErrorString(e));
+      return 0;
+    }
     e = gen2 ? conv16_launch_dispatch(kind, a, reinterpret_cast<const __half*>(tmp), st) : conv_launch_dispatch(kind, a, st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

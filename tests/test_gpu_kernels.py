@@ -449,6 +449,57 @@ def test_conv3x3_fp16_maps(fmt):
     assert U.rel_err(U.to_nchw(out.float()), ref) <= TF32_TOL
 
 
+# ---- third conv generation: tcgen05 shifted-view implicit GEMM (conv_tc.cuh), selected on fp16 maps whose rows are
+# multiples of 128 pixels.  Each case runs through cfen_conv2d_nhwc twice - CFEN_CONV_TC=1 and =0 (conv16) - against fp64.
+@pytest.mark.parametrize("B,H,W", [(1, 8, 128), (2, 24, 256), (3, 64, 128), (1, 136, 512)])
+@pytest.mark.parametrize("mode", ["plain", "relu", "relu_res", "actnorm_relu"])
+def test_conv_tc_3x3(B, H, W, mode, monkeypatch):
+    """3x3 12->12 (ResBlock / tail conv, common.py:41-62, v3.py:351): banded-weight groups of 4 output rows, zero
+    padding at all four image borders, several tiles per CTA (H=136, W=512: 68 tiles), residual, folded ActNorm."""
+    x, w, b = dev(B, 12, H, W, seed=1), dev(12, 12, 3, 3, seed=2, scale=0.1), dev(12, seed=3)
+    res = dev(B, 12, H, W, seed=4)
+    an_w, an_b = dev(12, seed=5, scale=0.3), dev(12, seed=6)
+    xin, rin = U.to_nhwc(x).half(), U.to_nhwc(res).half()
+    flags = IN16 | OUT16 | (RELU if mode != "plain" else 0) | ((RES | RES16) if mode == "relu_res" else 0)
+    y = F.conv2d(U.to_nchw(xin.float()).double(), w.double(), b.double(), padding=1)
+    if mode == "actnorm_relu":
+        y = (y + an_b.double().view(1, -1, 1, 1)) * torch.exp(an_w.double()).view(1, -1, 1, 1)
+    if mode != "plain":
+        y = torch.relu(y)
+    if mode == "relu_res":
+        y = y + U.to_nchw(rin.float()).double()
+    outs = {}
+    for tcv in ("1", "0"):
+        monkeypatch.setenv("CFEN_CONV_TC", tcv)
+        out = torch.full((B, H, W, 12), float("nan"), device="cuda", dtype=torch.float16)
+        _conv("conv3x3_12_12", xin, rin if mode == "relu_res" else None, w, b,
+              an_w if mode == "actnorm_relu" else None, an_b if mode == "actnorm_relu" else None, out, B, H, W, flags)
+        assert bool(torch.isfinite(out).all())
+        assert U.rel_err(U.to_nchw(out.float()), y) <= TF32_TOL, tcv
+        outs[tcv] = out
+    assert U.rel_err(outs["1"].float(), outs["0"].float().double()) <= 2e-3     # both round the output to fp16
+
+
+@pytest.mark.parametrize("kind,cin,cout,B,H,W", [("up_24_12", 24, 12, 2, 8, 128), ("up_24_12", 24, 12, 1, 40, 256),
+                                                  ("up_48_24", 48, 24, 2, 8, 128), ("up_48_24", 48, 24, 1, 40, 128)])
+def test_conv_tc_transposed(kind, cin, cout, B, H, W, monkeypatch):
+    """ConvTranspose2d(4, 2, 1) with the four sub-pixel phases as accumulator columns (v3.py:303-322); up_24_12 sums
+    its two input maps in the loader (block_out + xf, v3.py:696)."""
+    x, w, b = dev(B, cin, H, W, seed=1), dev(cin, cout, 4, 4, seed=2, scale=0.1), dev(cout, seed=3)
+    x2 = dev(B, cin, H, W, seed=7)
+    xi, x2i = U.to_nhwc(x).half(), U.to_nhwc(x2).half()
+    two = kind == "up_24_12"
+    src = U.to_nchw(xi.float()).double() + (U.to_nchw(x2i.float()).double() if two else 0)
+    # (conv_tc sums the two maps in the fp32 accumulator; conv16 rounds their sum to fp16 first: both within tolerance)
+    ref = torch.relu(F.conv_transpose2d(src, w.double(), b.double(), stride=2, padding=1))
+    for tcv in ("1", "0"):
+        monkeypatch.setenv("CFEN_CONV_TC", tcv)
+        out = torch.full((B, 2 * H, 2 * W, cout), float("nan"), device="cuda", dtype=torch.float16)
+        _conv(kind, xi, x2i if two else None, w, b, None, None, out, B, H, W, RELU | IN16 | OUT16 | (EXTRA_IN if two else 0))
+        assert bool(torch.isfinite(out).all())
+        assert U.rel_err(U.to_nchw(out.float()), ref) <= TF32_TOL, tcv
+
+
 def test_conv_fp16_map_chain_up_tail():
     """The full-resolution decoder tail as cfen_forward stores it: up_24_12 -> fp16 map -> 3x3 -> fp16 map -> reflect
     7x7 + tanh -> fp32 NCHW; ds_12_24 reading an fp16 map."""

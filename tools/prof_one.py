@@ -44,6 +44,31 @@ if which == "attn":      # prof_one.py attn E heads nseq [L]   (CFEN_ATTN_TC=0/1
         os.environ.get("CFEN_ATTN_TC", "1"), E, heads, nseq, Lq, us, 4.0 * nseq * Lq * Lq * E / us / 1e6,
         8.0 * nseq * Lq * E / us / 1e3))
     sys.exit(0)
+if which == "conv":      # prof_one.py conv KIND B H W   (CFEN_CONV_TC=0/1 selects the generation); fp16 maps, relu
+    import torch.nn.functional as F
+    kind, B, H, W = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    cin, cout, up = {"conv3x3_12_12": (12, 12, False), "up_24_12": (24, 12, True), "up_48_24": (48, 24, True)}[kind]
+    x = torch.randn(B, H, W, cin, device="cuda").half()
+    x2 = torch.randn(B, H, W, cin, device="cuda").half()
+    w = (torch.randn(cin, cout, 4, 4, device="cuda") if up else torch.randn(cout, cin, 3, 3, device="cuda")) * 0.1
+    b = torch.randn(cout, device="cuda")
+    out = torch.empty(B, (2 if up else 1) * H, (2 if up else 1) * W, cout, device="cuda", dtype=torch.float16)
+    flags = 1 | 256 | 512 | (32 if kind == "up_24_12" else 0)
+    # the one-off entry packs weights + synchronises: time a plan-free loop through it for relative numbers only
+    run = lambda: _native.check(L.cfen_conv2d_nhwc(kind.encode(), P(x), P(x2) if kind == "up_24_12" else None, P(w), P(b),
+                                                   None, None, P(out), B, H, W, flags, ST()))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    N = 10
+    import time
+    t0 = time.perf_counter()
+    for _ in range(N):
+        run()
+    torch.cuda.synchronize()
+    print("conv %s tc=%s B%d %dx%d: %.1f us/call incl. weight pack + sync (relative only)" % (
+        kind, os.environ.get("CFEN_CONV_TC", "1"), B, H, W, (time.perf_counter() - t0) * 1e6 / N))
+    sys.exit(0)
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 hid = int(sys.argv[3]) if len(sys.argv) > 3 else 4 * E
 M = int(sys.argv[4]) if len(sys.argv) > 4 else 148 * 256
