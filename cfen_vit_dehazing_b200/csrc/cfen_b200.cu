@@ -234,12 +234,14 @@ static bool conv_has_gen1(int kind) {
 
 // third generation (conv_tc.cuh): tcgen05 shifted-view implicit GEMM for the 3x3 12->12 layers and the two thin
 // up-convolutions, on fp16 maps whose rows are multiples of 128 pixels
-static bool conv_tc_kind(int kind) { return kind == K_C3 || kind == K_UP1 || kind == K_UP2; }
+static bool conv_tc_kind(int kind) { return kind == K_C3 || kind == K_UP1 || kind == K_UP2 || kind == K_T3 || kind == K_T1; }
 static ConvTcProg conv_tc_prog(int kind) {
   switch (kind) {
     case K_C3: return conv_tc_prog_s1(12, 12, 3, CTC_S3, 2);
     case K_UP1: return conv_tc_prog_t(24, 12, 4, 2);
     case K_UP2: return conv_tc_prog_t(48, 24, 2);
+    case K_T3: return conv_tc_prog_s1(12, 3, 7, CTC_S7, 2);
+    case K_T1: return conv_tc_prog_s1(12, 1, 7, CTC_S7, 2);
   }
   return ConvTcProg{};
 }
@@ -250,15 +252,22 @@ static cudaError_t conv_tc_pack_dispatch(int kind, const float* src, __half* dst
     case K_C3: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 12, 12, 3, CTC_S3, 0, 1); break;
     case K_UP1: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 24, 12, 4, 1, 1, 2); break;
     case K_UP2: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 48, 24, 4, 1, 1, 1); break;
+    case K_T3: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 12, 3, 7, CTC_S7, 0, 1); break;
+    case K_T1: conv_tc_pack_kernel<<<ew_blocks(n), 256, 0, st>>>(src, dst, pg, 12, 1, 7, CTC_S7, 0, 1); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
-static bool conv_tc_eligible(int kind, const ConvArgs& a) {
-  if (!conv_tc_kind(kind) || a.stats) return false;
+// level 1 (default): the layers where the tcgen05 kernel wins (3x3 12->12: 2.0x, up_24_12: 1.6x, up_48_24: 1.4x over
+// conv16); level 2 adds the 7x7 tails, correct but slower than conv16's row-pair kernel (597 vs 551 us) - kept for tests
+static bool conv_tc_eligible(int kind, const ConvArgs& a, int level = 1) {
+  if (!conv_tc_kind(kind) || a.stats || level < 1) return false;
+  if ((kind == K_T3 || kind == K_T1) && level < 2) return false;
   const ConvTcProg pg = conv_tc_prog(kind);
   if (a.W % 128 != 0 || a.H % (pg.groups * pg.rows_per_group) != 0) return false;
   const int f = a.flags;
+  if (kind == K_T3 || kind == K_T1)   // reflect 7x7 + tanh, fp16 map in, fp32 NCHW or uint8 HWC out
+    return (f & CF_IN16) && (f & CF_TANH) && (f & CF_OUT_NCHW) && !(f & (CF_RELU | CF_RES | CF_OUT16 | CF_IN_U8));
   if (!(f & CF_IN16) || !(f & CF_OUT16) || (f & (CF_TANH | CF_OUT_NCHW | CF_IN_U8 | CF_OUT_U8))) return false;
   if (f & CF_RES) return kind == K_C3 && (f & CF_RES16);
   return true;
@@ -267,13 +276,15 @@ static cudaError_t conv_tc_launch_dispatch(int kind, const ConvArgs& a, const __
   ConvTcArgs t;
   t.in0 = reinterpret_cast<const __half*>(a.in0); t.in1 = reinterpret_cast<const __half*>(a.in1);
   t.res = (a.flags & CF_RES) ? reinterpret_cast<const __half*>(a.res) : nullptr;
-  t.wpack = wpack_tc; t.scale = a.scale; t.shift = a.shift; t.out = reinterpret_cast<__half*>(a.out);
-  t.B = a.B; t.H = a.H; t.W = a.W; t.relu = (a.flags & CF_RELU) != 0;
+  t.wpack = wpack_tc; t.scale = a.scale; t.shift = a.shift; t.out = a.out;
+  t.B = a.B; t.H = a.H; t.W = a.W; t.relu = (a.flags & CF_RELU) != 0; t.out_u8 = (a.flags & CF_OUT_U8) != 0;
   t.prog = conv_tc_prog(kind);
   switch (kind) {
     case K_C3: return launch_conv_tc<12, 12, false, false, CTC_S3, 2>(t, st);
     case K_UP1: return launch_conv_tc<24, 12, true, true, 1, 4>(t, st);
     case K_UP2: return launch_conv_tc<48, 24, true, false, 1, 2>(t, st);
+    case K_T3: return launch_conv_tc<12, 3, false, false, CTC_S7, 2, 7, true>(t, st);
+    case K_T1: return launch_conv_tc<12, 1, false, false, CTC_S7, 2, 7, true>(t, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -592,7 +603,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->tail_variant = default_tail_variant();
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
   if (const char* at = getenv("CFEN_ATTN_TC")) p->attn_tc = atoi(at) != 0;
-  if (const char* ct = getenv("CFEN_CONV_TC")) p->conv_tc = atoi(ct) != 0;
+  if (const char* ct = getenv("CFEN_CONV_TC")) p->conv_tc = atoi(ct);
   if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm);
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
@@ -712,7 +723,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "tail_variant") == 0) { p->tail_variant = (int)value; return 0; }
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
   if (strcmp(name, "attn_tc") == 0) { p->attn_tc = value != 0; return 0; }
-  if (strcmp(name, "conv_tc") == 0) { p->conv_tc = value != 0; return 0; }
+  if (strcmp(name, "conv_tc") == 0) { p->conv_tc = (int)value; return 0; }
   if (strcmp(name, "maps16") == 0) { p->maps16 = (int)value; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
@@ -1214,7 +1225,7 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
   }
   a.scale = c.scale; a.shift = c.shift; a.flags = flags; a.stats = stats;
   Launch l(r, pcls, cflops, cbytes, "%s %dx%d b%d", name.c_str(), H, W, r.nb);
-  if (p->conv_path && p->conv_tc && c.wpack_tc && conv_tc_eligible(c.kind, a)) {
+  if (p->conv_path && p->conv_tc && c.wpack_tc && conv_tc_eligible(c.kind, a, p->conv_tc)) {
     l.sym("conv_tc_kernel<%s>", conv_kind_name(c.kind));
     CU(conv_tc_launch_dispatch(c.kind, a, c.wpack_tc, r.st));
     return 0;
@@ -1795,7 +1806,7 @@ static int conv_oneoff(int kind, const float* in0, const float* in1, const float
     a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = tmp; a.scale = scale; a.shift = shift; a.out = out;
     a.stats = stats; a.B = B; a.H = H; a.W = W; a.flags = flags; a.win = win;
     const char* cte = getenv("CFEN_CONV_TC");   // same selection as the plan (option "conv_tc")
-    if (gen2 && (!cte || atoi(cte) != 0) && conv_tc_eligible(kind, a)) {
+    if (gen2 && conv_tc_eligible(kind, a, cte ? atoi(cte) : 1)) {
       __half* wtc = nullptr;
       e = cudaMalloc(&wtc, (size_t)conv_tc_wpack_halves(conv_tc_prog(kind)) * 2);
       if (e == cudaSuccess) e = conv_tc_pack_dispatch(kind, weight, wtc, st);

@@ -34,7 +34,7 @@
 
 namespace cfen {
 
-constexpr int CTC_MAX_STEPS = 64;
+constexpr int CTC_MAX_STEPS = 128;
 
 #ifdef CTC_TIMELINE
 // device-side timeline of CTA 0 (tools/conv_tc_bench.cu -DCTC_TIMELINE; compiled out of the library)
@@ -65,16 +65,19 @@ struct ConvTcArgs {
   const __half* wpack;    // [n_steps][2][N][8] halves
   const float* scale;     // [COUT]
   const float* shift;     // [COUT]
-  __half* out;
+  void* out;              // fp16 NHWC map; tails: fp32 NCHW or uint8 HWC x3 (out_u8)
   int B, H, W;            // INPUT map size (output is 2H x 2W when transposed)
   int relu;
+  int out_u8;             // tails only: tensor2im in the epilogue (util/util.py:12-24)
   ConvTcProg prog;
 };
 
 // Compile-time geometry of one instantiation.  S = output rows per group (stride-1), GROUPS = groups per CTA tile.
-template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS>
+// KSZ = kernel size of a stride-1 layer (3, or 7 = the reflect-padded tanh tails: TAIL); transposed layers walk the 3x3
+// input offsets of the 4x4 stride-2 kernel.
+template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS, int KSZ = 3, bool TAIL = false>
 struct ConvTc {
-  static constexpr int THREADS = 288, TILE_W = 128, KS = 3;  // 3x3 taps / 3x3 input offsets of the 4x4 stride-2 kernel
+  static constexpr int THREADS = 288, TILE_W = 128, KS = TRANSPOSED ? 3 : KSZ, PAD = KS / 2;
   static constexpr int NSUB = TRANSPOSED ? 4 : S;           // COUT-column sub-blocks of a group: phases / output rows
   static constexpr int N = (NSUB * COUT + 15) / 16 * 16;    // accumulator columns per group
   static constexpr int CB = CIN % 8 == 0 ? 16 : 8;          // bytes per copy piece
@@ -89,7 +92,7 @@ struct ConvTc {
   static constexpr int IROWS = TRANSPOSED ? 3 : S + KS - 1; // input rows a group reads
   static constexpr int NSTEPS = IROWS * KS * KP;
   static constexpr int RPG = TRANSPOSED ? 1 : S;            // input-row advance between groups
-  static constexpr int HALO_ROWS = GROUPS * RPG + KS - 1, PITCH = TILE_W + 2;
+  static constexpr int HALO_ROWS = GROUPS * RPG + KS - 1, PITCH = TILE_W + 2 * PAD;
   static constexpr int PLANE_BYTES = HALO_ROWS * PITCH * 16, STAGE_BYTES = PLANES * PLANE_BYTES;
   static constexpr int W_BYTES = NSTEPS * N * 32;
   static constexpr int NS = (3 * STAGE_BYTES + W_BYTES + 128 <= 200 * 1024) ? 3 : 2;   // halo stages
@@ -166,9 +169,9 @@ inline ConvTcProg conv_tc_prog_t(int cin, int cout, int groups, int maps = 1) {
   return p;
 }
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS>
+template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS, int KSZ, bool TAIL>
 __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
-  using K = ConvTc<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS>;
+  using K = ConvTc<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS, KSZ, TAIL>;
   constexpr int NS = K::NS, NSETS = K::NSETS;
   extern __shared__ uint8_t ctc_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[3], empty_bar[3], acc_full[4], acc_empty[4];
@@ -228,14 +231,23 @@ __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
     // the first map's in the pixel's chunk list
     auto issue_tile = [&](int t, int s) {
       const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-      const int gy0 = ty * rows_tile - 1, gx0 = tx * K::TILE_W - 1;
+      const int gy0 = ty * rows_tile - K::PAD, gx0 = tx * K::TILE_W - K::PAD;
       uint8_t* dst = smem + s * K::STAGE_BYTES;
       bool okx[EPR];
+      int sx[TAIL ? EPR : 1];   // TAIL (ReflectionPad2d, v3.py:354): source shift of reflected halo columns, in halves
 #pragma unroll
-      for (int e = 0; e < EPR; ++e) okx[e] = (unsigned)(gx0 + e_px[e]) < (unsigned)a.W;
-      const long long img = ((long long)b * a.H * a.W + gx0) * CIN;   // halves; gx0 may be -1
+      for (int e = 0; e < EPR; ++e) {
+        int gx = gx0 + e_px[e];
+        if constexpr (TAIL) {
+          if (e_px[e] >= 0) gx = gx < 0 ? -gx : (gx >= a.W ? 2 * (a.W - 1) - gx : gx);
+          sx[e] = (gx - gx0 - (e_px[e] >= 0 ? e_px[e] : 0)) * CIN;
+        }
+        okx[e] = (unsigned)gx < (unsigned)a.W;
+      }
+      const long long img = ((long long)b * a.H * a.W + gx0) * CIN;   // halves; gx0 may be negative
       for (int hy = 0; hy < K::HALO_ROWS; ++hy) {
-        const int gy = gy0 + hy;
+        int gy = gy0 + hy;
+        if constexpr (TAIL) gy = gy < 0 ? -gy : (gy >= a.H ? 2 * (a.H - 1) - gy : gy);
         const bool row_ok = (unsigned)gy < (unsigned)a.H;
         const long long rowoff = img + (long long)(row_ok ? gy : 0) * a.W * CIN;
         uint8_t* drow = dst + hy * K::PITCH * 16;
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
             if (e_px[e] >= 0) {
               const bool ok = row_ok && okx[e];
               const __half* map = (SUM2 && e_second[e]) ? a.in1 : a.in0;
-              const __half* src = ok ? map + (rowoff + e_src[e]) : a.in0;
+              const __half* src = ok ? map + (rowoff + e_src[e] + (TAIL ? sx[TAIL ? e : 0] : 0)) : a.in0;
               if (K::CB == 16) cp_async16(drow + e_dst[e], src, ok);
               else cp_async8(drow + e_dst[e], src, ok);
             }
@@ -343,7 +355,26 @@ __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
           tc::tc_fence_before();
           tc::mbar_arrive(&acc_empty[as]);
         }
-        if (TRANSPOSED) {
+        if (TAIL) {
+          // tanh, then fp32 NCHW (the module contract) or uint8 HWC x3 (tensor2im fused, one-channel maps tiled)
+#pragma unroll
+          for (int sb = 0; sb < S; ++sb) {
+            const int oy = ty * rows_tile + g * S + sb, ox = tx * K::TILE_W + x;
+            float o[COUT];
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) o[c] = tanhf(__uint_as_float(v[sb * COUT + c]) * sc[c] + sh[c]);
+            if (a.out_u8) {
+              uint8_t* op = static_cast<uint8_t*>(a.out) + (((size_t)b * a.H + oy) * a.W + ox) * 3;
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                op[c] = (uint8_t)fminf(fmaxf((o[COUT > 1 ? c % COUT : 0] + 1.f) * 0.5f * 255.f, 0.f), 255.f);
+            } else {
+              float* op = static_cast<float*>(a.out) + ((size_t)b * COUT * a.H + oy) * a.W + ox;
+#pragma unroll
+              for (int c = 0; c < COUT; ++c) op[(size_t)c * a.H * a.W] = o[c];
+            }
+          }
+        } else if (TRANSPOSED) {
           // the two horizontal phases of this input pixel are adjacent output pixels: 2 * COUT halves contiguous
 #pragma unroll
           for (int py = 0; py < 2; ++py) {
@@ -357,7 +388,7 @@ __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
               o[i] = pack_half2(r0, r1);
             }
             const int oy = 2 * (ty * rows_tile + g) + py, ox = 2 * (tx * K::TILE_W + x);
-            uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)b * 2 * a.H + oy) * (2 * a.W) + ox) * COUT);
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(a.out) + (((size_t)b * 2 * a.H + oy) * (2 * a.W) + ox) * COUT);
 #pragma unroll
             for (int q = 0; q < COUT / 4; ++q) op[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
           }
@@ -382,7 +413,7 @@ __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
                 o[4 * c4] += p0.x; o[4 * c4 + 1] += p0.y; o[4 * c4 + 2] += p1.x; o[4 * c4 + 3] += p1.y;
               }
             }
-            uint2* op = reinterpret_cast<uint2*>(a.out + opix * COUT);
+            uint2* op = reinterpret_cast<uint2*>(static_cast<__half*>(a.out) + opix * COUT);
 #pragma unroll
             for (int c4 = 0; c4 < COUT / 4; ++c4)
               op[c4] = make_uint2(pack_half2(o[4 * c4], o[4 * c4 + 1]), pack_half2(o[4 * c4 + 2], o[4 * c4 + 3]));
@@ -399,34 +430,36 @@ __global__ void __launch_bounds__(288, 1) conv_tc_kernel(const ConvTcArgs a) {
 
 // the instantiations the plan uses
 constexpr int CTC_S3 = 4;   // output rows per group of the 3x3 layers
-using ConvTcC3 = ConvTc<12, 12, false, false, CTC_S3, 2>;
-using ConvTcUp1 = ConvTc<24, 12, true, true, 1, 4>;
-using ConvTcUp2 = ConvTc<48, 24, true, false, 1, 2>;
+constexpr int CTC_S7 = 4;   // ... of the 7x7 tails (70 steps per group, N = 16)
 
-template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS>
+template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS, int KSZ = 3, bool TAIL = false>
 inline cudaError_t conv_tc_set_attr_one() {
-  return cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTc<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS>::SMEM_BYTES);
+  return cudaFuncSetAttribute(conv_tc_kernel<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS, KSZ, TAIL>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              ConvTc<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS, KSZ, TAIL>::SMEM_BYTES);
 }
 inline cudaError_t conv_tc_set_attr() {
   cudaError_t e;
   if ((e = conv_tc_set_attr_one<12, 12, false, false, CTC_S3, 2>()) != cudaSuccess) return e;
   if ((e = conv_tc_set_attr_one<24, 12, true, true, 1, 4>()) != cudaSuccess) return e;
-  return conv_tc_set_attr_one<48, 24, true, false, 1, 2>();
+  if ((e = conv_tc_set_attr_one<48, 24, true, false, 1, 2>()) != cudaSuccess) return e;
+  if ((e = conv_tc_set_attr_one<12, 3, false, false, CTC_S7, 2, 7, true>()) != cudaSuccess) return e;
+  return conv_tc_set_attr_one<12, 1, false, false, CTC_S7, 2, 7, true>();
 }
 
-template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS>
+template <int CIN, int COUT, bool TRANSPOSED, bool SUM2, int S, int GROUPS, int KSZ = 3, bool TAIL = false>
 inline cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
-  using K = ConvTc<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS>;
+  using K = ConvTc<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS, KSZ, TAIL>;
   if (a.B <= 0) return cudaSuccess;
   constexpr int rows_tile = GROUPS * K::RPG;
   // the host-side program (weight packing) and the kernel's compile-time geometry must describe the same steps
   if (a.W % 128 != 0 || a.H % rows_tile != 0 || a.prog.n_steps != K::NSTEPS || a.prog.N != K::N ||
-      a.prog.groups != GROUPS || a.prog.halo_rows != K::HALO_ROWS || a.prog.planes != K::PLANES)
+      a.prog.groups != GROUPS || a.prog.halo_rows != K::HALO_ROWS || a.prog.planes != K::PLANES ||
+      a.prog.pitch != K::PITCH)
     return cudaErrorInvalidValue;
   const int n_tiles = a.B * (a.H / rows_tile) * (a.W / 128);
   const int grid = n_tiles < 148 ? n_tiles : 148;
-  conv_tc_kernel<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS><<<grid, 288, K::SMEM_BYTES, st>>>(a);
+  conv_tc_kernel<CIN, COUT, TRANSPOSED, SUM2, S, GROUPS, KSZ, TAIL><<<grid, 288, K::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -158,6 +158,8 @@ OPTION_SETS = [
     {"CFEN_FUSE_MIN_TILES": "1", "CFEN_TAIL_VARIANT": "0"},
     {"CFEN_FUSE_MIN_TILES": "1", "CFEN_TAIL_VARIANT": "1"},
     {"CFEN_FUSE_MIN_TILES": "1", "CFEN_ATTN_TC": "0"},
+    {"CFEN_CONV_TC": "0"},
+    {"CFEN_CONV_TC": "2"},
     {"CFEN_SPLIT_K": "0"},
     {"CFEN_STREAMS": "0"},
     {"CFEN_MAPS16": "0"},

@@ -500,6 +500,35 @@ def test_conv_tc_transposed(kind, cin, cout, B, H, W, monkeypatch):
         assert U.rel_err(U.to_nchw(out.float()), ref) <= TF32_TOL, tcv
 
 
+@pytest.mark.parametrize("kind,cout", [("tail7x7_3", 3), ("tail7x7_1", 1)])
+@pytest.mark.parametrize("B,H,W", [(2, 32, 128), (1, 64, 256), (1, 128, 128)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_conv_tc_tail7x7(kind, cout, B, H, W, u8, monkeypatch):
+    """ReflectionPad2d(3) + conv7x7 12->{3,1} + tanh (v3.py:354-356, 366-368, 378-380) on tcgen05: reflected halo rows
+    and columns in the loader, banded weights over 4 output rows, fp32 NCHW or fused-tensor2im uint8 HWC output."""
+    x, w, b = dev(B, 12, H, W, seed=1), dev(cout, 12, 7, 7, seed=2, scale=0.05), dev(cout, seed=3)
+    xi = U.to_nhwc(x).half()
+    y = torch.tanh(F.conv2d(F.pad(U.to_nchw(xi.float()).double(), (3, 3, 3, 3), mode="reflect"), w.double(), b.double()))
+    outs = {}
+    for tcv in ("2", "0"):      # level 2 selects the tcgen05 tails (level 1, the default, leaves them to conv16)
+        monkeypatch.setenv("CFEN_CONV_TC", tcv)
+        if u8:
+            out = torch.zeros(B, H, W, 3, device="cuda", dtype=torch.uint8)
+            _conv(kind, xi, None, w, b, None, None, out, B, H, W, TANH | ONCHW | IN16 | 4096)
+            y3 = y.expand(-1, 3, -1, -1) if cout == 1 else y
+            ref = ((y3.permute(0, 2, 3, 1) + 1) / 2.0 * 255.0).clamp(0, 255)
+            d = (out.double() - ref.floor()).abs()
+            assert d.max().item() <= 1 and d.mean().item() <= 0.2, (tcv, d.max().item(), d.mean().item())
+        else:
+            out = torch.full((B, cout, H, W), float("nan"), device="cuda")
+            _conv(kind, xi, None, w, b, None, None, out, B, H, W, TANH | ONCHW | IN16)
+            assert bool(torch.isfinite(out).all())
+            assert (out.double() - y).abs().max().item() <= 3e-3, tcv      # tanh output in [-1, 1]
+        outs[tcv] = out
+    if not u8:
+        assert (outs["2"] - outs["0"]).abs().max().item() <= 3e-3
+
+
 def test_conv_fp16_map_chain_up_tail():
     """The full-resolution decoder tail as cfen_forward stores it: up_24_12 -> fp16 map -> 3x3 -> fp16 map -> reflect
     7x7 + tanh -> fp32 NCHW; ds_12_24 reading an fp16 map."""
