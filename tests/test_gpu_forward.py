@@ -407,3 +407,52 @@ def test_forward_host_streaming_defer_sync(monkeypatch):
     for out, ref in zip(outs, refs):
         for a, b in zip(out, ref):
             assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_sharded_data_parallel_two_gpus():
+    """define_G with two gpu_ids (v3.py:77-83 wraps in DataParallel): the wrapper here cuts the batch into contiguous
+    image shards over per-device plans.  Bit-identical to the single-device forward, outputs gathered on device 0,
+    the caller's current device untouched, `.module` / isinstance as BaseModel.save_networks expects."""
+    import cfen_vit_dehazing_b200 as prod
+    from cfen_vit_dehazing_b200.networks_iid_hlgvit_crs_gd4_cfs_v3 import ImageShardedDataParallel
+    net0, sd0, sd1, x0, opt = U.seeded_state(2, 128)
+    import copy
+    opt2 = copy.copy(opt)
+    opt2.gpu_ids = [0, 1]
+    with contextlib.redirect_stdout(io.StringIO()):
+        dp = prod.define_G(opt2, prod.common.default_conv)
+    assert isinstance(dp, torch.nn.DataParallel) and isinstance(dp, ImageShardedDataParallel)
+    dp.module.load_state_dict(sd1, strict=True)
+    assert next(dp.module.parameters()).device == torch.device("cuda", 0)
+    x = orc.make_inputs(128, [1, 5])[1]
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        single = dp.module(x.cuda(0))
+        both = dp(x.cuda(0))
+        again = dp(x)                       # CPU input is scattered like nn.DataParallel does
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert {k[0] for k in dp.module._plans} == {0, 1}
+    for a, b, c in zip(single, both, again):
+        assert b.device == torch.device("cuda", 0) and torch.equal(a, b) and torch.equal(a, c)
+    ref = orc.forward(sd1, x)
+    for a, b in zip(both, ref):
+        mx, ps = U.err01(a, b)
+        assert mx <= MAX_ABS_01 and ps >= MIN_PSNR
+    # weights changed on the master -> every device re-packs
+    with torch.no_grad():
+        dp.module.tail_D[0][5].bias.add_(0.25)
+        moved = dp(x.cuda(0))
+    assert not torch.equal(moved[2], both[2]) and torch.equal(moved[2][:3], dp.module(x[:3].cuda(0))[2])
+    # un-primed module: the first forward calibrates on the master device with the whole batch
+    with contextlib.redirect_stdout(io.StringIO()):
+        dp2 = prod.define_G(opt2, prod.common.default_conv)
+    dp2.module.load_state_dict(sd0, strict=True)
+    with torch.no_grad():
+        dp2(x0.cuda(0))
+        out2 = dp2(x.cuda(0))
+    for a, b in zip(out2, ref):
+        mx, ps = U.err01(a, b)
+        assert mx <= 2 * MAX_ABS_01 and ps >= MIN_PSNR - 3
