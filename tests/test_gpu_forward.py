@@ -428,7 +428,9 @@ def test_sharded_data_parallel_two_gpus():
     x = orc.make_inputs(128, [1, 5])[1]
     torch.cuda.set_device(0)
     with torch.no_grad():
-        single = dp.module(x.cuda(0))
+        # the shards (3 + 2 images) run the kernels a 3- / 2-image batch selects: compare with those batches on device 0
+        head, tail = dp.module(x[:3].cuda(0)), dp.module(x[3:].cuda(0))
+        single = [torch.cat((a, b), 0) for a, b in zip(head, tail)]
         both = dp(x.cuda(0))
         again = dp(x)                       # CPU input is scattered like nn.DataParallel does
     torch.cuda.synchronize(0)
