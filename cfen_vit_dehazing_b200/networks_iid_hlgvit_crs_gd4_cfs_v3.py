@@ -517,6 +517,40 @@ class dec_ipt(nn.Module):
             lo += n
         return [torch.cat([p[i].to(out_dev, non_blocking=True) for p in parts], 0) for i in range(3)]
 
+    # ------------------------------------------------------------------ fp16 range guard
+    _WIDE_RANGE = {"gemm_path": 1, "conv_path": 0, "maps16": 0}      # TF32 operands (8-bit exponent), fp32 maps
+
+    def verify_fp16_range(self, x, tol=2e-2, fallback=True):
+        """Guard for real checkpoints.  The default configuration stores every stage map and token operand as fp16
+        with saturating conversions (+-65504): fine for activations of the magnitude the parity suite sees, silently
+        wrong beyond.  This runs ``x`` (a representative [B,3,H,W] CUDA batch) through the default configuration AND
+        through the wide-range one (TF32 tensor-core operands, fp32 maps: ``CFEN_GEMM_PATH=1 CFEN_CONV_PATH=0
+        CFEN_MAPS16=0``, each parity-tested against the oracle) and compares the raw [-1,1] outputs.  If they differ by
+        more than ``tol`` (default: the parity gate) some activation left the fp16 range: with ``fallback`` the plan
+        for this device / size stays on the wide-range configuration (about 2.5x slower), otherwise RuntimeError.
+        Returns {"max_abs_diff", "ok", "fallback_engaged"}."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4):
+            raise RuntimeError("verify_fp16_range expects a [B, 3, H, W] CUDA batch")
+        b, _, h, w = x.shape
+        with torch.no_grad():
+            fast = [o.clone() for o in self.forward(x)]
+            plan = self._plan_for(x.device, h, w, b)
+            saved = {k: plan.get_option(k) for k in self._WIDE_RANGE}
+            for k, v in self._WIDE_RANGE.items():
+                plan.set_option(k, v)
+            wide = self.forward(x)
+            diff = max((a - c).abs().max().item() for a, c in zip(fast, wide))
+            finite = all(bool(torch.isfinite(a).all()) for a in fast)
+        ok = finite and diff <= tol
+        if ok or not fallback:
+            for k, v in saved.items():
+                plan.set_option(k, v)
+        if not ok and not fallback:
+            raise RuntimeError("fp16 range exceeded: the fp16 configuration differs from the wide-range one by %.3g "
+                               "(> %.3g) on this batch; run with CFEN_GEMM_PATH=1 CFEN_CONV_PATH=0 CFEN_MAPS16=0 or "
+                               "call verify_fp16_range(..., fallback=True)" % (diff, tol))
+        return {"max_abs_diff": diff, "ok": ok, "fallback_engaged": (not ok) and fallback}
+
     # ------------------------------------------------------------------ fused uint8 boundary / fake_A-only (F1)
     _OUTPUT_NAMES = ("fake_R", "fake_S", "fake_A")      # DECHLGVIT.forward, model_iid_dehazing.py:143
 

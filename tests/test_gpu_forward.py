@@ -248,6 +248,36 @@ def test_cfs_sibling_batch16_fused_kernels_uint8_and_calibration():
     assert all(int(got[k]) == 1 for k in sd1 if k.endswith(".initialized"))
 
 
+def test_fp16_range_guard_detects_and_falls_back():
+    """ADVICE r1 / VERDICT r1 #9: fp16 stage maps saturate silently at +-65504.  verify_fp16_range compares the default
+    configuration with the wide-range one (TF32 operands, fp32 maps).  Normal weights: agree, nothing changes.  A head
+    convolution scaled x30000 drives the full-resolution maps beyond fp16 (InstanceNorm behind ds_conv_e01 makes the
+    REFERENCE scale-invariant, so the oracle output stays ordinary): the guard reports it, engages the fallback, and
+    the forward then matches the oracle again."""
+    gnet, sd0, sd1, x0 = _gpu_net(2, 128)
+    x = orc.make_inputs(128, [1, 2])[1]
+    rep = gnet.verify_fp16_range(x.cuda())
+    assert rep["ok"] and not rep["fallback_engaged"] and rep["max_abs_diff"] <= 1e-2
+    plan = gnet._plans[(torch.cuda.current_device(), 128, 128)]
+    assert plan.get_option("gemm_path") == 2 and plan.get_option("maps16") == 2
+    big = {k: v.clone() for k, v in sd1.items()}
+    big["head.0.0.weight"] = big["head.0.0.weight"] * 30000.0
+    big["head.0.0.bias"] = big["head.0.0.bias"] * 30000.0
+    ref = orc.forward(big, x)
+    assert all(bool(torch.isfinite(r).all()) for r in ref)
+    gnet.load_state_dict(big, strict=True)
+    with pytest.raises(RuntimeError, match="fp16 range exceeded"):
+        gnet.verify_fp16_range(x.cuda(), fallback=False)
+    rep = gnet.verify_fp16_range(x.cuda())
+    assert not rep["ok"] and rep["fallback_engaged"]
+    assert plan.get_option("gemm_path") == 1 and plan.get_option("maps16") == 0
+    with torch.no_grad():
+        out = gnet(x.cuda())
+    for a, b in zip(out, ref):
+        mx, ps = U.err01(a, b)
+        assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (mx, ps)
+
+
 def test_batch_chunking_and_batch_invariance(monkeypatch):
     """A batch larger than the plan's internal chunk (set to 16 images here) equals the same chunks run as
     separate calls bit for bit; a single image differs from its in-batch result only by kernel selection
