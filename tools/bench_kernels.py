@@ -1,6 +1,6 @@
 """Micro-benchmarks of individual kernels through the C ABI (CUDA events, L2 flushed between reps).
 
-    python tools/bench_kernels.py mlp|gemm|attn [--json out.json]
+    python tools/bench_kernels.py mlp|gemm|attn|gemm16|mlp16|attn16|dcn [--json out.json]
 """
 import ctypes
 import json
@@ -143,10 +143,67 @@ def attn16():
     return out
 
 
+def dcn():
+    """Deformable conv v1 / v2 forward (row A14) at EDVR-like alignment shapes.  The op is a gather: per output pixel
+    and tap 4 bilinear corners of Cin/dg channels.  Algorithmic bytes = input + offset (+ mask) + output + weight, fp32;
+    the reference materialises the sampled columns (Cin*k*k floats per output pixel, written and read once more) - the
+    figure `columns_gb_saved` - before its cuBLAS product; here gather and contraction are one kernel."""
+    from cfen_vit_dehazing_b200 import dcn as D
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+        if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    out = []
+    for B, C, H, W, Co, k, dg, mod in [(8, 64, 128, 128, 64, 3, 8, True), (8, 64, 128, 128, 64, 3, 8, False),
+                                        (4, 64, 256, 256, 64, 3, 8, True), (16, 128, 64, 64, 128, 3, 4, True)]:
+        x = torch.randn(B, C, H, W, device="cuda")
+        off = torch.randn(B, dg * 2 * k * k, H, W, device="cuda") * 2.0
+        mask = torch.sigmoid(torch.randn(B, dg * k * k, H, W, device="cuda"))
+        wt = torch.randn(Co, C, k, k, device="cuda") * 0.05
+        bias = torch.zeros(Co, device="cuda")
+        if mod:
+            fn = lambda: D.modulated_deform_conv(x, off, mask, wt, bias, 1, 1, 1, 1, dg)
+        else:
+            fn = lambda: D.deform_conv(x, off, wt, 1, 1, 1, 1, dg)
+        us = timeit(fn)
+        ref_us = None
+        ref_so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libdcn_ref.so")
+        if os.path.exists(ref_so):
+            # the reference's own CUDA path on this GPU: its im2col kernel (compiled unmodified, oracle/build_dcn_ref.py;
+            # bench.py's cpu_baseline leg and this tool are the only places outside tests/ that execute oracle/) + the
+            # weight x columns product (cuBLAS through torch.matmul, as the reference's addmm_)
+            R = ctypes.CDLL(ref_so)
+            i32 = ctypes.c_int
+            col = torch.empty(B, C * k * k, H * W, device="cuda")
+            wm = wt.view(Co, -1)
+            outb = torch.empty(B, Co, H * W, device="cuda")
+
+            def ref():
+                if mod:
+                    for bi in range(B):
+                        R.dcn_ref_modulated_deformable_im2col(P(x[bi]), P(off[bi]), P(mask[bi]), i32(1), i32(C), i32(H), i32(W),
+                                                              i32(H), i32(W), i32(k), i32(k), i32(1), i32(1), i32(1), i32(1),
+                                                              i32(1), i32(1), i32(dg), P(col[bi]))
+                        torch.matmul(wm, col[bi], out=outb[bi])
+                else:
+                    for bi in range(B):
+                        R.dcn_ref_deformable_im2col(P(x[bi]), P(off[bi]), i32(C), i32(H), i32(W), i32(k), i32(k), i32(1), i32(1),
+                                                    i32(1), i32(1), i32(1), i32(1), i32(1), i32(dg), P(col[bi]))
+                        torch.matmul(wm, col[bi], out=outb[bi])
+            ref_us = timeit(ref, reps=4)
+        by = 4.0 * (x.numel() + off.numel() + (mask.numel() if mod else 0) + B * Co * H * W + wt.numel())
+        fl = 2.0 * B * H * W * C * k * k * Co
+        out.append(dict(kernel="deform_conv_fwd_kernel", v2=mod, B=B, C=C, H=H, W=W, Cout=Co, k=k, dg=dg, us=us,
+                        gbs=by / us / 1e3, frac_of_hbm_peak=by / us / 1e3 / peaks["hbm_gbs"], tflops=fl / us / 1e6,
+                        gather_gsamples_per_s=B * H * W * C * k * k / us / 1e3,
+                        columns_gb_saved=2 * 4.0 * B * H * W * C * k * k / 1e9,
+                        reference_cuda_path_us=ref_us, speedup_vs_reference_cuda_path=(ref_us / us if ref_us else None)))
+        print(out[-1])
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "mlp"
     res = []
     for w in which.split(","):
-        res += {"mlp": mlp, "gemm": gemm, "attn": attn, "gemm16": gemm16, "mlp16": mlp16, "attn16": attn16}[w]()
+        res += {"mlp": mlp, "gemm": gemm, "attn": attn, "gemm16": gemm16, "mlp16": mlp16, "attn16": attn16, "dcn": dcn}[w]()
     if "--json" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
