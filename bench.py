@@ -249,10 +249,15 @@ def launch_units(tag):
     return 0.0
 
 
-def ncu_traffic(table, sym, units, launches):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of kernel `sym`: bytes per work unit (token row or
-    pixel x image) measured by one `ncu --set full` capture of that kernel (profiles/ncu_traffic.json) times the
-    units an average launch of the timed region processed."""
+def ncu_traffic(table, sym, units, launches, images_per_pass=None, workload=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of kernel `sym`.  Preferred source: the per-launch ncu
+    pass over EVERY kernel of one 64-image pass of the 512x512 / hidden_dim_ratio 4 workload (profiles/ncu_traffic.json
+    "_per_pass", profiles/r2_v3_dram_per_kernel.md), scaled to this run's images per pass.  Otherwise bytes per work
+    unit (token row or pixel x image) from one `ncu --set full` capture of that kernel times the units an average
+    launch of the timed region processed.  None without a capture."""
+    pp = table.get("_per_pass")
+    if pp and workload == (512, 4) and images_per_pass and sym in pp["kernels"]:
+        return pp["kernels"][sym]["dram_bytes_per_launch"] * images_per_pass / pp["images"]
     ent = table.get(sym)
     if not ent or not launches or not units:
         return None
@@ -491,7 +496,7 @@ def run_ours(args):
             e = roofline_of(d, peaks)
             e.update({"kernel": sym, "share_of_step": d["us"] / t_all, "launches": d["launches"],
                       "avg_launch_us": d["us"] / max(1, d["launches"]),
-                      "traffic": ncu_traffic(traffic_table, sym, d["units"], d["launches"])})
+                      "traffic": ncu_traffic(traffic_table, sym, d["units"], d["launches"], plan.max_batch, (size, hr))})
             roofline_all.append(e)
         name, d = max(kernels.items(), key=lambda kv: kv[1]["us"])
         nl = max(1, d["launches"])

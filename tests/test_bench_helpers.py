@@ -77,7 +77,12 @@ def test_ncu_traffic_table_scales_with_units():
     t2 = b.ncu_traffic(table, sym, 1048576.0 * 4, 4)
     assert t1 and abs(t2 / t1 - 2.0) < 1e-9
     assert abs(t1 - table[sym]["bytes_per_unit"] * 524288) < 1.0
-    assert b.ncu_traffic(table, "gemm16_kernel<192>", 512.0, 1) is None     # no capture for that kernel
+    assert b.ncu_traffic(table, "gemm16_kernel<192>", 512.0, 1) is None     # no per-unit capture for that kernel
+    # ... but the per-pass table (every kernel of one 64-image pass of the 512x512 / hr 4 workload) has it
+    full = b.ncu_traffic(table, "gemm16_kernel<192>", 512.0, 1, images_per_pass=64, workload=(512, 4))
+    half = b.ncu_traffic(table, "gemm16_kernel<192>", 512.0, 1, images_per_pass=32, workload=(512, 4))
+    assert full and abs(full / half - 2.0) < 1e-9
+    assert b.ncu_traffic(table, "gemm16_kernel<192>", 512.0, 1, images_per_pass=64, workload=(1024, 4)) is None
 
 
 @pytest.mark.parametrize("size,hr,world,gb,per", [(512, 4, 1, 256, 256), (512, 4, 2, 256, 128), (512, 4, 8, 256, 32),
