@@ -28,6 +28,7 @@
 #include "attn16.cuh"
 #include "attn_tc.cuh"
 #include "gemm16.cuh"
+#include "gemm_small.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tf32.cuh"
 #include "map_kernels.cuh"
@@ -307,6 +308,7 @@ static cudaError_t set_kernel_attributes() {
   if ((e = gemm_tc_set_attr()) != cudaSuccess) return e;
   if ((e = mlp_tc_set_attr()) != cudaSuccess) return e;
   if ((e = gemm16_set_attr()) != cudaSuccess) return e;
+  if ((e = gemm_small_set_attr()) != cudaSuccess) return e;
   if ((e = mlp16_set_attr()) != cudaSuccess) return e;
   if ((e = attention16_set_attr()) != cudaSuccess) return e;
   if ((e = attention_tc_set_attr()) != cudaSuccess) return e;
@@ -401,6 +403,8 @@ struct cfen_plan {
                              // GEMMs (tiles over M x N) fill the machine better - unless launch count matters (batch 1)
   int maps16 = 2;      // 0: fp32 maps; 1: fp16 full-resolution maps only; 2: every stage map is fp16
   //     // conv_path 1: the full-resolution 12-channel maps (head, last up-convolution, tail) are stored as fp16
+  int gemm_small = 1;  // gemm_path 2: Linears with <= 256 rows (global ViTs at small batch) as ONE launch (gemm_small.cuh)
+                       // instead of a 128-row tcgen05 tile grid + split-K + reduce launch
   int conv_tc = 1;     // conv_path 1: tcgen05 convolutions where eligible (conv_tc.cuh), else conv16
   int attn_tc = 1;     // gemm_path 2, 256-token windows with 24-wide heads: tcgen05 / TMEM attention (attn_tc.cuh)
   int fuse_front = 1;  // gemm_path 2, local ViTs with E <= 192: window gather + linear_encoding + pos + LN + in-projection
@@ -604,6 +608,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* ff = getenv("CFEN_FUSE_FRONT")) p->fuse_front = atoi(ff) != 0;
   if (const char* at = getenv("CFEN_ATTN_TC")) p->attn_tc = atoi(at) != 0;
   if (const char* ct = getenv("CFEN_CONV_TC")) p->conv_tc = atoi(ct);
+  if (const char* gs = getenv("CFEN_GEMM_SMALL")) p->gemm_small = atoi(gs) != 0;
   if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm);
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
@@ -701,6 +706,7 @@ extern "C" int32_t cfen_plan_get_option(const cfen_plan* p, const char* name, in
   if (strcmp(name, "fuse_front") == 0) { *value = p->fuse_front; return 0; }
   if (strcmp(name, "attn_tc") == 0) { *value = p->attn_tc; return 0; }
   if (strcmp(name, "conv_tc") == 0) { *value = p->conv_tc; return 0; }
+  if (strcmp(name, "gemm_small") == 0) { *value = p->gemm_small; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { *value = p->fuse_tail; return 0; }
   if (strcmp(name, "split_k") == 0) { *value = p->split_k; return 0; }
   return fail(5, "unknown option '%s'", name);
@@ -724,6 +730,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "fuse_front") == 0) { p->fuse_front = value != 0; return 0; }
   if (strcmp(name, "attn_tc") == 0) { p->attn_tc = value != 0; return 0; }
   if (strcmp(name, "conv_tc") == 0) { p->conv_tc = (int)value; return 0; }
+  if (strcmp(name, "gemm_small") == 0) { p->gemm_small = value != 0; return 0; }
   if (strcmp(name, "maps16") == 0) { p->maps16 = (int)value; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
@@ -964,6 +971,15 @@ static bool all_maps16(const cfen_plan* p) { return p->conv_path && p->maps16 >=
 static int run_gemm16(Run& r, const __half* A, const __half* W, float* C32, __half* C16, int M, int N, int K,
                       const float* bias, const float* res, const float* pos, int period, int relu,
                       float* part = nullptr) {
+  if (r.p->gemm_small && gemm_small_supported(M, N, K)) {
+    Gemm16Epilogue ep{bias, pos, period > 0 ? period : 1, relu, res != nullptr, C32 != nullptr, C16 != nullptr};
+    Launch l(r, PC_GEMM, 2.0 * M * N * K,
+             2.0 * ((double)M * K + (double)N * K) + (double)M * N * ((C32 ? 4 : 0) + (C16 ? 2 : 0) + (res ? 4 : 0)),
+             "gemm_small M%d N%d K%d", M, N, K);
+    l.sym("gemm_small_kernel");
+    CU(launch_gemm_small(A, W, C32, C16, res, M, N, K, ep, r.st));
+    return 0;
+  }
   const int BN = gemm16_pick_bn(M, N);
   const CUtensorMap *ta, *tw, *tc32, *tr, *tc16;
   RET(get_tmap2(r.p, A, 2, M, K, 64, 128, &ta));
@@ -1630,6 +1646,15 @@ extern "C" int32_t cfen_gemm_f16(const void* A16, const void* W16, float* C32, v
   if (!A16 || !W16 || (!C32 && !C16)) return fail(1, "cfen_gemm_f16: null argument");
   if (N % 96 != 0 || K % 16 != 0) return fail(1, "cfen_gemm_f16: N must be a multiple of 96 and K of 16");
   CU(set_kernel_attributes());
+  {
+    const char* gse = getenv("CFEN_GEMM_SMALL");   // same selection as the plan (option "gemm_small")
+    if ((!gse || atoi(gse) != 0) && gemm_small_supported(M, N, K)) {
+      Gemm16Epilogue eps{bias, pos, pos_period > 0 ? pos_period : 1, relu, residual != nullptr, C32 != nullptr, C16 != nullptr};
+      CU(launch_gemm_small(static_cast<const __half*>(A16), static_cast<const __half*>(W16), C32, static_cast<__half*>(C16),
+                           residual, M, N, K, eps, static_cast<cudaStream_t>(stream)));
+      return 0;
+    }
+  }
   const int BN = gemm16_pick_bn(M, N);
   CUtensorMap ta, tw, tc32, tr, tc16;
   bool ok = make_tmap_2d(&ta, A16, 2, M, K, 64, 128) && make_tmap_2d(&tw, W16, 2, N, K, 64, BN);

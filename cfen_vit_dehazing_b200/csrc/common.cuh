@@ -103,6 +103,14 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return v;
 }
 
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
 // ---------------------------------------------------------------- bilinear x2 applied twice
 // nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) applied twice (v3.py:1323)
 // equals, on an edge-replicated signal, a 3-tap stencil over source samples k-1, k, k+1 for output

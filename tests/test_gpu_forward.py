@@ -159,6 +159,7 @@ OPTION_SETS = [
     {"CFEN_FUSE_MIN_TILES": "1", "CFEN_TAIL_VARIANT": "1"},
     {"CFEN_FUSE_MIN_TILES": "1", "CFEN_ATTN_TC": "0"},
     {"CFEN_CONV_TC": "0"},
+    {"CFEN_GEMM_SMALL": "0"},
     {"CFEN_CONV_TC": "2"},
     {"CFEN_SPLIT_K": "0"},
     {"CFEN_STREAMS": "0"},

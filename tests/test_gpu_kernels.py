@@ -60,6 +60,42 @@ def test_gemm_tf32(M, N, K, mode, path):
     assert U.rel_err(C, ref) <= TF32_TOL
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 384, 384), (16, 1536, 6144), (16, 4608, 1536), (17, 2304, 768), (33, 96, 96),
+                                   (64, 768, 3072), (64, 3072, 768), (48, 1536, 1536), (8, 6144, 1536)])
+@pytest.mark.parametrize("mode", ["f16_bias_relu", "both_bias_res_pos", "f32_inplace_res"])
+def test_gemm_small_vs_gemm16(M, N, K, mode, monkeypatch):
+    """gemm_small_kernel (<= 64 rows: one launch, every CTA owns a slab of output columns for all rows; the global ViT
+    Linears at small batch) against fp64 and against the tcgen05 tile kernel + split-K + reduce it replaces
+    (CFEN_GEMM_SMALL=0), same operands, same epilogue contract."""
+    L = _native.lib()
+    A, W = dev(M, K, seed=1), dev(N, K, seed=2, scale=K ** -0.5)
+    bias, res, pos = dev(N, seed=3), dev(M, N, seed=4), dev(16, N, seed=5)
+    A16, W16 = to_f16(A), to_f16(W)
+    base = A16.double() @ W16.double().t()
+    got = {}
+    for sm in ("1", "0"):
+        monkeypatch.setenv("CFEN_GEMM_SMALL", sm)
+        C32 = torch.full((M, N), float("nan"), device="cuda")
+        C16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+        if mode == "f16_bias_relu":
+            G.check(L.cfen_gemm_f16(G.ptr(A16), G.ptr(W16), None, G.ptr(C16), M, N, K, G.ptr(bias), None, None, 0, 1, G.stream()))
+            ref, outs = torch.relu(base + bias.double()), [(C16, F16OUT_TOL)]
+        elif mode == "both_bias_res_pos":
+            G.check(L.cfen_gemm_f16(G.ptr(A16), G.ptr(W16), G.ptr(C32), G.ptr(C16), M, N, K, G.ptr(bias), G.ptr(res), G.ptr(pos),
+                                    16, 0, G.stream()))
+            ref = base + bias.double() + res.double() + pos.double()[torch.arange(M, device="cuda") % 16]
+            outs = [(C32, F32OUT_TOL), (C16, F16OUT_TOL)]
+        else:
+            C32 = res.clone()
+            G.check(L.cfen_gemm_f16(G.ptr(A16), G.ptr(W16), G.ptr(C32), None, M, N, K, None, G.ptr(C32), None, 0, 0, G.stream()))
+            ref, outs = base + res.double(), [(C32, F32OUT_TOL)]
+        torch.cuda.synchronize()
+        for out, tol in outs:
+            assert bool(torch.isfinite(out).all()) and U.rel_err(out, ref) <= tol, sm
+        got[sm] = outs[0][0].double()
+    assert U.rel_err(got["1"], got["0"]) <= 2e-3
+
+
 @pytest.mark.parametrize("M,E,hid", [(1000, 96, 384), (256, 96, 192), (4096, 192, 768), (130, 192, 384),
                                      (1024, 384, 1536), (64, 384, 768), (16384, 96, 384)])
 @pytest.mark.parametrize("alias", ["none", "ffn_inplace", "head_inplace"])
