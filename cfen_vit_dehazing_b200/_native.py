@@ -27,7 +27,8 @@ EXPORTED_SYMBOLS = (
     "cfen_f32_to_f16", "cfen_debug_set_buffer", "cfen_gemm_f16", "cfen_mlp_f16", "cfen_layernorm_f16", "cfen_attention_f16", "cfen_vit_tail_f16", "cfen_vit_front_f16",
     "cfen_gemm_tf32", "cfen_gemm_tc", "cfen_mlp_tc", "cfen_layernorm", "cfen_attention", "cfen_tokenize_local",
     "cfen_tokenize_global", "cfen_conv2d_nhwc", "cfen_conv2d_instnorm_relu_nhwc", "cfen_cfsm", "cfen_merge_lg",
-    "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward",
+    "cfen_deform_conv2d_forward", "cfen_modulated_deform_conv2d_forward", "cfen_deform_conv2d_backward_input",
+    "cfen_deform_conv2d_backward_parameters", "cfen_modulated_deform_conv2d_backward",
 )
 
 
@@ -96,6 +97,9 @@ def lib():
         L.cfen_merge_lg.argtypes = [vp] * 8 + [i32] * 5 + [vp]
         L.cfen_deform_conv2d_forward.argtypes = [vp, vp, vp, vp] + [i32] * 16 + [vp]
         L.cfen_modulated_deform_conv2d_forward.argtypes = [vp, vp, vp, vp, vp, vp] + [i32] * 16 + [vp]
+        L.cfen_deform_conv2d_backward_input.argtypes = [vp] * 6 + [i32] * 16 + [vp]
+        L.cfen_deform_conv2d_backward_parameters.argtypes = [vp] * 4 + [i32] * 15 + [ctypes.c_float, i32, vp]
+        L.cfen_modulated_deform_conv2d_backward.argtypes = [vp] * 10 + [i32] * 16 + [vp]
         for name in EXPORTED_SYMBOLS:
             getattr(L, name)  # AttributeError here means the .so is stale: rebuild
         _lib = L

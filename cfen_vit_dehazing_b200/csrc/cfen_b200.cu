@@ -25,6 +25,7 @@
 #include "conv_igemm.cuh"
 #include "conv_tc.cuh"
 #include "dcn.cuh"
+#include "dcn_bwd.cuh"
 #include "attn16.cuh"
 #include "attn_tc.cuh"
 #include "gemm16.cuh"
@@ -2002,4 +2003,80 @@ extern "C" int32_t cfen_modulated_deform_conv2d_forward(const float* input, cons
                 deformable_group * kH * kW);
   CU(e);
   return 0;
+}
+
+// ---- dcn backward (row F4) - kernels in dcn_bwd.cuh
+static int dcn_sm_count(int* n) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+static int dcn_bwd_status(const char* who, cudaError_t e, int kH, int kW) {
+  if (e == cudaErrorInvalidConfiguration)
+    return fail(3, "%s: kH*kW = %d (or Cout/group) exceeds the on-chip column tile", who, kH * kW);
+  CU(e);
+  return 0;
+}
+
+extern "C" int32_t cfen_deform_conv2d_backward_input(const float* input, const float* offset,
+                                                     const float* grad_output, float* grad_input,
+                                                     float* grad_offset, const float* weight, int32_t B,
+                                                     int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t kH,
+                                                     int32_t kW, int32_t strideH, int32_t strideW, int32_t padH,
+                                                     int32_t padW, int32_t dilH, int32_t dilW, int32_t group,
+                                                     int32_t deformable_group, int32_t im2col_step, void* stream) {
+  const char* who = "cfen_deform_conv2d_backward_input";
+  if (!input || !offset || !grad_output || !grad_input || !grad_offset || !weight) return fail(1, "%s: null argument", who);
+  DcnBwdArgs a{input, weight, offset, nullptr, grad_output, grad_input, grad_offset, nullptr, nullptr, nullptr, 1.f,
+               B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW, dilH, dilW, group, deformable_group, 0, 0};
+  RET(dcn_check(who, B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW, dilH, dilW, group, deformable_group,
+                &a.Ho, &a.Wo));
+  if (im2col_step <= 0 || (B > 0 && B % (im2col_step < B ? im2col_step : B) != 0))
+    return fail(1, "%s: im2col step must divide batchsize", who);
+  return dcn_bwd_status(who, launch_deform_conv_bwd_data(a, static_cast<cudaStream_t>(stream)), kH, kW);
+}
+
+extern "C" int32_t cfen_deform_conv2d_backward_parameters(const float* input, const float* offset,
+                                                          const float* grad_output, float* grad_weight, int32_t B,
+                                                          int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                                          int32_t kH, int32_t kW, int32_t strideH, int32_t strideW,
+                                                          int32_t padH, int32_t padW, int32_t dilH, int32_t dilW,
+                                                          int32_t group, int32_t deformable_group, float scale,
+                                                          int32_t im2col_step, void* stream) {
+  const char* who = "cfen_deform_conv2d_backward_parameters";
+  if (!input || !offset || !grad_output || !grad_weight) return fail(1, "%s: null argument", who);
+  DcnBwdArgs a{input, nullptr, offset, nullptr, grad_output, nullptr, nullptr, nullptr, grad_weight, nullptr, scale,
+               B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW, dilH, dilW, group, deformable_group, 0, 0};
+  RET(dcn_check(who, B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW, dilH, dilW, group, deformable_group,
+                &a.Ho, &a.Wo));
+  if (im2col_step <= 0 || (B > 0 && B % (im2col_step < B ? im2col_step : B) != 0))
+    return fail(1, "%s: im2col step must divide batchsize", who);
+  int sms = 0;
+  RET(dcn_sm_count(&sms));
+  return dcn_bwd_status(who, launch_deform_conv_bwd_weight(a, sms, static_cast<cudaStream_t>(stream)), kH, kW);
+}
+
+extern "C" int32_t cfen_modulated_deform_conv2d_backward(const float* input, const float* weight, const float* offset,
+                                                         const float* mask, const float* grad_output,
+                                                         float* grad_input, float* grad_weight, float* grad_bias,
+                                                         float* grad_offset, float* grad_mask, int32_t B, int32_t Cin,
+                                                         int32_t H, int32_t W, int32_t Cout, int32_t kH, int32_t kW,
+                                                         int32_t strideH, int32_t strideW, int32_t padH, int32_t padW,
+                                                         int32_t dilH, int32_t dilW, int32_t group,
+                                                         int32_t deformable_group, int32_t with_bias, void* stream) {
+  const char* who = "cfen_modulated_deform_conv2d_backward";
+  if (!input || !weight || !offset || !mask || !grad_output || !grad_input || !grad_weight || !grad_offset ||
+      !grad_mask || (with_bias && !grad_bias))
+    return fail(1, "%s: null argument", who);
+  DcnBwdArgs a{input, weight, offset, mask, grad_output, grad_input, grad_offset, grad_mask, grad_weight,
+               with_bias ? grad_bias : nullptr, 1.f, B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW,
+               dilH, dilW, group, deformable_group, 0, 0};
+  RET(dcn_check(who, B, Cin, H, W, Cout, kH, kW, strideH, strideW, padH, padW, dilH, dilW, group, deformable_group,
+                &a.Ho, &a.Wo));
+  int sms = 0;
+  RET(dcn_sm_count(&sms));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RET(dcn_bwd_status(who, launch_deform_conv_bwd_data(a, st), kH, kW));
+  return dcn_bwd_status(who, launch_deform_conv_bwd_weight(a, sms, st), kH, kW);
 }

@@ -1,9 +1,9 @@
-"""Host-side mirror of the reference's ``dcn/deform_conv.py`` (forward only).
+"""Host-side mirror of the reference's ``dcn/deform_conv.py`` (forward and backward).
 
 Same callables, argument order, defaults, parameter names/initialisation and error behaviour as
 
-* ``deform_conv`` / ``DeformConvFunction.forward``                    dcn/deform_conv.py:15-49, 157
-* ``modulated_deform_conv`` / ``ModulatedDeformConvFunction.forward`` dcn/deform_conv.py:97-120, 158
+* ``deform_conv`` = ``DeformConvFunction.apply``                    dcn/deform_conv.py:15-78, 157
+* ``modulated_deform_conv`` = ``ModulatedDeformConvFunction.apply`` dcn/deform_conv.py:97-145, 158
 * ``DeformConv`` :161, ``DeformConvPack`` :200, ``ModulatedDeformConv`` :221,
   ``ModulatedDeformConvPack`` :258, ``ModulatedDeformConvPack2`` :294
 
@@ -11,8 +11,10 @@ but instead of the pybind module ``deform_conv_cuda`` (dcn/src/deform_conv_cuda.
 kernel + cuBLAS addmm per image/group) the two forward functions call the C-ABI entry points
 ``cfen_deform_conv2d_forward`` / ``cfen_modulated_deform_conv2d_forward`` of libcfen_b200.so: one
 fused gather+contraction kernel, no ``columns`` buffer.  CPU tensors raise NotImplementedError exactly
-like the reference (deform_conv.py:36-37, 109-110); there is no fallback.  Backward (training) is out
-of scope: outputs do not carry autograd history.
+like the reference (deform_conv.py:36-37, 109-110); there is no fallback.  Backward
+goes through ``cfen_deform_conv2d_backward_input`` / ``_backward_parameters`` /
+``cfen_modulated_deform_conv2d_backward`` (csrc/dcn_bwd.cuh), again with no ``columns`` buffer; like the
+reference's Functions it is once-differentiable and computes in fp32.
 """
 import ctypes
 import logging
@@ -20,6 +22,8 @@ import math
 
 import torch
 import torch.nn as nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 from torch.nn.modules.utils import _pair
 
 from .. import _native
@@ -52,14 +56,11 @@ def _output_size(input, weight, padding, dilation, stride):
     return shape
 
 
-def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
-                im2col_step=64):
-    """DCNv1 forward; mirrors DeformConvFunction.forward (deform_conv.py:17-49)."""
-    if input is not None and input.dim() != 4:
-        raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
-    stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
-    if not input.is_cuda:
-        raise NotImplementedError
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _deform_conv_forward(input, offset, weight, stride, padding, dilation, groups, deformable_groups, im2col_step):
     x, off, w = _f32c(input), _f32c(offset), _f32c(weight)
     output = x.new_empty(_output_size(x, w, padding, dilation, stride))
     cur_im2col_step = min(im2col_step, x.shape[0])
@@ -75,43 +76,127 @@ def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1
         raise RuntimeError("invalid number of input planes, expected: %d, but got: %d"
                            % (w.size(1) * groups, x.size(1)))
     with torch.cuda.device(x.device):
-        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         _native.check(_native.lib().cfen_deform_conv2d_forward(
             _ptr(x), _ptr(w), _ptr(off), _ptr(output), x.size(0), x.size(1), x.size(2), x.size(3), w.size(0),
             w.size(2), w.size(3), stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
-            groups, deformable_groups, cur_im2col_step, stream))
+            groups, deformable_groups, cur_im2col_step, _stream(x)))
     return output
 
 
-def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                          deformable_groups=1):
-    """DCNv2 forward; mirrors ModulatedDeformConvFunction.forward (deform_conv.py:99-120): scalar
-    stride/padding/dilation, optional bias."""
-    if not input.is_cuda:
-        raise NotImplementedError
-    x, off, msk, w = _f32c(input), _f32c(offset), _f32c(mask), _f32c(weight)
-    with_bias = bias is not None
-    b = _f32c(bias) if with_bias else None
+class DeformConvFunction(Function):
+    """DCNv1; mirrors DeformConvFunction (dcn/deform_conv.py:15-93): forward :17-49, backward :51-78."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        ctx.groups, ctx.deformable_groups, ctx.im2col_step = groups, deformable_groups, im2col_step
+        ctx.save_for_backward(input, offset, weight)
+        if not input.is_cuda:
+            raise NotImplementedError
+        return _deform_conv_forward(input, offset, weight, ctx.stride, ctx.padding, ctx.dilation, groups,
+                                    deformable_groups, im2col_step)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, weight = ctx.saved_tensors
+        grad_input = grad_offset = grad_weight = None
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        x, off, w, go = _f32c(input), _f32c(offset), _f32c(weight), _f32c(grad_output)
+        cur_im2col_step = min(ctx.im2col_step, x.shape[0])
+        assert (x.shape[0] % cur_im2col_step) == 0, 'im2col step must divide batchsize'
+        shape = (x.size(0), x.size(1), x.size(2), x.size(3), w.size(0), w.size(2), w.size(3), ctx.stride[0],
+                 ctx.stride[1], ctx.padding[0], ctx.padding[1], ctx.dilation[0], ctx.dilation[1], ctx.groups,
+                 ctx.deformable_groups)
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                grad_input = torch.zeros_like(x)
+                grad_offset = torch.zeros_like(off)
+                _native.check(_native.lib().cfen_deform_conv2d_backward_input(
+                    _ptr(x), _ptr(off), _ptr(go), _ptr(grad_input), _ptr(grad_offset), _ptr(w), *shape,
+                    cur_im2col_step, _stream(x)))
+                grad_input, grad_offset = grad_input.to(input.dtype), grad_offset.to(offset.dtype)
+            if ctx.needs_input_grad[2]:
+                grad_weight = torch.zeros_like(w)
+                _native.check(_native.lib().cfen_deform_conv2d_backward_parameters(
+                    _ptr(x), _ptr(off), _ptr(go), _ptr(grad_weight), *shape, ctypes.c_float(1.0), cur_im2col_step,
+                    _stream(x)))
+                grad_weight = grad_weight.to(weight.dtype)
+        return (grad_input, grad_offset, grad_weight, None, None, None, None, None, None)
+
+
+def _modulated_shapes(x, off, msk, w, stride, padding, dilation, groups, deformable_groups):
     kh, kw = w.shape[2:4]
     if x.size(1) != w.size(1) * groups:
         raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (x.size(1), w.size(1) * groups))
     n, height, width = x.size(0), x.size(2), x.size(3)
     height_out = (height + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1      # _infer_shape :147-155
     width_out = (width + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
-    output = x.new_empty((n, w.size(0), height_out, width_out))
     if tuple(off.shape) != (n, deformable_groups * 2 * kh * kw, height_out, width_out):
         raise RuntimeError("offset must be [%d, %d, %d, %d], got %s"
                            % (n, deformable_groups * 2 * kh * kw, height_out, width_out, tuple(off.shape)))
     if tuple(msk.shape) != (n, deformable_groups * kh * kw, height_out, width_out):
         raise RuntimeError("mask must be [%d, %d, %d, %d], got %s"
                            % (n, deformable_groups * kh * kw, height_out, width_out, tuple(msk.shape)))
-    with torch.cuda.device(x.device):
-        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        _native.check(_native.lib().cfen_modulated_deform_conv2d_forward(
-            _ptr(x), _ptr(w), _ptr(b) if with_bias else None, _ptr(off), _ptr(msk), _ptr(output), n, x.size(1),
-            height, width, w.size(0), kh, kw, stride, stride, padding, padding, dilation, dilation, groups,
-            deformable_groups, 1 if with_bias else 0, stream))
-    return output
+    return (n, x.size(1), height, width, w.size(0), kh, kw, stride, stride, padding, padding, dilation, dilation,
+            groups, deformable_groups), (n, w.size(0), height_out, width_out)
+
+
+class ModulatedDeformConvFunction(Function):
+    """DCNv2; mirrors ModulatedDeformConvFunction (dcn/deform_conv.py:97-155): forward :99-120 (scalar
+    stride/padding/dilation, optional bias), backward :122-145."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1):
+        ctx.stride, ctx.padding, ctx.dilation = stride, padding, dilation
+        ctx.groups, ctx.deformable_groups = groups, deformable_groups
+        ctx.with_bias = bias is not None
+        if not ctx.with_bias:
+            bias = input.new_empty(1)  # fake tensor, as the reference passes (deform_conv.py:107-108)
+        if not input.is_cuda:
+            raise NotImplementedError
+        if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
+            ctx.save_for_backward(input, offset, mask, weight, bias)
+        x, off, msk, w = _f32c(input), _f32c(offset), _f32c(mask), _f32c(weight)
+        b = _f32c(bias) if ctx.with_bias else None
+        shape, out_shape = _modulated_shapes(x, off, msk, w, stride, padding, dilation, groups, deformable_groups)
+        output = x.new_empty(out_shape)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().cfen_modulated_deform_conv2d_forward(
+                _ptr(x), _ptr(w), _ptr(b) if ctx.with_bias else None, _ptr(off), _ptr(msk), _ptr(output), *shape,
+                1 if ctx.with_bias else 0, _stream(x)))
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, mask, weight, bias = ctx.saved_tensors
+        x, off, msk, w, go = _f32c(input), _f32c(offset), _f32c(mask), _f32c(weight), _f32c(grad_output)
+        shape, _ = _modulated_shapes(x, off, msk, w, ctx.stride, ctx.padding, ctx.dilation, ctx.groups,
+                                     ctx.deformable_groups)
+        grad_input, grad_offset, grad_mask = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(msk)
+        grad_weight = torch.zeros_like(w)
+        grad_bias = torch.zeros(w.size(0), dtype=torch.float32, device=x.device) if ctx.with_bias else None
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().cfen_modulated_deform_conv2d_backward(
+                _ptr(x), _ptr(w), _ptr(off), _ptr(msk), _ptr(go), _ptr(grad_input), _ptr(grad_weight),
+                _ptr(grad_bias) if ctx.with_bias else None, _ptr(grad_offset), _ptr(grad_mask), *shape,
+                1 if ctx.with_bias else 0, _stream(x)))
+        if ctx.with_bias:
+            grad_bias = grad_bias.to(bias.dtype)
+        return (grad_input.to(input.dtype), grad_offset.to(offset.dtype), grad_mask.to(mask.dtype),
+                grad_weight.to(weight.dtype), grad_bias, None, None, None, None, None)
+
+
+deform_conv = DeformConvFunction.apply                          # dcn/deform_conv.py:157
+modulated_deform_conv = ModulatedDeformConvFunction.apply       # dcn/deform_conv.py:158
 
 
 class DeformConv(nn.Module):

@@ -261,6 +261,40 @@ int32_t cfen_modulated_deform_conv2d_forward(const float* input, const float* we
                                              int32_t deformable_group, int32_t with_bias,
                                              void* stream);
 
+/* Backward entry points, one per function the reference's pybind module exports
+ * (dcn/src/deform_conv_cuda.cpp:681-695):
+ *   deform_conv_backward_input_cuda       :260-266   -> cfen_deform_conv2d_backward_input
+ *   deform_conv_backward_parameters_cuda  :373-378   -> cfen_deform_conv2d_backward_parameters
+ *   modulated_deform_conv_cuda_backward   :566-575   -> cfen_modulated_deform_conv2d_backward
+ * Same accumulation contract as those functions: grad_input, grad_weight and grad_bias are ADDED to (the caller
+ * passes zeros, as dcn/deform_conv.py:63-64,72,127-131 does); grad_offset and grad_mask are overwritten.  The
+ * reference's `columns` / `ones` scratch tensors have no counterpart: the column matrix never leaves the SM.
+ * grad_weight / grad_input sums are formed with red.global.add like the reference's col2im, so their last bits
+ * depend on scheduling.  kH*kW > 64 returns status 3. */
+int32_t cfen_deform_conv2d_backward_input(const float* input, const float* offset, const float* grad_output,
+                                          float* grad_input, float* grad_offset, const float* weight,
+                                          int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                          int32_t kH, int32_t kW, int32_t strideH, int32_t strideW,
+                                          int32_t padH, int32_t padW, int32_t dilH, int32_t dilW,
+                                          int32_t group, int32_t deformable_group, int32_t im2col_step,
+                                          void* stream);
+int32_t cfen_deform_conv2d_backward_parameters(const float* input, const float* offset,
+                                               const float* grad_output, float* grad_weight, int32_t B,
+                                               int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t kH,
+                                               int32_t kW, int32_t strideH, int32_t strideW, int32_t padH,
+                                               int32_t padW, int32_t dilH, int32_t dilW, int32_t group,
+                                               int32_t deformable_group, float scale, int32_t im2col_step,
+                                               void* stream);
+/* grad_bias may be NULL when with_bias == 0. */
+int32_t cfen_modulated_deform_conv2d_backward(const float* input, const float* weight, const float* offset,
+                                              const float* mask, const float* grad_output,
+                                              float* grad_input, float* grad_weight, float* grad_bias,
+                                              float* grad_offset, float* grad_mask, int32_t B, int32_t Cin,
+                                              int32_t H, int32_t W, int32_t Cout, int32_t kH, int32_t kW,
+                                              int32_t strideH, int32_t strideW, int32_t padH, int32_t padW,
+                                              int32_t dilH, int32_t dilW, int32_t group,
+                                              int32_t deformable_group, int32_t with_bias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

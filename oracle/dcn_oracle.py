@@ -1,4 +1,4 @@
-"""CPU ORACLE for the deformable-convolution forward ops (dcn v1 / v2).  TEST INFRASTRUCTURE ONLY.
+"""CPU ORACLE for the deformable-convolution ops (dcn v1 / v2), forward and backward.  TEST INFRASTRUCTURE ONLY.
 
 Only ``tests/`` may import this file; the shipped op (cfen_vit_dehazing_b200.dcn) never does and has
 no CPU path.
@@ -11,6 +11,13 @@ APIs, SURVEY.md section 2.1 - and refuses CPU tensors, dcn/deform_conv.py:36-37)
 * ``modulated_deformable_im2col_gpu_kernel``  dcn/src/deform_conv_cuda_kernel.cu:570-632
 * ``deformable_im2col_bilinear`` / ``dmcn_im2col_bilinear``     .cu:84-114, :467-496
 * grouped ``addmm_`` over the columns + bias  dcn/src/deform_conv_cuda.cpp:229-234, :545-563
+* backward (``deform_conv2d_backward``): the restatement above is differentiable torch code, and autograd through
+  it IS the reference's backward - d(columns)/d(input) are the bilinear corner weights of
+  ``(dmcn_)get_gradient_weight`` (.cu:117-143, :497-521), d(columns)/d(offset) the corner differences of
+  ``(dmcn_)get_coordinate_weight`` (.cu:145-188, :523-568; floor() has zero gradient, corners outside the image
+  drop out through the same validity masks), d/d(mask) the unmasked sample (.cu:748-752), and the two grouped
+  products of deform_conv_cuda.cpp:330-333, :456-461, :618-620, :655-665.  tests/test_gpu_dcn.py checks that claim
+  against the reference's own col2im / col2im_coord kernels.
 
 Pinning: the reference ships no tests or vectors for dcn.  The oracle is pinned (a) against
 ``torchvision.ops.deform_conv2d`` - an independent implementation of the same mmdetection
@@ -22,7 +29,7 @@ reference's weight x columns product, and checks both this oracle and the produc
 """
 import torch
 
-__all__ = ["deform_im2col", "deform_conv2d", "modulated_deform_conv2d", "output_size"]
+__all__ = ["deform_im2col", "deform_conv2d", "modulated_deform_conv2d", "deform_conv2d_backward", "output_size"]
 
 
 def output_size(h, w, kh, kw, stride, padding, dilation):
@@ -110,3 +117,25 @@ def modulated_deform_conv2d(x, offset, mask, weight, bias=None, stride=1, paddin
     if bias is not None:
         out = out + bias.view(1, -1, 1, 1)                        # .cpp:561-563
     return out
+
+
+def deform_conv2d_backward(x, offset, mask, weight, bias, grad_output, stride=1, padding=0, dilation=1, groups=1,
+                           deformable_groups=1):
+    """Gradients of the v1 (mask None) / v2 op w.r.t. input, offset, mask, weight, bias for a given grad_output:
+    deform_conv_backward_input_cuda + deform_conv_backward_parameters_cuda (deform_conv_cuda.cpp:260-484) /
+    modulated_deform_conv_cuda_backward (:566-679).  Returns a dict; entries for absent tensors are None."""
+    leaves = {"input": x, "offset": offset, "mask": mask, "weight": weight, "bias": bias}
+    leaves = {k: (v.detach().clone().requires_grad_(True) if v is not None else None) for k, v in leaves.items()}
+    if mask is None:
+        out = deform_conv2d(leaves["input"], leaves["offset"], leaves["weight"], stride, padding, dilation, groups,
+                            deformable_groups)
+        if bias is not None:
+            out = out + leaves["bias"].view(1, -1, 1, 1)
+    else:
+        out = modulated_deform_conv2d(leaves["input"], leaves["offset"], leaves["mask"], leaves["weight"],
+                                      leaves["bias"], stride, padding, dilation, groups, deformable_groups)
+    names = [k for k, v in leaves.items() if v is not None]
+    grads = torch.autograd.grad(out, [leaves[k] for k in names], grad_output)
+    res = {k: None for k in leaves}
+    res.update(dict(zip(names, grads)))
+    return res

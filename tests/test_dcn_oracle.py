@@ -72,3 +72,24 @@ def test_integer_offsets_shift_samples():
     shifted[:, :, :-1, 1:] = x[:, :, 1:, :-1]
     ref = F.conv2d(shifted, wt, padding=1)
     assert (got - ref)[:, :, 2:-2, 2:-2].abs().max().item() <= 1e-12
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("modulated", [False, True])
+def test_backward_matches_torchvision(case, modulated):
+    """oracle.deform_conv2d_backward (autograd through the restatement) against torchvision's own backward kernels."""
+    b, cin, h, w, cout, k, s, p, d, g, dg = case
+    x, off, mask, wt, bias = _inputs(case, seed=7, scale=3.0)
+    if not modulated:
+        mask = None
+    gen = torch.Generator().manual_seed(11)
+    ho, wo = dcn.output_size(h, w, k, k, (s, s), (p, p), (d, d))
+    gout = torch.randn(b, cout, ho, wo, generator=gen, dtype=torch.float64)
+    got = dcn.deform_conv2d_backward(x, off, mask, wt, bias, gout, s, p, d, g, dg)
+    leaves = [t.clone().requires_grad_(True) for t in (x, off, wt, bias)] + ([mask.clone().requires_grad_(True)] if modulated else [])
+    out = tv_ops.deform_conv2d(leaves[0], leaves[1], leaves[2], leaves[3], stride=s, padding=p, dilation=d,
+                               mask=leaves[4] if modulated else None)
+    ref = torch.autograd.grad(out, leaves, gout)
+    names = ["input", "offset", "weight", "bias"] + (["mask"] if modulated else [])
+    for name, r in zip(names, ref):
+        assert (got[name] - r).abs().max().item() <= 1e-9 * max(1.0, r.abs().max().item()), name

@@ -1,6 +1,6 @@
 """Micro-benchmarks of individual kernels through the C ABI (CUDA events, L2 flushed between reps).
 
-    python tools/bench_kernels.py mlp|gemm|attn|gemm16|mlp16|attn16|dcn [--json out.json]
+    python tools/bench_kernels.py mlp|gemm|attn|gemm16|mlp16|attn16|dcn|dcn_bwd [--json out.json]
 """
 import ctypes
 import json
@@ -200,10 +200,76 @@ def dcn():
     return out
 
 
+def dcn_bwd():
+    """Deformable conv v2 / v1 backward (row F4): all five gradients of one call, zero-fill of the accumulated outputs
+    included, against the reference's own CUDA path on this GPU - per image W^T x grad_output (cuBLAS via torch.matmul),
+    its col2im_coord and col2im kernels, its im2col kernel again and grad_output x columns^T (cuBLAS)
+    (deform_conv_cuda.cpp:611-667), kernels compiled unmodified into oracle/_ref/libdcn_ref.so."""
+    out = []
+    i32 = ctypes.c_int
+    for B, C, H, W, Co, k, dg, mod in [(8, 64, 128, 128, 64, 3, 8, True), (8, 64, 128, 128, 64, 3, 8, False),
+                                        (4, 64, 256, 256, 64, 3, 8, True), (16, 128, 64, 64, 128, 3, 4, True)]:
+        x = torch.randn(B, C, H, W, device="cuda")
+        off = torch.randn(B, dg * 2 * k * k, H, W, device="cuda") * 2.0
+        mask = torch.sigmoid(torch.randn(B, dg * k * k, H, W, device="cuda"))
+        wt = torch.randn(Co, C, k, k, device="cuda") * 0.05
+        go = torch.randn(B, Co, H, W, device="cuda")
+        gin, goff, gmask, gw = torch.empty_like(x), torch.empty_like(off), torch.empty_like(mask), torch.empty_like(wt)
+        gb = torch.empty(Co, device="cuda")
+        shape = (B, C, H, W, Co, k, k, 1, 1, 1, 1, 1, 1, 1, dg)
+
+        def fn():
+            gin.zero_(); gw.zero_()
+            if mod:
+                gb.zero_()
+                _native.check(L.cfen_modulated_deform_conv2d_backward(P(x), P(wt), P(off), P(mask), P(go), P(gin), P(gw), P(gb),
+                                                                      P(goff), P(gmask), *shape, 1, ST()))
+            else:
+                _native.check(L.cfen_deform_conv2d_backward_input(P(x), P(off), P(go), P(gin), P(goff), P(wt), *shape, B, ST()))
+                _native.check(L.cfen_deform_conv2d_backward_parameters(P(x), P(off), P(go), P(gw), *shape,
+                                                                       ctypes.c_float(1.0), B, ST()))
+        us = timeit(fn, reps=6)
+        ref_us = None
+        ref_so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libdcn_ref.so")
+        if os.path.exists(ref_so):
+            R = ctypes.CDLL(ref_so)
+            col = torch.empty(C * k * k, H * W, device="cuda")
+            wm = wt.view(Co, -1)
+            geo = (i32(k), i32(k), i32(1), i32(1), i32(1), i32(1), i32(1), i32(1))
+
+            def ref():
+                gin.zero_(); gw.zero_(); gb.zero_()
+                gwm = gw.view(Co, -1)
+                for bi in range(B):
+                    gob = go[bi].view(Co, -1)
+                    torch.matmul(wm.t(), gob, out=col)
+                    if mod:
+                        R.dcn_ref_modulated_deformable_col2im_coord(P(col), P(x[bi]), P(off[bi]), P(mask[bi]), i32(1), i32(C), i32(H),
+                                                                    i32(W), i32(H), i32(W), *geo, i32(dg), P(goff[bi]), P(gmask[bi]))
+                        R.dcn_ref_modulated_deformable_col2im(P(col), P(off[bi]), P(mask[bi]), i32(1), i32(C), i32(H), i32(W), i32(H),
+                                                              i32(W), *geo, i32(dg), P(gin[bi]))
+                        R.dcn_ref_modulated_deformable_im2col(P(x[bi]), P(off[bi]), P(mask[bi]), i32(1), i32(C), i32(H), i32(W),
+                                                              i32(H), i32(W), *geo, i32(dg), P(col))
+                        gb.add_(gob.sum(1))
+                    else:
+                        R.dcn_ref_deformable_col2im_coord(P(col), P(x[bi]), P(off[bi]), i32(C), i32(H), i32(W), *geo, i32(1), i32(dg),
+                                                          P(goff[bi]))
+                        R.dcn_ref_deformable_col2im(P(col), P(off[bi]), i32(C), i32(H), i32(W), *geo, i32(1), i32(dg), P(gin[bi]))
+                        R.dcn_ref_deformable_im2col(P(x[bi]), P(off[bi]), i32(C), i32(H), i32(W), *geo, i32(1), i32(dg), P(col))
+                    gwm.addmm_(gob, col.t())
+            ref_us = timeit(ref, reps=3)
+        out.append(dict(kernel="deform_conv_bwd_data_kernel+deform_conv_bwd_weight_kernel", v2=mod, B=B, C=C, H=H, W=W, Cout=Co,
+                        k=k, dg=dg, us=us, gather_gsamples_per_s=2.0 * B * H * W * C * k * k / us / 1e3,
+                        columns_gb_saved=3 * 2 * 4.0 * B * H * W * C * k * k / 1e9,
+                        reference_cuda_path_us=ref_us, speedup_vs_reference_cuda_path=(ref_us / us if ref_us else None)))
+        print(out[-1])
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "mlp"
     res = []
     for w in which.split(","):
-        res += {"mlp": mlp, "gemm": gemm, "attn": attn, "gemm16": gemm16, "mlp16": mlp16, "attn16": attn16, "dcn": dcn}[w]()
+        res += {"mlp": mlp, "gemm": gemm, "attn": attn, "gemm16": gemm16, "mlp16": mlp16, "attn16": attn16, "dcn": dcn, "dcn_bwd": dcn_bwd}[w]()
     if "--json" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
