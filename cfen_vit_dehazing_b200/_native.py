@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
 
 IO_U8, ONLY_FAKE_A = 1, 2     # cfen_forward_ex io_flags (include/cfen_b200.h)
 VARIANT_CFS = 1                # cfen_config.flags: iid_hlgvit_crs_gd4_cfs graph
+VARIANT_CRS = 2                # cfen_config.flags: iid_hlgvit_crs_gd4 graph (cfs with concat-skip convs)
 
 
 class cfen_config(ctypes.Structure):
@@ -109,10 +110,11 @@ def lib():
 def is_dead_key(name):
     """state_dict entries the forward never reads: the TransformerDecoder stacks and query_embed of
     every ViT (constructed at v3.py:1116-1123, their use commented out at :1158-1168) and sub_mean / add_mean
-    (v3.py:120-121).  208.6 M of the 479.9 M elements at hidden_dim_ratio=4; they round-trip through state_dict but
-    are never copied to the plan."""
+    (v3.py:120-121); for iid_hlgvit_crs_gd4 also the never-called SpatialPyramid ``sp`` (crs_gd4.py:364, 985).
+    208.6 M of the 479.9 M elements at hidden_dim_ratio=4; they round-trip through state_dict but are never copied to
+    the plan."""
     return (".decoder." in name or name.endswith(".query_embed.weight") or name.startswith("sub_mean.")
-            or name.startswith("add_mean."))
+            or name.startswith("add_mean.") or name.startswith("sp."))
 
 
 def check(status):

@@ -128,7 +128,9 @@ static cudaError_t set_kernel_attributes();
   X(K_C3_24, Conv3x3_24, 24, "conv3x3_24_24", 24, 216, 24.0, 0)                                  \
   X(K_C3S_24, Conv3x3_24S, 24, "conv3x3_24_24_sum2", 24, 216, 48.0, 0)                           \
   X(K_T3_24, ConvTail7_3_24, 24, "tail7x7_24_3", 3, 1176, 24.0, 0)                               \
-  X(K_T1_24, ConvTail7_1_24, 24, "tail7x7_24_1", 1, 1176, 24.0, 0)
+  X(K_T1_24, ConvTail7_1_24, 24, "tail7x7_24_1", 1, 1176, 24.0, 0)                                \
+  X(K_SK3C, ConvSk144_48, 144, "skip3_144_48", 48, 144, 144.0, 0)                                \
+  X(K_SK2C, ConvSk72_24, 72, "skip3_72_24", 24, 72, 72.0, 0)
 
 enum ConvKind {
 #define X(K, S, CS, NAME, COUT, KLEN, CINB, G1) K,
@@ -374,7 +376,8 @@ struct Lane {
 struct cfen_plan {
   cfen_config cfg;
   int H, W, nbmax, hr, win;
-  int variant = 0;     // 0: iid_hlgvit_crs_gd4_cfs_v3; 1: iid_hlgvit_crs_gd4_cfs (no half-resolution stem)
+  int variant = 0;     // 0: iid_hlgvit_crs_gd4_cfs_v3; 1: iid_hlgvit_crs_gd4_cfs (no half-resolution stem);
+                       // 2: iid_hlgvit_crs_gd4 (the cfs graph with concat-skip 1x1 convs instead of the CFS gates)
   int H1 = 0, Cf = 12; // level-1 map edge; channels of the input-resolution maps (head / tails)
   int Hl[4], Cl[4];  // level 1..3 map size / channels
   std::unordered_map<std::string, std::pair<const float*, int64_t>> reg;
@@ -525,7 +528,7 @@ static void plan_declare_convs(cfen_plan* p) {
     c.ankey = an;
     p->conv[name] = c;
   };
-  const bool cfs = p->variant == 1;
+  const bool cfs = p->variant >= 1, crs = p->variant == 2;
   add("head.0.0", cfs ? K_HEAD5_24 : K_HEAD5, "head.0.0", true, "");
   add("head.0.1.body.0", cfs ? K_C3_24 : K_C3, "head.0.1.body.0", true, "");
   add("head.0.1.body.2", cfs ? K_C3_24 : K_C3, "head.0.1.body.2", true, "");
@@ -547,6 +550,10 @@ static void plan_declare_convs(cfen_plan* p) {
     std::string b(br);
     add("sk_conv_d03" + b, K_SK3, "sk_conv_d03" + b + ".0", true, "sk_conv_d03" + b + ".1");
     add("sk_conv_d02" + b, K_SK2, "sk_conv_d02" + b + ".0", true, "sk_conv_d02" + b + ".1");
+  }
+  if (crs) {   // networks_iid_hlgvit_crs_gd4.py:327-330
+    add("sk_conv_d03d", K_SK3C, "sk_conv_d03d.0", true, "sk_conv_d03d.1");
+    add("sk_conv_d02d", K_SK2C, "sk_conv_d02d.0", true, "sk_conv_d02d.1");
   }
   if (cfs) {   // tail_color serves R and D (cfs.py:334-345, 669, 977), tail_gray S (:346-358, 823)
     add("tail_color.c1", K_C3S_24, "tail_color.0.1", true, "tail_color.0.2");
@@ -573,8 +580,11 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (cfg->hidden_dim_ratio != 2 && cfg->hidden_dim_ratio != 4)
     return fail(3, "unsupported hidden_dim_ratio=%d (2 or 4)", cfg->hidden_dim_ratio);
   if (cfg->num_heads != 4 || cfg->patch_dim != 2) return fail(3, "num_heads/patch_dim must be 4/2");
-  if (cfg->flags & ~CFEN_VARIANT_CFS) return fail(3, "unknown cfen_config.flags bits 0x%x", cfg->flags);
-  const bool cfs = (cfg->flags & CFEN_VARIANT_CFS) != 0;
+  if (cfg->flags & ~(CFEN_VARIANT_CFS | CFEN_VARIANT_CRS)) return fail(3, "unknown cfen_config.flags bits 0x%x", cfg->flags);
+  if ((cfg->flags & CFEN_VARIANT_CFS) && (cfg->flags & CFEN_VARIANT_CRS))
+    return fail(1, "cfen_config.flags: CFEN_VARIANT_CFS and CFEN_VARIANT_CRS are exclusive");
+  const bool crs = (cfg->flags & CFEN_VARIANT_CRS) != 0;
+  const bool cfs = crs || (cfg->flags & CFEN_VARIANT_CFS) != 0;   // crs shares the cfs graph and geometry
   const int edge = cfs ? 64 : 128;   // level-1 map edge must be a multiple of 64 (8 windows of >= 8 px; 16x pooling)
   if (cfg->height != cfg->width || cfg->height % edge != 0 || cfg->height < edge)
     return fail(3, "input must be square with edge a multiple of %d (got %dx%d)", edge, cfg->height, cfg->width);
@@ -596,7 +606,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->cfg = *cfg;
   p->H = cfg->height; p->W = cfg->width; p->nbmax = cfg->max_batch; p->hr = cfg->hidden_dim_ratio;
   p->win = cfg->patch_size;
-  p->variant = cfs ? 1 : 0;
+  p->variant = crs ? 2 : (cfs ? 1 : 0);
   p->H1 = cfs ? p->H : p->H / 2;
   p->Cf = cfs ? 24 : 12;
   if (const char* gp = getenv("CFEN_GEMM_PATH")) {
@@ -866,7 +876,7 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
   CU(cudaGetLastError());
   static const char* kMlp[8] = {"fc_avg_cf1.0", "fc_avg_cf1.2", "fc_avg_cf2.0", "fc_avg_cf2.2",
                                 "fc_max_cf1.0", "fc_max_cf1.2", "fc_max_cf2.0", "fc_max_cf2.2"};
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 2 && p->variant != 2; ++k) {   // (iid_hlgvit_crs_gd4 has no CFS gates)
     const int C = k == 0 ? 48 : 24, R = C / 4;
     const std::string pre = k == 0 ? "cfsm2g_d03d.0." : "cfsm2g_d02d.0.";
     for (int j = 0; j < 8; ++j) {
@@ -1198,13 +1208,13 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
 
 // One conv-family layer; handles ActNorm calibration (two-pass) when the plan is calibrating.
 static int run_conv(Run& r, const std::string& name, const float* in0, const float* in1, const float* res,
-                    float* out, int H, int W, int flags, float* stats = nullptr) {
+                    float* out, int H, int W, int flags, float* stats = nullptr, const float* in2 = nullptr) {
   cfen_plan* p = r.p;
   auto it = p->conv.find(name);
   if (it == p->conv.end()) return fail(7, "internal: unknown conv layer %s", name.c_str());
   ConvLayer& c = it->second;
   ConvArgs a;
-  a.in0 = in0; a.in1 = in1; a.res = res; a.wpack = c.wpack; a.out = out;
+  a.in0 = in0; a.in1 = in1; a.in2 = in2; a.res = res; a.wpack = c.wpack; a.out = out;
   a.B = r.nb; a.H = H; a.W = W; a.win = p->win;
   const bool is_lg = c.kind == K_LG1 || c.kind == K_LG2 || c.kind == K_LG3;
   // every stage map is fp16 (maps16 level 2): the map operands of every conv-family layer; loaders / epilogues that
@@ -1481,7 +1491,10 @@ static int forward_chunk_cfs(cfen_plan* p, int nb, const float* in, float* xr, f
       RET(run_conv(r, "sk_conv_d03" + b, S("u3" + b), S("e2"), nullptr, S("d2in" + b), H2, H2, CF_RELU));
     } else {
       if (multi) { CU(cudaStreamWaitEvent(r.st, up_done[0], 0)); CU(cudaStreamWaitEvent(r.st, up_done[1], 0)); }
-      RET(run_cfsm(r, 0, S("u3d"), S("u3r"), S("u3s"), S("d2ind"), H2, H2));
+      if (p->variant == 2)   // sk_conv_d03d(cat(d, r, s)) (networks_iid_hlgvit_crs_gd4.py:854)
+        RET(run_conv(r, "sk_conv_d03d", S("u3d"), S("u3r"), nullptr, S("d2ind"), H2, H2, CF_RELU, nullptr, S("u3s")));
+      else
+        RET(run_cfsm(r, 0, S("u3d"), S("u3r"), S("u3s"), S("d2ind"), H2, H2));
     }
     RET(run_block(r, 3 + bi * 3 + 1, S("d2in" + b), S("d2" + b)));
     RET(run_conv(r, "us_conv_d02" + b, S("d2" + b), nullptr, nullptr, S("u2" + b), H2, H2, CF_RELU));
@@ -1495,7 +1508,10 @@ static int forward_chunk_cfs(cfen_plan* p, int nb, const float* in, float* xr, f
       RET(run_conv(r, "sk_conv_d02" + b, S("u2" + b), S("e1"), nullptr, S("d1in" + b), H1, H1, CF_RELU));
     } else {
       if (multi) { CU(cudaStreamWaitEvent(r.st, up_done[0], 0)); CU(cudaStreamWaitEvent(r.st, up_done[1], 0)); }
-      RET(run_cfsm(r, 1, S("u2d"), S("u2r"), S("u2s"), S("d1ind"), H1, H1));
+      if (p->variant == 2)   // sk_conv_d02d(cat(d, r, s)) (networks_iid_hlgvit_crs_gd4.py:889)
+        RET(run_conv(r, "sk_conv_d02d", S("u2d"), S("u2r"), nullptr, S("d1ind"), H1, H1, CF_RELU, nullptr, S("u2s")));
+      else
+        RET(run_cfsm(r, 1, S("u2d"), S("u2r"), S("u2s"), S("d1ind"), H1, H1));
     }
     RET(run_block(r, 3 + bi * 3 + 2, S("d1in" + b), S("d1" + b)));
     float* f1 = r.ln->f1;

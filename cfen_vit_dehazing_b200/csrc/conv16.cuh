@@ -282,6 +282,10 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
           const int c = c4 * 4;
           v = c < C1 ? ld_map4(a.in0, (img * C1 + (pidx * C1 + c)) >> 2, in16)
                      : ld_map4(a.in1, (img * C1 + (pidx * C1 + (c - C1))) >> 2, in16);
+        } else if (S::LOADER == LD_CAT3) {
+          constexpr int C1 = S::CIN / 3;
+          const int c = c4 * 4, src = c / C1;
+          v = ld_map4(src == 0 ? a.in0 : (src == 1 ? a.in1 : a.in2), (img * C1 + (pidx * C1 + (c - src * C1))) >> 2, in16);
         } else if (a.flags & CF_IN_U8) {   // uint8 HWC image: ToTensor + Normalize(0.5, 0.5) on load
           const uint8_t* p = reinterpret_cast<const uint8_t*>(a.in0) + (img + pidx) * 3;
           v = make_float4(((float)p[0] / 255.f - 0.5f) / 0.5f, ((float)p[1] / 255.f - 0.5f) / 0.5f,
@@ -295,16 +299,18 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
       return v;
     };
     bool async_in = false;
-    if constexpr (S::LOADER == LD_NHWC || S::LOADER == LD_CAT2) async_in = (a.flags & CF_IN16) != 0;
+    if constexpr (S::LOADER == LD_NHWC || S::LOADER == LD_CAT2 || S::LOADER == LD_CAT3) async_in = (a.flags & CF_IN16) != 0;
     if (async_in) {
       // fp16 map: the halo tile is copied global -> shared asynchronously (cp.async, zero-fill outside the image),
       // no registers and no conversion; the copy group is waited for together with the first weight chunk
-      // (LD_CAT2: channel halves [0, CIN/2) / [CIN/2, CIN) come from the two source maps)
-      constexpr int CSRC = S::LOADER == LD_CAT2 ? S::CIN / 2 : S::CIN;   // channels per source map
+      // (LD_CAT2 / LD_CAT3: channel halves / thirds come from the two / three source maps)
+      constexpr int NSRC = S::LOADER == LD_CAT3 ? 3 : (S::LOADER == LD_CAT2 ? 2 : 1);
+      constexpr int CSRC = S::CIN / NSRC;                  // channels per source map
       constexpr int CH = CSRC % 8 == 0 ? 8 : 4;            // halves per copy
       constexpr int CPP = CSRC / CH;
       const __half* in16 = reinterpret_cast<const __half*>(a.in0) + img * CSRC;
-      const __half* in16b = S::LOADER == LD_CAT2 ? reinterpret_cast<const __half*>(a.in1) + img * CSRC : nullptr;
+      const __half* in16b = NSRC >= 2 ? reinterpret_cast<const __half*>(a.in1) + img * CSRC : nullptr;
+      const __half* in16c = NSRC >= 3 ? reinterpret_cast<const __half*>(a.in2) + img * CSRC : nullptr;
       for (int pix = tid; pix < C::IN_H * C::IN_W; pix += S::THREADS) {   // one pixel (all its chunks) per item
         const int iy = pix / C::IN_W, ix = pix - iy * C::IN_W;
         int gy = oy0 + iy, gx = ox0 + ix;
@@ -322,11 +328,18 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
           if (CH == 8) cp_async16(dst + cc * CH, in16 + poff + (inside ? cc * CH : 0), inside);
           else cp_async8(dst + cc * CH, in16 + poff + (inside ? cc * CH : 0), inside);
         }
-        if constexpr (S::LOADER == LD_CAT2) {
+        if constexpr (NSRC >= 2) {
 #pragma unroll
           for (int cc = 0; cc < CPP; ++cc) {
             if (CH == 8) cp_async16(dst + CSRC + cc * CH, in16b + poff + (inside ? cc * CH : 0), inside);
             else cp_async8(dst + CSRC + cc * CH, in16b + poff + (inside ? cc * CH : 0), inside);
+          }
+        }
+        if constexpr (NSRC >= 3) {
+#pragma unroll
+          for (int cc = 0; cc < CPP; ++cc) {
+            if (CH == 8) cp_async16(dst + 2 * CSRC + cc * CH, in16c + poff + (inside ? cc * CH : 0), inside);
+            else cp_async8(dst + 2 * CSRC + cc * CH, in16c + poff + (inside ? cc * CH : 0), inside);
           }
         }
       }

@@ -18,7 +18,7 @@
 
 namespace cfen {
 
-enum ConvLoader { LD_NHWC = 0, LD_NCHW3 = 1, LD_SUM2 = 2, LD_CAT2 = 3, LD_LG = 4 };
+enum ConvLoader { LD_NHWC = 0, LD_NCHW3 = 1, LD_SUM2 = 2, LD_CAT2 = 3, LD_LG = 4, LD_CAT3 = 5 };
 enum ConvFlags {
   CF_RELU = 1, CF_TANH = 2, CF_RES = 4, CF_OUT_NCHW = 8,
   // fp16 map storage (conv16 generation only): in0 / out / res are __half NHWC maps
@@ -44,6 +44,7 @@ struct ConvArgs {
   int B, H, W;         // tile domain: output H,W (normal) or INPUT H,W (transposed, output is 2H x 2W)
   int flags;
   int win;             // LG loader: window edge in pixels
+  const float* in2 = nullptr;  // CAT3 loader: third source map (channels [2*CIN/3, CIN))
 };
 
 template <int CIN_, int COUT_, int KS_, int STRIDE_, int PAD_, bool REFLECT_, bool TRANSPOSED_, int LOADER_>
@@ -416,5 +417,9 @@ using Conv3x3_24 = ConvSpec<24, 24, 3, 1, 1, false, false, LD_NHWC>;
 using Conv3x3_24S = ConvSpec<24, 24, 3, 1, 1, false, false, LD_SUM2>;
 using ConvTail7_3_24 = ConvSpec<24, 3, 7, 1, 3, true, false, LD_NHWC>;
 using ConvTail7_1_24 = ConvSpec<24, 1, 7, 1, 3, true, false, LD_NHWC>;
+// iid_hlgvit_crs_gd4 (networks_iid_hlgvit_crs_gd4.py:327-330, 854, 889): the dehazing branch's skip is a 1x1 conv over
+// cat(d, r, s) up-sampled maps instead of the CFS gate (conv16 generation only)
+using ConvSk144_48 = ConvSpec<144, 48, 1, 1, 0, false, false, LD_CAT3>;
+using ConvSk72_24 = ConvSpec<72, 24, 1, 1, 0, false, false, LD_CAT3>;
 
 }  // namespace cfen

@@ -227,6 +227,24 @@ class CFSM2G(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
 
+class SpatialPyramid(nn.Module):
+    """Parameters of the refinement pyramid that ``iid_hlgvit_crs_gd4`` constructs (networks_iid_hlgvit_crs_gd4.py:364,
+    1441-1465) but never calls (its only use is commented out, :985): kept so that the ``state_dict`` keys and the RNG
+    stream of ``init_weights`` match the reference; the forward does not read them (_native.is_dead_key)."""
+
+    def __init__(self):
+        super().__init__()
+        self.relu = nn.LeakyReLU(0.2, inplace=True)
+        self.tanh = nn.Tanh()
+        self.refine1 = nn.Conv2d(10, 32, kernel_size=3, stride=1, padding=1)
+        self.refine2 = nn.Conv2d(32, 32, kernel_size=3, stride=1, padding=1)
+        for name in ("conv1010", "conv1020", "conv1030", "conv1040", "conv1050"):
+            setattr(self, name, nn.Conv2d(32, 16, kernel_size=1, stride=1, padding=0))
+        self.refine3 = nn.Sequential(nn.Conv2d(32 + 5 * 16, 3, kernel_size=3, stride=1, padding=1), nn.Tanh())
+        self.batch20 = ActNorm2d(20)
+        self.batch1 = ActNorm2d(1)
+
+
 class _NoParams(nn.Module):
     """Stand-in for the reference's Crop2x2/Join2x2 (v3.py:1025-1056): window partition and
     merge are address arithmetic inside the CUDA kernels."""
@@ -247,13 +265,14 @@ def _level_of(stage):
 
 class dec_ipt(nn.Module):
     # "v3": iid_hlgvit_crs_gd4_cfs_v3 (this file's reference); "cfs": the sibling iid_hlgvit_crs_gd4_cfs without the
-    # half-resolution stem (networks_iid_hlgvit_crs_gd4_cfs.py subclasses and flips this)
+    # half-resolution stem (networks_iid_hlgvit_crs_gd4_cfs.py subclasses and flips this); "crs": iid_hlgvit_crs_gd4 =
+    # the cfs graph with concat-skip 1x1 convs in place of the two CFS gates (networks_iid_hlgvit_crs_gd4.py)
     VARIANT = "v3"
 
     def __init__(self, opt, conv=common.default_conv):
         super().__init__()
         self._check_supported(opt)
-        cfs = self.VARIANT == "cfs"
+        cfs = self.VARIANT in ("cfs", "crs")
         self.scale_idx = 0
         self.opt = opt
         nf = opt.n_feats
@@ -329,8 +348,14 @@ class dec_ipt(nn.Module):
                 self.add_module("sk_conv_d0%d%s" % (lvl, branch), nn.Sequential(
                     nn.Conv2d(int(cin), int(cout), kernel_size=1, stride=1, padding=0),
                     ActNorm2d(int(cout)), nn.ReLU(True)))
-        self.cfsm2g_d03d = nn.Sequential(CFSM2G(int(2 * nf), int(2 * nf / 4)))
-        self.cfsm2g_d02d = nn.Sequential(CFSM2G(int(nf), int(nf / 4)))
+        if self.VARIANT == "crs":   # networks_iid_hlgvit_crs_gd4.py:327-330
+            self.sk_conv_d03d = nn.Sequential(nn.Conv2d(int(6 * nf), int(2 * nf), kernel_size=1, stride=1, padding=0),
+                                              ActNorm2d(int(2 * nf)), nn.ReLU(True))
+            self.sk_conv_d02d = nn.Sequential(nn.Conv2d(int(3 * nf), nf, kernel_size=1, stride=1, padding=0),
+                                              ActNorm2d(nf), nn.ReLU(True))
+        else:
+            self.cfsm2g_d03d = nn.Sequential(CFSM2G(int(2 * nf), int(2 * nf / 4)))
+            self.cfsm2g_d02d = nn.Sequential(CFSM2G(int(nf), int(nf / 4)))
 
         # ---- tails (v3.py:348-383)
         def tail(out_ch, with_actnorm):
@@ -352,6 +377,8 @@ class dec_ipt(nn.Module):
 
         self.crop2x2 = _NoParams()
         self.join2x2 = _NoParams()
+        if self.VARIANT == "crs":
+            self.sp = SpatialPyramid()   # networks_iid_hlgvit_crs_gd4.py:364 (never called)
 
         # ---- native state (not part of state_dict)
         self._plans = {}
@@ -405,7 +432,7 @@ class dec_ipt(nn.Module):
 
     def _plan_for(self, device, height, width, batch, exact_batch=False):
         opt = self.opt
-        cfs = self.VARIANT == "cfs"
+        cfs = self.VARIANT in ("cfs", "crs")
         baked = int(opt.loadSize) * (1 if cfs else 2)
         if height != width or height != baked:
             raise RuntimeError(
@@ -423,7 +450,7 @@ class dec_ipt(nn.Module):
                                 n_feats=opt.n_feats, hidden_dim_ratio=opt.hidden_dim_ratio,
                                 num_heads=opt.num_heads, patch_dim=opt.patch_dim,
                                 patch_size=int(opt.patch_size), load_size=int(opt.loadSize),
-                                max_batch=need, flags=_native.VARIANT_CFS if cfs else 0)
+                                max_batch=need, flags={"v3": 0, "cfs": _native.VARIANT_CFS, "crs": _native.VARIANT_CRS}[self.VARIANT])
             self._plans[key] = plan
         version = (self._weights_version, self._tensors_version())
         if plan.weights_version != version:
@@ -449,7 +476,9 @@ class dec_ipt(nn.Module):
         return plan
 
     def _actnorm_modules(self):
-        return [m for m in self.modules() if isinstance(m, ActNorm2d)]
+        """The ActNorm layers the forward goes through (not those of the never-called ``sp`` of iid_hlgvit_crs_gd4,
+        which stay un-initialised in the reference too)."""
+        return [m for n, m in self.named_modules() if isinstance(m, ActNorm2d) and not _native.is_dead_key(n + ".weight")]
 
     def forward(self, input):
         if not isinstance(input, torch.Tensor) or input.dim() != 4 or input.size(1) != 3:

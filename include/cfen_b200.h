@@ -57,6 +57,10 @@ typedef struct cfen_config {
  * height == width, height % 64 == 0.  State_dict keys: tail_color / tail_gray instead of tail_R / tail_D / tail_S, no
  * ds_conv_e01 / us_conv_d01*. */
 #define CFEN_VARIANT_CFS 1
+/* iid_hlgvit_crs_gd4 (models/networks_iid_hlgvit_crs_gd4.py, --model_G iid_hlgvit_crs_gd4, model_iid_dehazing.py:50-53):
+ * the CFS graph and geometry, with the dehazing branch's two CFS gates replaced by 1x1 convs over cat(d, r, s)
+ * (:327-330, 854, 889).  Exclusive with CFEN_VARIANT_CFS. */
+#define CFEN_VARIANT_CRS 2
 
 int32_t     cfen_abi_version(void);
 const char* cfen_last_error(void);

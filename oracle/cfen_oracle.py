@@ -178,8 +178,8 @@ def _up(sd, name, x, norm):
     return F.relu(y)
 
 
-def _skip(sd, name, a, b):
-    return F.relu(actnorm(sd, name + ".1", _conv(sd, name + ".0", torch.cat((a, b), 1))))
+def _skip(sd, name, *maps):
+    return F.relu(actnorm(sd, name + ".1", _conv(sd, name + ".0", torch.cat(maps, 1))))
 
 
 def _tail(sd, name, x, with_actnorm):
@@ -195,12 +195,18 @@ def is_cfs(sd):
     return "tail_color.0.1.weight" in sd
 
 
+def is_crs(sd):
+    """iid_hlgvit_crs_gd4 (models/networks_iid_hlgvit_crs_gd4.py): the cfs graph whose dehazing-branch skips are
+    sk_conv_d03d / sk_conv_d02d over cat(d, r, s) (:327-330, 854, 889) instead of the CFS gates."""
+    return "sk_conv_d03d.0.weight" in sd
+
+
 def forward_cfs(sd, x, num_heads=4, taps=None):
     """[xr, xs, xd] = dec_ipt.forward(x) of models/networks_iid_hlgvit_crs_gd4_cfs.py:366-985 (== ..._cfs_v2.py): the
     v3 graph without the half-resolution stem - xf = head(x) has 24 channels at the input size (:368-369), the level-1
     windows are size/8 px, there is no ds_conv_e01 / us_conv_d01, and the tails (tail_color for R and D, tail_gray for
     S, :334-358) take block_out + xf (:669, 823, 977).  tail_color's ActNorm initialises on its FIRST use, the
-    reflectance branch."""
+    reflectance branch.  Also serves iid_hlgvit_crs_gd4 (``is_crs``), which differs in the two dehazing-branch skips only."""
     x = x.float()
     size = x.shape[-1]
     window = size // 8
@@ -233,9 +239,14 @@ def forward_cfs(sd, x, num_heads=4, taps=None):
                 taps.update({"u3" + br: u3, "u2" + br: u2})
         d3 = blk("decoder_03d", e3)
         u3 = _up(sd, "us_conv_d03d", d3, "in")
-        d2 = blk("decoder_02d", cfsm(sd, "cfsm2g_d03d.0", u3, ups["r"][0], ups["s"][0]))
+        crs = is_crs(sd)
+        d2in = (_skip(sd, "sk_conv_d03d", u3, ups["r"][0], ups["s"][0]) if crs
+                else cfsm(sd, "cfsm2g_d03d.0", u3, ups["r"][0], ups["s"][0]))
+        d2 = blk("decoder_02d", d2in)
         u2 = _up(sd, "us_conv_d02d", d2, "an")
-        d1 = blk("decoder_01d", cfsm(sd, "cfsm2g_d02d.0", u2, ups["r"][1], ups["s"][1]))
+        d1in = (_skip(sd, "sk_conv_d02d", u2, ups["r"][1], ups["s"][1]) if crs
+                else cfsm(sd, "cfsm2g_d02d.0", u2, ups["r"][1], ups["s"][1]))
+        d1 = blk("decoder_01d", d1in)
         outs["d"] = _tail(sd, "tail_color", d1 + xf, True)
         if taps is not None:
             taps.update(u3d=u3, u2d=u2)
@@ -289,9 +300,14 @@ def forward(sd, x, num_heads=4, taps=None):
         # dehazed decoder with CFS fusion (v3.py:865-1009)
         d3 = blk("decoder_03d", e3)
         u3 = _up(sd, "us_conv_d03d", d3, "in")
-        d2 = blk("decoder_02d", cfsm(sd, "cfsm2g_d03d.0", u3, ups["r"][0], ups["s"][0]))
+        crs = is_crs(sd)
+        d2in = (_skip(sd, "sk_conv_d03d", u3, ups["r"][0], ups["s"][0]) if crs
+                else cfsm(sd, "cfsm2g_d03d.0", u3, ups["r"][0], ups["s"][0]))
+        d2 = blk("decoder_02d", d2in)
         u2 = _up(sd, "us_conv_d02d", d2, "an")
-        d1 = blk("decoder_01d", cfsm(sd, "cfsm2g_d02d.0", u2, ups["r"][1], ups["s"][1]))
+        d1in = (_skip(sd, "sk_conv_d02d", u2, ups["r"][1], ups["s"][1]) if crs
+                else cfsm(sd, "cfsm2g_d02d.0", u2, ups["r"][1], ups["s"][1]))
+        d1 = blk("decoder_01d", d1in)
         u1 = _up(sd, "us_conv_d01d", d1 + xf, "an")
         outs["d"] = _tail(sd, "tail_D", u1, True)
         if taps is not None:

@@ -33,9 +33,12 @@ def seeded_state(hr, size, seed=1):
 
 
 @functools.lru_cache(maxsize=2)
-def seeded_state_cfs(hr, size, seed=1):
-    """Same for the sibling generator iid_hlgvit_crs_gd4_cfs (input edge = loadSize = ``size``)."""
-    from cfen_vit_dehazing_b200 import common, networks_iid_hlgvit_crs_gd4_cfs as cfs
+def seeded_state_cfs(hr, size, seed=1, family="cfs"):
+    """Same for the sibling generators iid_hlgvit_crs_gd4_cfs (``family="cfs"``) and iid_hlgvit_crs_gd4 (``"crs"``);
+    input edge = loadSize = ``size``."""
+    import importlib
+    from cfen_vit_dehazing_b200 import common
+    cfs = importlib.import_module("cfen_vit_dehazing_b200.networks_iid_hlgvit_crs_gd4" + ("_cfs" if family == "cfs" else ""))
     opt = orc.cfs_opt(hr, size)
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):

@@ -39,6 +39,11 @@ CFS_CONFIGS = {
     "cfs_hr2_128_b2": (2, 128, 2, 2),
     "cfs_hr4_256_b1": (4, 256, 1, 4),
 }
+# sibling generator iid_hlgvit_crs_gd4 (models/networks_iid_hlgvit_crs_gd4.py): the cfs geometry, concat-skip convs
+CRS_CONFIGS = {
+    "crs_hr2_128_b2": (2, 128, 2, 2),
+    "crs_hr4_256_b1": (4, 256, 1, 4),
+}
 SEED = 1
 WEIGHT_KEYS = (
     "head.0.0.weight", "localvit_encoder_01.linear_encoding.weight",
@@ -52,6 +57,8 @@ CFS_WEIGHT_KEYS = ("head.0.0.weight", "head.0.1.body.2.weight", "localvit_encode
                    "tail_color.0.1.weight", "tail_color.0.5.weight", "tail_gray.0.4.weight")
 CFS_ACTNORM_KEYS = ("lgcat_conv_e01.1.weight", "lgcat_conv_e01.1.bias", "sk_conv_d03s.1.bias", "tail_color.0.2.weight",
                     "tail_color.0.2.bias")
+CRS_WEIGHT_KEYS = CFS_WEIGHT_KEYS + ("sk_conv_d03d.0.weight", "sk_conv_d02d.0.bias", "sp.refine3.0.weight", "sp.conv1050.bias")
+CRS_ACTNORM_KEYS = CFS_ACTNORM_KEYS + ("sk_conv_d03d.1.weight", "sk_conv_d03d.1.bias", "sk_conv_d02d.1.weight")
 ACTNORM_KEYS = ("lgcat_conv_e01.1.weight", "lgcat_conv_e01.1.bias", "us_conv_d01d.1.weight",
                 "sk_conv_d03s.1.bias", "tail_D.0.2.weight", "tail_R.0.2.bias")
 
@@ -60,8 +67,10 @@ def main(only=None):
     from models import common as rcommon
     from models import networks_iid_hlgvit_crs_gd4_cfs_v3 as rv3
     from models import networks_iid_hlgvit_crs_gd4_cfs as rcfs
+    from models import networks_iid_hlgvit_crs_gd4 as rcrs
     jobs = [(n, c, rv3, orc.default_opt, WEIGHT_KEYS, ACTNORM_KEYS) for n, c in CONFIGS.items()] + \
-           [(n, c, rcfs, orc.cfs_opt, CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) for n, c in CFS_CONFIGS.items()]
+           [(n, c, rcfs, orc.cfs_opt, CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) for n, c in CFS_CONFIGS.items()] + \
+           [(n, c, rcrs, orc.cfs_opt, CRS_WEIGHT_KEYS, CRS_ACTNORM_KEYS) for n, c in CRS_CONFIGS.items()]
     for name, (hr, size, batch, stride), ref_mod, make_opt, WEIGHT_KEYS_, ACTNORM_KEYS_ in jobs:
         if only and name not in only:
             continue
@@ -71,7 +80,7 @@ def main(only=None):
         net = ref_mod.define_G(opt, rcommon.default_conv)
         x0, x1 = orc.make_inputs(size, [1, batch])
         sd0 = net.state_dict()
-        blob = {"seed": SEED, "hr": hr, "size": size, "batch": batch, "stride": stride}
+        blob = {"seed": SEED, "hr": hr, "size": size, "batch": batch, "stride": stride, "n_keys": len(sd0)}
         for k in WEIGHT_KEYS_:
             blob["w_sum/" + k] = sd0[k].double().sum().item()
             blob["w_abs/" + k] = sd0[k].double().abs().sum().item()

@@ -189,9 +189,13 @@ def test_forward_parity_option_paths(monkeypatch, env):
 
 
 # ---- sibling generator iid_hlgvit_crs_gd4_cfs: second plan graph over the same kernels
-def _gpu_net_cfs(hr, size, primed=True):
-    net, sd0, sd1, x0, opt = U.seeded_state_cfs(hr, size)
-    from cfen_vit_dehazing_b200 import common, networks_iid_hlgvit_crs_gd4_cfs as cfs
+def _gpu_net_cfs(hr, size, primed=True, family="cfs"):
+    net, sd0, sd1, x0, opt = U.seeded_state_cfs(hr, size, family=family)
+    from cfen_vit_dehazing_b200 import common
+    if family == "cfs":
+        from cfen_vit_dehazing_b200 import networks_iid_hlgvit_crs_gd4_cfs as cfs
+    else:
+        from cfen_vit_dehazing_b200 import networks_iid_hlgvit_crs_gd4 as cfs
     with contextlib.redirect_stdout(io.StringIO()):
         gnet = cfs.dec_ipt(opt, common.default_conv)
     gnet.load_state_dict(sd1 if primed else sd0, strict=True)
@@ -247,6 +251,61 @@ def test_cfs_sibling_batch16_fused_kernels_uint8_and_calibration():
                 if (k.rsplit(".", 1)[0] + ".initialized") in sd1 and not k.endswith(".initialized"))
     assert worst <= 2e-2, worst
     assert all(int(got[k]) == 1 for k in sd1 if k.endswith(".initialized"))
+
+
+# ---- sibling generator iid_hlgvit_crs_gd4: the cfs graph with concat-skip 1x1 convs (LD_CAT3 loader)
+@pytest.mark.parametrize("name", ["crs_hr2_128_b2", "crs_hr4_256_b1"])
+def test_crs_sibling_parity_vs_oracle_and_goldens(name):
+    from tests.golden.make_goldens import CRS_CONFIGS
+    hr, size, batch, stride = CRS_CONFIGS[name]
+    gnet, sd0, sd1, x0 = _gpu_net_cfs(hr, size, family="crs")
+    x1 = orc.make_inputs(size, [1, batch])[1]
+    ref = orc.forward(sd1, x1)
+    with torch.no_grad():
+        out = gnet(x1.cuda())
+    torch.cuda.synchronize()
+    g = U.load_golden(name)
+    for tag, a, b in zip(("xr", "xs", "xd"), out, ref):
+        assert a.shape == b.shape
+        mx, ps = U.err01(a, b)
+        assert mx <= MAX_ABS_01 and ps >= MIN_PSNR and bool(torch.isfinite(a).all()), (tag, mx, ps)
+        d = np.abs(a[:, :, ::stride, ::stride].cpu().numpy() - g[tag]).max() / 2.0     # the real reference's outputs
+        assert d <= MAX_ABS_01, (tag, d)
+
+
+def test_crs_sibling_batch16_option_paths_and_calibration(monkeypatch):
+    """256x256 batch 16 on the default path and with fp32 stage maps (CFEN_MAPS16=0: the three-source loader's
+    register path instead of cp.async), the fake_A-only uint8 output, and first-forward ActNorm initialisation of the
+    two concat-skip convs; the never-called SpatialPyramid's ActNorms stay un-initialised, as in the reference."""
+    x = orc.make_inputs(256, [1, 16])[1]
+    for env in ({}, {"CFEN_MAPS16": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        gnet, sd0, sd1, x0 = _gpu_net_cfs(2, 256, family="crs")
+        with torch.no_grad():
+            out = gnet(x.cuda())
+        for i in (0, 15):
+            ref = orc.forward(sd1, x[i:i + 1])
+            for a, b in zip(out, ref):
+                mx, ps = U.err01(a[i:i + 1], b)
+                assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (env, i, mx, ps)
+        for k in env:
+            monkeypatch.delenv(k)
+    img = ((x[:2] + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    with torch.no_grad():
+        u8 = gnet.forward_u8(img.cuda())
+        only = gnet.forward_u8(img.cuda(), outputs=("fake_A",))
+    assert torch.equal(only[0], u8[2])
+    gnet2, sd0, sd1, x0 = _gpu_net_cfs(2, 256, primed=False, family="crs")
+    with torch.no_grad():
+        gnet2(x0.cuda())
+    got = gnet2.state_dict()
+    live = [k for k in sd1 if not k.startswith("sp.")]
+    worst = max((got[k].cpu() - sd1[k]).abs().max().item() for k in live
+                if (k.rsplit(".", 1)[0] + ".initialized") in sd1 and not k.endswith(".initialized"))
+    assert worst <= 2e-2, worst
+    assert all(int(got[k]) == 1 for k in live if k.endswith(".initialized"))
+    assert int(got["sp.batch20.initialized"]) == 0 and int(got["sp.batch1.initialized"]) == 0
 
 
 def test_fp16_range_guard_detects_and_falls_back():

@@ -12,17 +12,23 @@ import torch
 from oracle import cfen_oracle as orc
 from tests import _util as U
 from tests.golden.make_goldens import (ACTNORM_KEYS, CFS_ACTNORM_KEYS, CFS_CONFIGS, CFS_WEIGHT_KEYS, CONFIGS,
-                                       WEIGHT_KEYS)
+                                       CRS_ACTNORM_KEYS, CRS_CONFIGS, CRS_WEIGHT_KEYS, WEIGHT_KEYS)
 
 TOL = 1e-4
 
 
 def _check(name):
-    cfs = name in CFS_CONFIGS
-    hr, size, batch, stride = (CFS_CONFIGS if cfs else CONFIGS)[name]
+    cfs, crs = name in CFS_CONFIGS, name in CRS_CONFIGS
+    hr, size, batch, stride = (CFS_CONFIGS if cfs else CRS_CONFIGS if crs else CONFIGS)[name]
     g = U.load_golden(name)
-    net, sd0, sd1, x0, opt = (U.seeded_state_cfs if cfs else U.seeded_state)(hr, size)
-    WEIGHT_KEYS, ACTNORM_KEYS = (CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) if cfs else (globals()["WEIGHT_KEYS"], globals()["ACTNORM_KEYS"])
+    if cfs or crs:
+        net, sd0, sd1, x0, opt = U.seeded_state_cfs(hr, size, family="cfs" if cfs else "crs")
+    else:
+        net, sd0, sd1, x0, opt = U.seeded_state(hr, size)
+    WEIGHT_KEYS, ACTNORM_KEYS = ((CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) if cfs else (CRS_WEIGHT_KEYS, CRS_ACTNORM_KEYS) if crs
+                                 else (globals()["WEIGHT_KEYS"], globals()["ACTNORM_KEYS"]))
+    if "n_keys" in g:
+        assert len(sd0) == int(g["n_keys"])
     # 1) init-stream mirror: seeded weights equal the reference's
     for k in WEIGHT_KEYS:
         assert abs(sd0[k].double().sum().item() - float(g["w_sum/" + k])) <= 1e-6 * max(1.0, abs(float(g["w_abs/" + k]))), k
@@ -60,6 +66,23 @@ def test_oracle_matches_reference_cfs_sibling_128_hr2():
 
 def test_oracle_matches_reference_cfs_sibling_256_hr4():
     _check("cfs_hr4_256_b1")
+
+
+def test_oracle_matches_reference_crs_sibling_128_hr2():
+    """iid_hlgvit_crs_gd4 (models/networks_iid_hlgvit_crs_gd4.py): concat-skip convs instead of the CFS gates, plus the
+    never-called SpatialPyramid in the state_dict / RNG stream."""
+    _check("crs_hr2_128_b2")
+
+
+def test_oracle_matches_reference_crs_sibling_256_hr4():
+    _check("crs_hr4_256_b1")
+
+
+def test_cfs_v2_and_cfs_pe_are_the_cfs_drop_in():
+    """The reference's ..._cfs_v2.py is byte-identical to ..._cfs.py and ..._cfs_pe.py differs by one print."""
+    from cfen_vit_dehazing_b200 import (networks_iid_hlgvit_crs_gd4_cfs as a, networks_iid_hlgvit_crs_gd4_cfs_pe as c,
+                                        networks_iid_hlgvit_crs_gd4_cfs_v2 as b)
+    assert b.dec_ipt is a.dec_ipt and c.dec_ipt is a.dec_ipt and b.define_G is a.define_G and c.define_G is a.define_G
 
 
 @pytest.mark.slow
