@@ -1994,7 +1994,7 @@ extern "C" int32_t cfen_deform_conv2d_forward(const float* input, const float* w
     return fail(1, "cfen_deform_conv2d_forward: im2col step must divide batchsize");
   cudaError_t e = launch_deform_conv(a, static_cast<cudaStream_t>(stream));
   if (e == cudaErrorInvalidConfiguration)
-    return fail(3, "cfen_deform_conv2d_forward: deformable_group*kH*kW = %d exceeds the on-chip offset tile", deformable_group * kH * kW);
+    return fail(3, "cfen_deform_conv2d_forward: kH*kW = %d (or H*W >= 2^24) exceeds the on-chip column tile", kH * kW);
   CU(e);
   return 0;
 }
@@ -2015,8 +2015,8 @@ extern "C" int32_t cfen_modulated_deform_conv2d_forward(const float* input, cons
                 dilH, dilW, group, deformable_group, &a.Ho, &a.Wo));
   cudaError_t e = launch_deform_conv(a, static_cast<cudaStream_t>(stream));
   if (e == cudaErrorInvalidConfiguration)
-    return fail(3, "cfen_modulated_deform_conv2d_forward: deformable_group*kH*kW = %d exceeds the on-chip offset tile",
-                deformable_group * kH * kW);
+    return fail(3, "cfen_modulated_deform_conv2d_forward: kH*kW = %d (or H*W >= 2^24) exceeds the on-chip column tile",
+                kH * kW);
   CU(e);
   return 0;
 }

@@ -23,6 +23,7 @@
 // dmcn_get_gradient_weight (:497-521) / dmcn_get_coordinate_weight (:523-568) / dmcn_im2col_bilinear (:466-495).
 #pragma once
 #include "common.cuh"
+#include "dcn.cuh"   // DcnRec helpers (dcn_make_record, dcn_rec_offset)
 
 namespace cfen {
 
@@ -84,7 +85,7 @@ struct DcnBwdDataCfg {
 };
 
 template <int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 deform_conv_bwd_data_kernel(const DcnBwdArgs a, int cc) {
   using Cfg = DcnBwdDataCfg<P>;
   extern __shared__ __align__(16) float dcn_smem[];
@@ -198,20 +199,33 @@ deform_conv_bwd_data_kernel(const DcnBwdArgs a, int cc) {
         float dh = 0.f, dw = 0.f, dm = 0.f;
         const float* im = a.input + ((size_t)b * a.Cin + c0) * HW;
         float* gi = a.gin + ((size_t)b * a.Cin + c0) * HW;
-        for (int cl = 0; cl < c1 - c0; ++cl, im += HW, gi += HW) {
-          const float gc = gcol[(cl * taps + tap) * Cfg::LDG + p];
-          const float gm = gc * m;
-          const float v1 = sp.c1 ? __ldg(im + sp.o1) : 0.f;
-          const float v2 = sp.c2 ? __ldg(im + sp.o2) : 0.f;
-          const float v3 = sp.c3 ? __ldg(im + sp.o3) : 0.f;
-          const float v4 = sp.c4 ? __ldg(im + sp.o4) : 0.f;
-          if (sp.c1) atomicAdd(gi + sp.o1, w1 * gm);
-          if (sp.c2) atomicAdd(gi + sp.o2, w2 * gm);
-          if (sp.c3) atomicAdd(gi + sp.o3, w3 * gm);
-          if (sp.c4) atomicAdd(gi + sp.o4, w4 * gm);
-          dh += gm * (sp.hw * (v3 - v1) + sp.lw * (v4 - v2));
-          dw += gm * (sp.hh * (v2 - v1) + sp.lh * (v4 - v3));
-          dm += gc * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+        constexpr int U = 4;   // channels per round: their 16 loads are issued before the first atomic
+        const int nch = c1 - c0;
+        for (int cl0 = 0; cl0 < nch; cl0 += U, im += U * HW, gi += U * HW) {
+          float gc[U], v1[U], v2[U], v3[U], v4[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool live = cl0 + u < nch;
+            const float* pi = im + u * HW;
+            gc[u] = live ? gcol[((cl0 + u) * taps + tap) * Cfg::LDG + p] : 0.f;
+            v1[u] = (live && sp.c1) ? __ldg(pi + sp.o1) : 0.f;
+            v2[u] = (live && sp.c2) ? __ldg(pi + sp.o2) : 0.f;
+            v3[u] = (live && sp.c3) ? __ldg(pi + sp.o3) : 0.f;
+            v4[u] = (live && sp.c4) ? __ldg(pi + sp.o4) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (cl0 + u >= nch) break;
+            const float gm = gc[u] * m;
+            float* po = gi + u * HW;
+            if (sp.c1) atomicAdd(po + sp.o1, w1 * gm);
+            if (sp.c2) atomicAdd(po + sp.o2, w2 * gm);
+            if (sp.c3) atomicAdd(po + sp.o3, w3 * gm);
+            if (sp.c4) atomicAdd(po + sp.o4, w4 * gm);
+            dh += gm * (sp.hw * (v3[u] - v1[u]) + sp.lw * (v4[u] - v2[u]));
+            dw += gm * (sp.hh * (v2[u] - v1[u]) + sp.lh * (v4[u] - v3[u]));
+            dm += gc[u] * (w1 * v1[u] + w2 * v2[u] + w3 * v3[u] + w4 * v4[u]);
+          }
         }
         sum_h[s] += dh; sum_w[s] += dw; sum_m[s] += dm;
       }
@@ -266,38 +280,71 @@ deform_conv_bwd_weight_kernel(const DcnBwdArgs a, int co_pass0, int tiles_per_im
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
+  // per-CTA row table: what row kk of the column tile samples (fixed for the whole kernel: k0 is)
+  __shared__ int4 rowtab[Cfg::KC];
+  if (tid < Cfg::KC) {
+    const int k = k0 + tid;
+    int4 e = make_int4(-1, 0, 0, 0);
+    if (k < K) {
+      const int c = k / taps, tap = k - c * taps;
+      const int cg = grp * cin_g + c, d = cg / ch_per_dg;
+      const int ki = tap / a.kW, kj = tap - ki * a.kW;
+      e = make_int4(cg, d * 2 * taps + 2 * tap, d * taps + tap,
+                    ((ki * a.dH - a.pH) << 16) | ((kj * a.dW - a.pW) & 0xffff));
+    }
+    rowtab[tid] = e;
+  }
+
   for (int tile = blockIdx.z; tile < total_tiles; tile += gridDim.z) {
     const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * P;
-    __syncthreads();  // previous tile consumed
+    __syncthreads();  // previous tile consumed (first pass: row table ready)
     const float* go = a.gout + ((size_t)b * a.Cout + (size_t)grp * cout_g + co_pass0) * HoWo;
     for (int i = tid; i < MROWS * P; i += Cfg::THREADS) {
       const int p = i % P, r = i / P;
       gs[r * Cfg::LD + p] = (co_pass0 + r < cout_g && p0 + p < HoWo) ? go[(size_t)r * HoWo + p0 + p] : 0.f;
     }
-    for (int i = tid; i < Cfg::KC * P; i += Cfg::THREADS) {
-      const int p = i % P, kk = i / P;
-      const int k = k0 + kk, pix = p0 + p;
-      float val = 0.f;
-      if (k < K && pix < HoWo) {
-        const int c = k / taps, tap = k - c * taps;
-        const int cg = grp * cin_g + c, d = cg / ch_per_dg;
-        const int ho = pix / a.Wo, wo = pix - ho * a.Wo;
-        const int ki = tap / a.kW, kj = tap - ki * a.kW;
-        const float* off = a.offset + ((size_t)(b * a.dg + d) * 2 * taps) * HoWo;
-        const float h = (float)(ho * a.sH - a.pH + ki * a.dH) + off[(size_t)(2 * tap) * HoWo + pix];
-        const float w = (float)(wo * a.sW - a.pW + kj * a.dW) + off[(size_t)(2 * tap + 1) * HoWo + pix];
-        const DcnSample sp = dcn_sample(h, w, a.H, a.W);
-        if (sp.inside) {
-          const float m = a.mask ? a.mask[((size_t)(b * a.dg + d) * taps + tap) * HoWo + pix] : 1.f;
-          const float* im = a.input + ((size_t)b * a.Cin + cg) * HW;
-          const float v1 = sp.c1 ? __ldg(im + sp.o1) : 0.f;
-          const float v2 = sp.c2 ? __ldg(im + sp.o2) : 0.f;
-          const float v3 = sp.c3 ? __ldg(im + sp.o3) : 0.f;
-          const float v4 = sp.c4 ? __ldg(im + sp.o4) : 0.f;
-          val = (sp.hh * sp.hw * v1 + sp.hh * sp.lw * v2 + sp.lh * sp.hw * v3 + sp.lh * sp.lw * v4) * m;
+    // column tile: a thread keeps its pixel and walks rows kk = q, q + 4, ... (their channel / tap come from the
+    // per-CTA row table); U rows per round, every load of a round issued before its first use
+    {
+      constexpr int U = 4, QS = Cfg::THREADS / P;
+      const int p = tid % P, q = tid / P, pix = p0 + p;
+      const bool pix_ok = pix < HoWo;
+      const int ho = pix / a.Wo, wo = pix - ho * a.Wo;
+      const int hbase = ho * a.sH, wbase = wo * a.sW;
+      const float* off_b = a.offset + (size_t)b * a.dg * 2 * taps * HoWo + pix;
+      const float* msk_b = a.mask ? a.mask + (size_t)b * a.dg * taps * HoWo + pix : nullptr;
+      const float* im_b = a.input + (size_t)b * a.Cin * HW;
+#pragma unroll 1
+      for (int kk0 = q; kk0 < Cfg::KC; kk0 += QS * U) {
+        float oh[U], ow[U], mk[U];
+        int4 rt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          rt[u] = rowtab[kk0 + u * QS];   // {channel or -1, offset plane of dy, mask plane, (ki*dH - pH) << 16 | (kj*dW - pW) & 0xffff}
+          const bool live = pix_ok && rt[u].x >= 0;
+          oh[u] = live ? off_b[(size_t)rt[u].y * HoWo] : -4.f;
+          ow[u] = live ? off_b[(size_t)(rt[u].y + 1) * HoWo] : -4.f;
+          mk[u] = (live && msk_b) ? msk_b[(size_t)rt[u].z * HoWo] : 1.f;
         }
+        float4 wq[U];
+        int ov[U];
+        float v1[U], v2[U], v3[U], v4[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float h = (float)(hbase + (rt[u].w >> 16)) + oh[u];
+          const float w = (float)(wbase + (int)(short)(rt[u].w & 0xffff)) + ow[u];
+          dcn_make_record(rt[u].x >= 0 && pix_ok ? h : -4.f, w, mk[u], a.H, a.W, wq[u], ov[u]);
+          const float* pc = im_b + (size_t)(rt[u].x < 0 ? 0 : rt[u].x) * HW + dcn_rec_offset(ov[u]);
+          v1[u] = (ov[u] & (1 << 28)) ? __ldg(pc) : 0.f;
+          v2[u] = (ov[u] & (1 << 29)) ? __ldg(pc + 1) : 0.f;
+          v3[u] = (ov[u] & (1 << 30)) ? __ldg(pc + a.W) : 0.f;
+          v4[u] = (ov[u] < 0) ? __ldg(pc + a.W + 1) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          col[(kk0 + u * QS) * Cfg::LD + p] =
+              fmaf(wq[u].x, v1[u], fmaf(wq[u].y, v2[u], fmaf(wq[u].z, v3[u], wq[u].w * v4[u])));
       }
-      col[kk * Cfg::LD + p] = val;
     }
     __syncthreads();
     // gw[co][kk] += sum_p gout[co][p] * col[kk][p]
@@ -385,7 +432,7 @@ inline cudaError_t dcn_bwd_data_variant(const DcnBwdArgs& a, cudaStream_t st) {
 inline cudaError_t launch_deform_conv_bwd_data(const DcnBwdArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.Ho <= 0 || a.Wo <= 0) return cudaSuccess;
   const int taps = a.kH * a.kW, cout_g = a.Cout / a.group;
-  if (taps > DcnBwdDataCfg<64>::ROWS) return cudaErrorInvalidConfiguration;
+  if (taps > DcnBwdDataCfg<64>::ROWS || (long long)a.H * a.W >= (1ll << 27)) return cudaErrorInvalidConfiguration;
   const size_t budget = 200 * 1024;
   if (DcnBwdDataCfg<64>::smem_bytes(cout_g, taps) <= budget) return dcn_bwd_data_variant<64>(a, st);
   if (DcnBwdDataCfg<32>::smem_bytes(cout_g, taps) <= budget) return dcn_bwd_data_variant<32>(a, st);
@@ -417,6 +464,9 @@ inline cudaError_t dcn_bwd_weight_variant(const DcnBwdArgs& a, int sm_count, cud
 // grad_weight and, when gbias is set, grad_bias.
 inline cudaError_t launch_deform_conv_bwd_weight(const DcnBwdArgs& a, int sm_count, cudaStream_t st) {
   if (a.B <= 0 || a.Ho <= 0 || a.Wo <= 0) return cudaSuccess;
+  // the row table packs (ki*dH - pH, kj*dW - pW) in 16 bits each, the record offset has 28
+  if ((long long)a.H * a.W >= (1ll << 27) || a.kH * a.dH + a.pH >= 32768 || a.kW * a.dW + a.pW >= 32768)
+    return cudaErrorInvalidConfiguration;
   if (a.gbias) {
     deform_conv_bwd_bias_kernel<<<a.Cout, 256, 0, st>>>(a.gout, a.gbias, a.B, a.Cout, a.Ho * a.Wo);
     cudaError_t e = cudaGetLastError();
