@@ -282,6 +282,23 @@ def workload_name(args, global_batch):
             "image-sharded over the GPUs, replicated weights (%s)" % (args.hr, args.size, args.size, global_batch, label))
 
 
+# What actually limits a kernel when neither of the two rooflines of the contract does (with the
+# ncu / timeline evidence under profiles/); carried as "limiter" next to the hbm / tensor fraction.
+LIMITERS = {
+    "attention_tc_kernel": "MUFU.EX2: 256 exponentials per query row = 2048 cycles per 128-query tile and SM sub-partition "
+                           "(240 us floor for the 64-image level-1 launch); profiles/r2_v1_attn_tc_timeline.md",
+    "gemm16_kernel<192>": "SM ingress: 40 KB of operands per 64-deep k-block and CTA = 78.6 flop per ingested byte; the "
+                          "aggregate L2->SM rate of these launches is 5-6.5 TB/s (DESIGN.md section 5)",
+    "gemm16_kernel<96>": "SM ingress, as gemm16_kernel<192>",
+    "vit_tail16r_kernel<96>": "serial GEMM -> epilogue -> GEMM chain per 128-token tile (69 % of warp samples wait on an "
+                              "mbarrier), UMMA N = 96 needs 128 B/clk of A-operand shared-memory reads; profiles/r1_v6_tailr96_full.md",
+    "vit_tail16r_kernel<192>": "as vit_tail16r_kernel<96>",
+    "vit_front16_kernel<96>": "L1 / LSU wavefronts of the thread-per-row window gather; profiles/r1_v5_front96_full.md",
+    "conv16_kernel<ConvTail7_3>": "shared-memory bandwidth of the A fragments: K = 588 per pixel against 3 (8) output columns",
+    "conv16_kernel<ConvTail7_1>": "as conv16_kernel<ConvTail7_3>",
+}
+
+
 def roofline_of(d, peaks):
     """Roofline entry of one kernel's totals: bound by whichever of tensor peak / HBM peak takes longer on its
     algorithmic flops / bytes."""
@@ -497,6 +514,8 @@ def run_ours(args):
             e.update({"kernel": sym, "share_of_step": d["us"] / t_all, "launches": d["launches"],
                       "avg_launch_us": d["us"] / max(1, d["launches"]),
                       "traffic": ncu_traffic(traffic_table, sym, d["units"], d["launches"], plan.max_batch, (size, hr))})
+            if sym in LIMITERS:
+                e["limiter"] = LIMITERS[sym]
             roofline_all.append(e)
         name, d = max(kernels.items(), key=lambda kv: kv[1]["us"])
         nl = max(1, d["launches"])

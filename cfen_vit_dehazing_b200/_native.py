@@ -124,10 +124,10 @@ def check(status):
 
 
 def chunk_images(height, batch):
-    """Images processed per internal pass: bounds the workspace (~90 MB/image at 512x512, 5.8 GB of the 180 GB at
-    64 images).  Measured: 16 -> 32 images per pass +16 % throughput, 32 -> 64 another +3.5 % (the small-M
-    GEMMs of the global branch and the level-3 kernels fill more of a wave)."""
-    per = 64 if height <= 512 else 16      # (cfs variant: callers pass the level-1 equivalent, 2 * input edge)
+    """Images processed per internal pass: bounds the workspace (~90 MB/image at 512x512, 11.5 GB of the 180 GB at
+    128 images).  Measured: 16 -> 32 images per pass +16 % throughput, 32 -> 64 another +3.5 %, 64 -> 128 +1.7 %
+    (the small-M GEMMs of the global branch and the level-3 kernels fill more of a wave); 256 gives nothing more."""
+    per = 128 if height <= 512 else 16     # (cfs variant: callers pass the level-1 equivalent, 2 * input edge)
     env = os.environ.get("CFEN_CHUNK_IMAGES")
     if env:
         per = max(1, int(env))
