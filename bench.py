@@ -287,9 +287,10 @@ def workload_name(args, global_batch):
 LIMITERS = {
     "attention_tc_kernel": "MUFU.EX2: 256 exponentials per query row = 2048 cycles per 128-query tile and SM sub-partition "
                            "(240 us floor for the 64-image level-1 launch); profiles/r2_v1_attn_tc_timeline.md",
-    "gemm16_kernel<192>": "SM ingress: 40 KB of operands per 64-deep k-block and CTA = 78.6 flop per ingested byte; the "
-                          "aggregate L2->SM rate of these launches is 5-6.5 TB/s (DESIGN.md section 5)",
-    "gemm16_kernel<96>": "SM ingress, as gemm16_kernel<192>",
+    "gemm16_kernel<192>": "mixed: long-K launches run at 620-900 TFLOP/s (tools/gemm_pair_bench.cu), the K = 384 launches "
+                          "are HBM / epilogue bound (fp32 residual in + fp32 out: M131072 N384 K384 moves 503 MB in 112 us "
+                          "= 0.69 of the HBM peak) and one tile per CTA has no main-loop / epilogue overlap; see frac_by_shape",
+    "gemm16_kernel<96>": "as gemm16_kernel<192>",
     "vit_tail16r_kernel<96>": "serial GEMM -> epilogue -> GEMM chain per 128-token tile (69 % of warp samples wait on an "
                               "mbarrier), UMMA N = 96 needs 128 B/clk of A-operand shared-memory reads; profiles/r1_v6_tailr96_full.md",
     "vit_tail16r_kernel<192>": "as vit_tail16r_kernel<96>",
@@ -310,6 +311,20 @@ def roofline_of(d, peaks):
         return {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": tf / peaks["tf_sustained"]}
     return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+
+
+def frac_by_shape(sym, shapes, peaks):
+    """Roofline fraction of a kernel that runs at several shapes, each shape against ITS OWN bound: the time the shapes
+    would take at whichever of the tensor / HBM peaks binds each of them, over the time they took.  (The contract's
+    `frac` sums flops and bytes over all shapes first, which files e.g. gemm16's short-K launches - 8 bytes of fp32
+    residual + output per element, HBM-bound - under the tensor roof of its long-K launches.)"""
+    ideal = took = 0.0
+    for v in shapes.values():
+        if v["kernel"] != sym:
+            continue
+        ideal += max(v["gflop"] * 1e9 / (peaks["tf_sustained"] * 1e12), v["mbytes"] * 1e6 / (peaks["hbm_gbs"] * 1e9))
+        took += v["us"] / 1e6
+    return ideal / took if took > 0 else 0.0
 
 
 def parity_vs_oracle(net, x_host, out, hr, size, picks):
@@ -514,6 +529,7 @@ def run_ours(args):
             e.update({"kernel": sym, "share_of_step": d["us"] / t_all, "launches": d["launches"],
                       "avg_launch_us": d["us"] / max(1, d["launches"]),
                       "traffic": ncu_traffic(traffic_table, sym, d["units"], d["launches"], plan.max_batch, (size, hr))})
+            e["frac_by_shape"] = frac_by_shape(sym, shapes, peaks)
             if sym in LIMITERS:
                 e["limiter"] = LIMITERS[sym]
             roofline_all.append(e)

@@ -106,3 +106,21 @@ def test_measured_peaks_fallback_and_file(tmp_path, monkeypatch):
     b = _bench()
     pk = b.measured_peaks()
     assert pk["hbm_gbs"] > 1000 and pk["tf_sustained"] > 100 and pk["source"] in ("measured", "fallback")
+
+
+def test_frac_by_shape_measures_each_shape_against_its_own_bound():
+    import bench as b
+    peaks = {"tf_sustained": 1000.0, "hbm_gbs": 5000.0}
+    shapes = {
+        # tensor-bound shape at half of the tensor peak: 1000 GFLOP in 2000 us (ideal 1000 us)
+        "gemm16 M1 N1 K4096": {"kernel": "gemm16_kernel<192>", "us": 2000.0, "gflop": 1000.0, "mbytes": 10.0, "launches": 1},
+        # byte-bound shape at 0.8 of the HBM peak: 4000 MB in 1000 us (ideal 800 us), few flops
+        "gemm16 M2 N2 K64": {"kernel": "gemm16_kernel<192>", "us": 1000.0, "gflop": 10.0, "mbytes": 4000.0, "launches": 1},
+        "other": {"kernel": "mlp16_kernel", "us": 5.0, "gflop": 1.0, "mbytes": 1.0, "launches": 1},
+    }
+    f = b.frac_by_shape("gemm16_kernel<192>", shapes, peaks)
+    assert abs(f - (1000.0 + 800.0) / 3000.0) < 1e-9
+    # the summed-first roofline of the contract files both under the tensor roof: 1010 GFLOP / 3000 us = 0.337
+    tot = {"us": 3000.0, "gflop": 1010.0, "mbytes": 4010.0}
+    assert b.roofline_of(tot, peaks)["bound"] == "tensor" and abs(b.roofline_of(tot, peaks)["frac"] - 0.33666) < 1e-3
+    assert b.frac_by_shape("absent", shapes, peaks) == 0.0
