@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
 IO_U8, ONLY_FAKE_A = 1, 2     # cfen_forward_ex io_flags (include/cfen_b200.h)
 VARIANT_CFS = 1                # cfen_config.flags: iid_hlgvit_crs_gd4_cfs graph
 VARIANT_CRS = 2                # cfen_config.flags: iid_hlgvit_crs_gd4 graph (cfs with concat-skip convs)
+VARIANT_V5 = 4                 # cfen_config.flags: iid_hlgvit_crs_gd4_cfs_v5 graph (v3 with quarter-width local ViTs)
 
 
 class cfen_config(ctypes.Structure):

@@ -148,6 +148,7 @@ class _ViTBase(nn.Module):
     """Shared constructor of the local / global ViT blocks (reference v3.py:1062-1134, 1197-1270)."""
 
     pooled = False  # GViT: AvgPool2 twice in front, bilinear x2 twice behind
+    SHRINK = 1      # LViT of iid_hlgvit_crs_gd4_cfs_v5: the ViT runs on num_channels / 4 behind 1x1 shrink / extend convs
 
     def __init__(self, img_dim, patch_dim, num_channels, embedding_dim, num_heads, num_layers,
                  hidden_dim, num_queries, positional_encoding_type="learned", dropout_rate=0,
@@ -159,6 +160,8 @@ class _ViTBase(nn.Module):
             raise NotImplementedError("cfen_b200 fast path supports num_layers == 1 only")
         self.no_norm = no_norm
         self.mlp = mlp
+        embedding_dim = embedding_dim // self.SHRINK      # v5.py:1086, 1090, 1095, 1097
+        hidden_dim = hidden_dim // self.SHRINK
         self.embedding_dim = embedding_dim
         self.hidden_dim = hidden_dim
         self.num_heads = num_heads
@@ -169,8 +172,15 @@ class _ViTBase(nn.Module):
         self.no_pos = no_pos
         self.num_patches = int((img_dim // patch_dim) ** 2)
         self.seq_length = self.num_patches
-        self.flatten_dim = patch_dim * patch_dim * num_channels
-        self.out_dim = patch_dim * patch_dim * num_channels
+        self.flatten_dim = patch_dim * patch_dim * num_channels // self.SHRINK
+        self.out_dim = patch_dim * patch_dim * num_channels // self.SHRINK
+        if self.SHRINK > 1:                               # v5.py:1101-1106, registered before linear_encoding
+            cs = int(num_channels / self.SHRINK)
+            self.conv_shrink = nn.Sequential(nn.Conv2d(num_channels, cs, kernel_size=1, stride=1, padding=0),
+                                             ActNorm2d(cs), nn.ReLU(True))
+            self.conv_extend = nn.Sequential(nn.Conv2d(cs, num_channels, kernel_size=1, stride=1, padding=0),
+                                             ActNorm2d(num_channels), nn.ReLU(True))
+            self.num_channels = cs
 
         if self.pooled:
             self.ave_pool2 = nn.Sequential(nn.AvgPool2d(2, stride=2))
@@ -207,6 +217,13 @@ class _ViTBase(nn.Module):
 class LViT(_ViTBase):
     """Windowed local ViT block (reference v3.py:1062-1189)."""
     pooled = False
+
+
+class LViT5(_ViTBase):
+    """Local ViT of iid_hlgvit_crs_gd4_cfs_v5 (networks_iid_hlgvit_crs_gd4_cfs_v5.py:1062-1192): conv_shrink (1x1, C -> C/4,
+    ActNorm, ReLU) -> the windowed ViT at a quarter of the width -> conv_extend (1x1, C/4 -> C, ActNorm, ReLU)."""
+    pooled = False
+    SHRINK = 4
 
 
 class GViT(_ViTBase):
@@ -266,7 +283,8 @@ def _level_of(stage):
 class dec_ipt(nn.Module):
     # "v3": iid_hlgvit_crs_gd4_cfs_v3 (this file's reference); "cfs": the sibling iid_hlgvit_crs_gd4_cfs without the
     # half-resolution stem (networks_iid_hlgvit_crs_gd4_cfs.py subclasses and flips this); "crs": iid_hlgvit_crs_gd4 =
-    # the cfs graph with concat-skip 1x1 convs in place of the two CFS gates (networks_iid_hlgvit_crs_gd4.py)
+    # the cfs graph with concat-skip 1x1 convs in place of the two CFS gates (networks_iid_hlgvit_crs_gd4.py); "v5":
+    # iid_hlgvit_crs_gd4_cfs_v5 = v3 with quarter-width local ViTs behind 1x1 shrink / extend convs
     VARIANT = "v3"
 
     def __init__(self, opt, conv=common.default_conv):
@@ -298,7 +316,7 @@ class dec_ipt(nn.Module):
         for stage in _STAGES:
             mult = 2 ** (_level_of(stage) - 1)
             ch = int(mult * nf)
-            self.add_module("localvit_" + stage, LViT(
+            self.add_module("localvit_" + stage, (LViT5 if self.VARIANT == "v5" else LViT)(
                 img_dim=opt.patch_size, patch_dim=p, num_channels=ch, embedding_dim=ch * p * p,
                 num_heads=int(opt.num_heads * mult), hidden_dim=ch * p * p * opt.hidden_dim_ratio,
                 **vit_kw))
@@ -450,7 +468,7 @@ class dec_ipt(nn.Module):
                                 n_feats=opt.n_feats, hidden_dim_ratio=opt.hidden_dim_ratio,
                                 num_heads=opt.num_heads, patch_dim=opt.patch_dim,
                                 patch_size=int(opt.patch_size), load_size=int(opt.loadSize),
-                                max_batch=need, flags={"v3": 0, "cfs": _native.VARIANT_CFS, "crs": _native.VARIANT_CRS}[self.VARIANT])
+                                max_batch=need, flags={"v3": 0, "cfs": _native.VARIANT_CFS, "crs": _native.VARIANT_CRS, "v5": _native.VARIANT_V5}[self.VARIANT])
             self._plans[key] = plan
         version = (self._weights_version, self._tensors_version())
         if plan.weights_version != version:

@@ -113,10 +113,25 @@ def _untokens(t, p, size):
     return F.fold(t.transpose(1, 2), size, p, stride=p)
 
 
+def _pointwise_actnorm_relu(sd, name, x, window):
+    """conv1x1 + ActNorm + ReLU of a v5 local ViT applied to the whole level map.  The reference applies it per window
+    call; an un-initialised ActNorm takes its statistics from the FIRST call = the top-left window (v5.py:403, 1139)."""
+    y = _conv(sd, name + ".0", x)
+    if int(sd[name + ".1.initialized"]) == 0:
+        actnorm(sd, name + ".1", y[:, :, :window, :window])
+    return F.relu(actnorm(sd, name + ".1", y))
+
+
 def local_vit(sd, prefix, x, heads, window):
     """All window tiles of one level at once.  The reference crops quadrants recursively down to
     window x window tiles, runs the same LViT on each and joins them back (e.g. v3.py:403-482);
-    that equals one batched window partition."""
+    that equals one batched window partition.  A v5 local ViT (networks_iid_hlgvit_crs_gd4_cfs_v5.py:1136-1192) wraps
+    the same token algebra, at a quarter of the channels, in conv_shrink / conv_extend."""
+    if prefix + ".conv_shrink.0.weight" in sd:
+        y = _pointwise_actnorm_relu(sd, prefix + ".conv_shrink", x, window)
+        inner = {k: v for k, v in sd.items() if k.startswith(prefix + ".") and ".conv_shrink." not in k}
+        z = local_vit(inner, prefix, y, heads, window)
+        return _pointwise_actnorm_relu(sd, prefix + ".conv_extend", z, window)
     b, c, hh, ww = x.shape
     ny, nx = hh // window, ww // window
     tiles = x.view(b, c, ny, window, nx, window).permute(0, 2, 4, 1, 3, 5).reshape(b * ny * nx, c, window, window)

@@ -33,6 +33,20 @@ def seeded_state(hr, size, seed=1):
 
 
 @functools.lru_cache(maxsize=2)
+def seeded_state_v5(hr, size, seed=1):
+    """Same for iid_hlgvit_crs_gd4_cfs_v5 (v3 geometry: input edge = 2 * loadSize)."""
+    from cfen_vit_dehazing_b200 import common, networks_iid_hlgvit_crs_gd4_cfs_v5 as v5
+    opt = orc.default_opt(hr, size)
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = v5.define_G(opt, common.default_conv)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x0 = orc.make_inputs(size, [1])[0]
+    sd1 = orc.prime(sd0, x0)
+    return net, sd0, sd1, x0, opt
+
+
+@functools.lru_cache(maxsize=2)
 def seeded_state_cfs(hr, size, seed=1, family="cfs"):
     """Same for the sibling generators iid_hlgvit_crs_gd4_cfs (``family="cfs"``) and iid_hlgvit_crs_gd4 (``"crs"``);
     input edge = loadSize = ``size``."""

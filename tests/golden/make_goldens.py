@@ -44,6 +44,11 @@ CRS_CONFIGS = {
     "crs_hr2_128_b2": (2, 128, 2, 2),
     "crs_hr4_256_b1": (4, 256, 1, 4),
 }
+# sibling generator iid_hlgvit_crs_gd4_cfs_v5 (models/networks_iid_hlgvit_crs_gd4_cfs_v5.py): v3 with quarter-width local ViTs
+V5_CONFIGS = {
+    "v5_hr2_128_b2": (2, 128, 2, 2),
+    "v5_hr4_512_b1": (4, 512, 1, 8),
+}
 SEED = 1
 WEIGHT_KEYS = (
     "head.0.0.weight", "localvit_encoder_01.linear_encoding.weight",
@@ -59,6 +64,12 @@ CFS_ACTNORM_KEYS = ("lgcat_conv_e01.1.weight", "lgcat_conv_e01.1.bias", "sk_conv
                     "tail_color.0.2.bias")
 CRS_WEIGHT_KEYS = CFS_WEIGHT_KEYS + ("sk_conv_d03d.0.weight", "sk_conv_d02d.0.bias", "sp.refine3.0.weight", "sp.conv1050.bias")
 CRS_ACTNORM_KEYS = CFS_ACTNORM_KEYS + ("sk_conv_d03d.1.weight", "sk_conv_d03d.1.bias", "sk_conv_d02d.1.weight")
+V5_WEIGHT_KEYS = ("head.0.0.weight", "localvit_encoder_01.conv_shrink.0.weight", "localvit_encoder_01.linear_encoding.weight",
+                  "localvit_decoder_02s.encoder.layers.0.self_attn.in_proj_weight", "localvit_decoder_03d.conv_extend.0.bias",
+                  "localvit_decoder_01r.mlp_head.3.weight", "globalvit_encoder_02.mlp_head.0.weight", "tail_S.0.4.weight")
+V5_ACTNORM_KEYS = ("localvit_encoder_01.conv_shrink.1.weight", "localvit_encoder_01.conv_shrink.1.bias",
+                   "localvit_encoder_01.conv_extend.1.weight", "localvit_decoder_03d.conv_extend.1.bias",
+                   "localvit_decoder_02s.conv_shrink.1.weight", "lgcat_conv_e01.1.weight", "tail_D.0.2.weight")
 ACTNORM_KEYS = ("lgcat_conv_e01.1.weight", "lgcat_conv_e01.1.bias", "us_conv_d01d.1.weight",
                 "sk_conv_d03s.1.bias", "tail_D.0.2.weight", "tail_R.0.2.bias")
 
@@ -68,9 +79,11 @@ def main(only=None):
     from models import networks_iid_hlgvit_crs_gd4_cfs_v3 as rv3
     from models import networks_iid_hlgvit_crs_gd4_cfs as rcfs
     from models import networks_iid_hlgvit_crs_gd4 as rcrs
+    from models import networks_iid_hlgvit_crs_gd4_cfs_v5 as rv5
     jobs = [(n, c, rv3, orc.default_opt, WEIGHT_KEYS, ACTNORM_KEYS) for n, c in CONFIGS.items()] + \
            [(n, c, rcfs, orc.cfs_opt, CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) for n, c in CFS_CONFIGS.items()] + \
-           [(n, c, rcrs, orc.cfs_opt, CRS_WEIGHT_KEYS, CRS_ACTNORM_KEYS) for n, c in CRS_CONFIGS.items()]
+           [(n, c, rcrs, orc.cfs_opt, CRS_WEIGHT_KEYS, CRS_ACTNORM_KEYS) for n, c in CRS_CONFIGS.items()] + \
+           [(n, c, rv5, orc.default_opt, V5_WEIGHT_KEYS, V5_ACTNORM_KEYS) for n, c in V5_CONFIGS.items()]
     for name, (hr, size, batch, stride), ref_mod, make_opt, WEIGHT_KEYS_, ACTNORM_KEYS_ in jobs:
         if only and name not in only:
             continue

@@ -12,20 +12,24 @@ import torch
 from oracle import cfen_oracle as orc
 from tests import _util as U
 from tests.golden.make_goldens import (ACTNORM_KEYS, CFS_ACTNORM_KEYS, CFS_CONFIGS, CFS_WEIGHT_KEYS, CONFIGS,
-                                       CRS_ACTNORM_KEYS, CRS_CONFIGS, CRS_WEIGHT_KEYS, WEIGHT_KEYS)
+                                       CRS_ACTNORM_KEYS, CRS_CONFIGS, CRS_WEIGHT_KEYS, V5_ACTNORM_KEYS, V5_CONFIGS,
+                                       V5_WEIGHT_KEYS, WEIGHT_KEYS)
 
 TOL = 1e-4
 
 
 def _check(name):
-    cfs, crs = name in CFS_CONFIGS, name in CRS_CONFIGS
-    hr, size, batch, stride = (CFS_CONFIGS if cfs else CRS_CONFIGS if crs else CONFIGS)[name]
+    cfs, crs, v5 = name in CFS_CONFIGS, name in CRS_CONFIGS, name in V5_CONFIGS
+    hr, size, batch, stride = (CFS_CONFIGS if cfs else CRS_CONFIGS if crs else V5_CONFIGS if v5 else CONFIGS)[name]
     g = U.load_golden(name)
     if cfs or crs:
         net, sd0, sd1, x0, opt = U.seeded_state_cfs(hr, size, family="cfs" if cfs else "crs")
+    elif v5:
+        net, sd0, sd1, x0, opt = U.seeded_state_v5(hr, size)
     else:
         net, sd0, sd1, x0, opt = U.seeded_state(hr, size)
     WEIGHT_KEYS, ACTNORM_KEYS = ((CFS_WEIGHT_KEYS, CFS_ACTNORM_KEYS) if cfs else (CRS_WEIGHT_KEYS, CRS_ACTNORM_KEYS) if crs
+                                 else (V5_WEIGHT_KEYS, V5_ACTNORM_KEYS) if v5
                                  else (globals()["WEIGHT_KEYS"], globals()["ACTNORM_KEYS"]))
     if "n_keys" in g:
         assert len(sd0) == int(g["n_keys"])
@@ -76,6 +80,16 @@ def test_oracle_matches_reference_crs_sibling_128_hr2():
 
 def test_oracle_matches_reference_crs_sibling_256_hr4():
     _check("crs_hr4_256_b1")
+
+
+def test_oracle_matches_reference_v5_sibling_128_hr2():
+    """iid_hlgvit_crs_gd4_cfs_v5 (models/networks_iid_hlgvit_crs_gd4_cfs_v5.py): quarter-width local ViTs behind
+    conv_shrink / conv_extend whose ActNorm layers initialise on the top-left window; 1078-key module and RNG stream."""
+    _check("v5_hr2_128_b2")
+
+
+def test_oracle_matches_reference_v5_sibling_512_hr4():
+    _check("v5_hr4_512_b1")
 
 
 def test_cfs_v2_and_cfs_pe_are_the_cfs_drop_in():
