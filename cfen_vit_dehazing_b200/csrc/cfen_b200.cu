@@ -26,6 +26,7 @@
 #include "conv_tc.cuh"
 #include "dcn.cuh"
 #include "dcn_bwd.cuh"
+#include "lvit5.cuh"
 #include "attn16.cuh"
 #include "attn_tc.cuh"
 #include "gemm16.cuh"
@@ -384,6 +385,8 @@ struct cfen_plan {
   Arena wa, ws;  // packed weights, workspace
   bool allocated = false, packed = false, from_blob = false;
   VitW lvit[12], gvit[12];
+  bool v5 = false;                       // iid_hlgvit_crs_gd4_cfs_v5: quarter-width local ViTs (lvit5.cuh)
+  float *v5_shrink[12][4] = {}, *v5_extend[12][4] = {};   // arena copies of conv_shrink / conv_extend {w, b, an_w, an_b}
   std::map<std::string, ConvLayer> conv;
   float* cfsm_w[2] = {nullptr, nullptr};  // d03d (C=48), d02d (C=24): 8 weights concatenated
   float* ones = nullptr;
@@ -449,6 +452,7 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
         const int lvl = stage_level(kStages[i]);
         v.prefix = std::string(g ? "globalvit_" : "localvit_") + kStages[i];
         v.C = p->Cl[lvl];
+        if (p->v5 && !g) v.C /= 4;   // the local ViT of v5 runs on the shrunk map (v5.py:1086-1106)
         v.P2 = g ? 16 : 4;
         v.E = v.C * v.P2;
         v.heads = p->cfg.num_heads << (lvl - 1);
@@ -463,6 +467,13 @@ static void plan_layout(cfen_plan* p, bool weights, bool workspace) {
         v.wm3 = a.take(E * hd); v.bm3 = a.take(E);
         v.h_le = a.take16(E * E); v.h_in = a.take16(3 * E * E); v.h_out = a.take16(E * E);
         v.h_1 = a.take16(hd * E); v.h_2 = a.take16(E * hd); v.h_m0 = a.take16(hd * E); v.h_m3 = a.take16(E * hd);
+        if (p->v5 && !g) {
+          const size_t Cf = p->Cl[lvl], Cq = Cf / 4;
+          p->v5_shrink[i][0] = a.take(Cq * Cf);
+          for (int k = 1; k < 4; ++k) p->v5_shrink[i][k] = a.take(Cq);
+          p->v5_extend[i][0] = a.take(Cf * Cq);
+          for (int k = 1; k < 4; ++k) p->v5_extend[i][k] = a.take(Cf);
+        }
       }
     }
     for (auto& kv : p->conv) {
@@ -580,9 +591,10 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (cfg->hidden_dim_ratio != 2 && cfg->hidden_dim_ratio != 4)
     return fail(3, "unsupported hidden_dim_ratio=%d (2 or 4)", cfg->hidden_dim_ratio);
   if (cfg->num_heads != 4 || cfg->patch_dim != 2) return fail(3, "num_heads/patch_dim must be 4/2");
-  if (cfg->flags & ~(CFEN_VARIANT_CFS | CFEN_VARIANT_CRS)) return fail(3, "unknown cfen_config.flags bits 0x%x", cfg->flags);
-  if ((cfg->flags & CFEN_VARIANT_CFS) && (cfg->flags & CFEN_VARIANT_CRS))
-    return fail(1, "cfen_config.flags: CFEN_VARIANT_CFS and CFEN_VARIANT_CRS are exclusive");
+  if (cfg->flags & ~(CFEN_VARIANT_CFS | CFEN_VARIANT_CRS | CFEN_VARIANT_V5))
+    return fail(3, "unknown cfen_config.flags bits 0x%x", cfg->flags);
+  if ((cfg->flags & (cfg->flags - 1)) != 0)
+    return fail(1, "cfen_config.flags: CFEN_VARIANT_CFS, CFEN_VARIANT_CRS and CFEN_VARIANT_V5 are exclusive");
   const bool crs = (cfg->flags & CFEN_VARIANT_CRS) != 0;
   const bool cfs = crs || (cfg->flags & CFEN_VARIANT_CFS) != 0;   // crs shares the cfs graph and geometry
   const int edge = cfs ? 64 : 128;   // level-1 map edge must be a multiple of 64 (8 windows of >= 8 px; 16x pooling)
@@ -607,6 +619,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   p->H = cfg->height; p->W = cfg->width; p->nbmax = cfg->max_batch; p->hr = cfg->hidden_dim_ratio;
   p->win = cfg->patch_size;
   p->variant = crs ? 2 : (cfs ? 1 : 0);
+  p->v5 = (cfg->flags & CFEN_VARIANT_V5) != 0;
   p->H1 = cfs ? p->H : p->H / 2;
   p->Cf = cfs ? 24 : 12;
   if (const char* gp = getenv("CFEN_GEMM_PATH")) {
@@ -851,6 +864,17 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
       RET(pack_linear(p, pre + ".mlp_head.0.bias", v.bm0, hid, 1, false, false, C, P2, false, st));
       RET(pack_linear(p, pre + ".mlp_head.3.weight", v.wm3, E, hid, true, false, C, P2, true, st, v.h_m3));
       RET(pack_linear(p, pre + ".mlp_head.3.bias", v.bm3, E, 1, true, false, C, P2, false, st));
+      if (p->v5 && !g) {   // conv_shrink / conv_extend: reference layout, copied so that the plan owns them
+        const int Cf = p->Cl[stage_level(kStages[i])], Cq = Cf / 4;
+        static const char* kSfx[4] = {".0.weight", ".0.bias", ".1.weight", ".1.bias"};
+        for (int k = 0; k < 4; ++k) {
+          const float* src;
+          RET(lookup(p, pre + ".conv_shrink" + kSfx[k], k == 0 ? (int64_t)Cq * Cf : Cq, &src));
+          CU(cudaMemcpyAsync(p->v5_shrink[i][k], src, sizeof(float) * (k == 0 ? (size_t)Cq * Cf : Cq), cudaMemcpyDeviceToDevice, st));
+          RET(lookup(p, pre + ".conv_extend" + kSfx[k], k == 0 ? (int64_t)Cq * Cf : Cf, &src));
+          CU(cudaMemcpyAsync(p->v5_extend[i][k], src, sizeof(float) * (k == 0 ? (size_t)Cq * Cf : Cf), cudaMemcpyDeviceToDevice, st));
+        }
+      }
     }
   for (auto& kv : p->conv) {
     ConvLayer& c = kv.second;
@@ -1100,6 +1124,13 @@ static int run_attn16(Run& r, const __half* qkv, __half* o, int nseq, int L, int
     CU(launch_attention_tc(qkv, o, nseq, L, E, heads, r.st));
     return 0;
   }
+  if (E / heads == 6) {   // local ViTs of iid_hlgvit_crs_gd4_cfs_v5 (level 3)
+    if (L <= 0 || 256 % L != 0) return fail(3, "attention with 6-wide heads needs windows of 16 / 64 / 256 tokens (got %d)", L);
+    l.sym("attention_hd6_kernel");
+    attention_hd6_kernel<<<(nseq * L + 255) / 256, 256, 0, r.st>>>(qkv, o, nseq * L, L, E);
+    CU(cudaGetLastError());
+    return 0;
+  }
   l.sym("attention16_kernel<%d>", E / heads);
   CU(launch_attention16(qkv, o, nseq, L, E, heads, r.st));
   return 0;
@@ -1311,6 +1342,48 @@ static int run_cfsm(Run& r, int which, const float* x0, const float* x1, const f
 
 // block(x) for stage index si (reference e.g. v3.py:403-488): the global ViT branch runs on the lane's
 // second stream while the local branch runs on the first; the merge conv joins them.
+// Local branch of one block of iid_hlgvit_crs_gd4_cfs_v5 (v5.py:1136-1192): conv_shrink -> quarter-width windowed ViT ->
+// conv_extend, result as the [M, 4C] fp32 token matrix the merge convolution reads.  Levels 1 / 2: one lvit5_kernel;
+// level 3: shrink -> the v3 token kernels on a token matrix (6-wide-head attention) -> extend.
+static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, const float** tokens_out) {
+  cfen_plan* p = r.p;
+  Lane& L = *r.ln;
+  const VitW& v = p->lvit[si];
+  const int M = r.nb * nwin * v.L;
+  const Lvit5Conv sh{p->v5_shrink[si][0], p->v5_shrink[si][1], p->v5_shrink[si][2], p->v5_shrink[si][3]};
+  const Lvit5Conv ex{p->v5_extend[si][0], p->v5_extend[si][1], p->v5_extend[si][2], p->v5_extend[si][3]};
+  const double flops = 2.0 * M * ((double)v.E * v.E * 5 + 4.0 * v.E * v.hid + 2.0 * v.L * v.E) + 4.0 * M * v.E * v.E;
+  const double bytes = (all_maps16(p) ? 2.0 : 4.0) * M * 4.0 * C + 4.0 * M * 4.0 * C;
+  if (C <= 48) {
+    Lvit5Args a{x, all_maps16(p) ? 1 : 0, r.nb, Hl, Hl, p->win, M, sh, ex, v.w_le, v.b_le, v.pos, v.ln1g, v.ln1b, v.w_in,
+                v.w_out, v.w1, v.b1, v.w2, v.b2, v.ln2g, v.ln2b, v.wm0, v.bm0, v.wm3, v.bm3, v.hid, L.lws.t1};
+    Launch l(r, PC_MLP, flops, bytes, "lvit5 M%d E%d hid%d", M, v.E, v.hid);
+    l.sym("lvit5_kernel<%d>", C);
+    const cudaError_t e = C == 24 ? launch_lvit5<24>(a, r.st) : launch_lvit5<48>(a, r.st);
+    if (e == cudaErrorInvalidConfiguration)
+      return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: windows of %d tokens are not supported (16 / 64 / 256)", v.L);
+    CU(e);
+    *tokens_out = L.lws.t1;
+    return 0;
+  }
+  {
+    Launch l(r, PC_TOKENIZE, 2.0 * M * C * C, (all_maps16(p) ? 2.0 : 4.0) * M * 4.0 * C + 6.0 * M * C, "lvit5_shrink M%d C%d", M, C);
+    l.sym("lvit5_shrink_tokens_kernel<96>");
+    lvit5_shrink_tokens_kernel<96><<<(4 * M + 127) / 128, 128, 0, r.st>>>(x, all_maps16(p) ? 1 : 0, r.nb, Hl, Hl, p->win, M, sh,
+                                                                        L.lws.t0, L.lws.x16);
+    CU(cudaGetLastError());
+  }
+  RET(run_vit(r, v, L.lws, r.nb * nwin));
+  {
+    Launch l(r, PC_TOKENIZE, 2.0 * M * C * C, 4.0 * M * C + 16.0 * M * C, "lvit5_extend M%d C%d", M, C);
+    l.sym("lvit5_extend_kernel<96>");
+    lvit5_extend_kernel<96><<<(4 * M + 127) / 128, 128, 0, r.st>>>(L.lws.t1, M, ex, L.lws.h);
+    CU(cudaGetLastError());
+  }
+  *tokens_out = L.lws.h;
+  return 0;
+}
+
 static int run_block(Run& r, int si, const float* x, float* out) {
   cfen_plan* p = r.p;
   Lane& L = *r.ln;
@@ -1331,6 +1404,13 @@ static int run_block(Run& r, int si, const float* x, float* out) {
     const int rc = run_vit(r, p->gvit[si], L.gws, r.nb);
     r.st = main_st;
     RET(rc);
+  }
+  if (p->v5) {
+    const float* local_tokens = nullptr;
+    RET(run_lvit5(r, si, x, Hl, C, nwin, &local_tokens));
+    RET(stream_edge(p, L.gst, main_st));
+    const std::string name5 = "lgcat_conv_" + stage_tag(kStages[si]);
+    return run_conv(r, name5, local_tokens, L.gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES);
   }
   if (front_fusable(p, p->lvit[si].E, r.nb * nwin * p->lvit[si].L)) {
     const FrontSrc src{x, Hl, Hl, C, p->win, all_maps16(p)};
@@ -1532,6 +1612,9 @@ static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void*
   if (batch < 0 || !in || !xd || (!only_d && (!xr || !xs))) return fail(1, "cfen_forward: bad argument");
   if (io & ~(CFEN_IO_U8 | CFEN_ONLY_FAKE_A)) return fail(1, "cfen_forward_ex: unknown io flag bits 0x%x", io);
   if (calibrate && io) return fail(1, "cfen_forward_calibrate takes fp32 tensors and produces all three outputs");
+  if (calibrate && p->v5)
+    return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: first-forward ActNorm initialisation is not available on the GPU (conv_shrink / "
+                   "conv_extend initialise on the top-left window only, v5.py:403): load initialised weights");
   if (calibrate && p->from_blob) return fail(8, "cfen_forward_calibrate: this plan was filled from a packed blob (no registered tensors to initialise)");
   if (u8 && !p->conv_path) return fail(3, "the fused uint8 boundary needs the conv16 generation (conv_path 1)");
   if (calibrate && batch > p->nbmax)
