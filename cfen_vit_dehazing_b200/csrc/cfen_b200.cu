@@ -320,6 +320,8 @@ static cudaError_t set_kernel_attributes() {
   if ((e = tail16_set_attr()) != cudaSuccess) return e;
   if ((e = tail16r_set_attr()) != cudaSuccess) return e;
   if ((e = front16_set_attr()) != cudaSuccess) return e;
+  if ((e = lvit5_set_attr<24>()) != cudaSuccess) return e;
+  if ((e = lvit5_set_attr<48>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1124,11 +1126,9 @@ static int run_attn16(Run& r, const __half* qkv, __half* o, int nseq, int L, int
     CU(launch_attention_tc(qkv, o, nseq, L, E, heads, r.st));
     return 0;
   }
-  if (E / heads == 6) {   // local ViTs of iid_hlgvit_crs_gd4_cfs_v5 (level 3)
-    if (L <= 0 || 256 % L != 0) return fail(3, "attention with 6-wide heads needs windows of 16 / 64 / 256 tokens (got %d)", L);
+  if (E / heads == 6) {   // local ViTs of iid_hlgvit_crs_gd4_cfs_v5
     l.sym("attention_hd6_kernel");
-    attention_hd6_kernel<<<(nseq * L + 255) / 256, 256, 0, r.st>>>(qkv, o, nseq * L, L, E);
-    CU(cudaGetLastError());
+    CU(launch_attention_hd6(qkv, o, nseq, L, E, r.st));
     return 0;
   }
   l.sym("attention16_kernel<%d>", E / heads);
@@ -1355,14 +1355,26 @@ static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, co
   const double flops = 2.0 * M * ((double)v.E * v.E * 5 + 4.0 * v.E * v.hid + 2.0 * v.L * v.E) + 4.0 * M * v.E * v.E;
   const double bytes = (all_maps16(p) ? 2.0 : 4.0) * M * 4.0 * C + 4.0 * M * 4.0 * C;
   if (C <= 48) {
+    if (v.L <= 0 || v.hid % 4 != 0) return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: unsupported local ViT geometry (L %d, hidden %d)", v.L, v.hid);
     Lvit5Args a{x, all_maps16(p) ? 1 : 0, r.nb, Hl, Hl, p->win, M, sh, ex, v.w_le, v.b_le, v.pos, v.ln1g, v.ln1b, v.w_in,
-                v.w_out, v.w1, v.b1, v.w2, v.b2, v.ln2g, v.ln2b, v.wm0, v.bm0, v.wm3, v.bm3, v.hid, L.lws.t1};
-    Launch l(r, PC_MLP, flops, bytes, "lvit5 M%d E%d hid%d", M, v.E, v.hid);
-    l.sym("lvit5_kernel<%d>", C);
-    const cudaError_t e = C == 24 ? launch_lvit5<24>(a, r.st) : launch_lvit5<48>(a, r.st);
-    if (e == cudaErrorInvalidConfiguration)
-      return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: windows of %d tokens are not supported (16 / 64 / 256)", v.L);
-    CU(e);
+                v.w_out, v.w1, v.b1, v.w2, v.b2, v.ln2g, v.ln2b, v.wm0, v.bm0, v.wm3, v.bm3, v.hid,
+                L.lws.t0, L.lws.qkv16, L.lws.o16, L.lws.t1};
+    const int blocks = (M + 255) / 256;
+    {
+      Launch l(r, PC_GEMM, 2.0 * M * (4.0 * v.E * v.E) + 2.0 * M * v.E * v.E, bytes / 2 + 10.0 * M * v.E, "lvit5_pre M%d E%d", M, v.E);
+      l.sym("lvit5_pre_kernel<%d>", C);
+      if (C == 24) lvit5_pre_kernel<24><<<blocks, 256, Lvit5Cfg<24>::SMEM, r.st>>>(a);
+      else lvit5_pre_kernel<48><<<blocks, 256, Lvit5Cfg<48>::SMEM, r.st>>>(a);
+      CU(cudaGetLastError());
+    }
+    RET(run_attn16(r, L.lws.qkv16, L.lws.o16, r.nb * nwin, v.L, v.E, v.heads));
+    {
+      Launch l(r, PC_MLP, 2.0 * M * (v.E * v.E + 4.0 * v.E * v.hid) + 2.0 * M * v.E * v.E, bytes / 2 + 6.0 * M * v.E, "lvit5_post M%d E%d hid%d", M, v.E, v.hid);
+      l.sym("lvit5_post_kernel<%d>", C);
+      if (C == 24) lvit5_post_kernel<24><<<blocks, 256, Lvit5Cfg<24>::SMEM, r.st>>>(a);
+      else lvit5_post_kernel<48><<<blocks, 256, Lvit5Cfg<48>::SMEM, r.st>>>(a);
+      CU(cudaGetLastError());
+    }
     *tokens_out = L.lws.t1;
     return 0;
   }
