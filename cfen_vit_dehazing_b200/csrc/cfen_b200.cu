@@ -1357,22 +1357,25 @@ static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, co
   if (C <= 48) {
     if (v.L <= 0 || v.hid % 4 != 0) return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: unsupported local ViT geometry (L %d, hidden %d)", v.L, v.hid);
     Lvit5Args a{x, all_maps16(p) ? 1 : 0, r.nb, Hl, Hl, p->win, M, sh, ex, v.w_le, v.b_le, v.pos, v.ln1g, v.ln1b, v.w_in,
-                v.w_out, v.w1, v.b1, v.w2, v.b2, v.ln2g, v.ln2b, v.wm0, v.bm0, v.wm3, v.bm3, v.hid,
+                v.w_out, v.w1, v.b1, v.w2, v.b2, v.ln2g, v.ln2b, v.wm0, v.bm0, v.wm3, v.bm3,
+                v.h_le, v.h_in, v.h_out, v.h_1, v.h_2, v.h_m0, v.h_m3, v.hid,
                 L.lws.t0, L.lws.qkv16, L.lws.o16, L.lws.t1};
-    const int blocks = (M + 255) / 256;
+    if (v.hid % 16 != 0 || v.hid > 4 * v.E) return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: hidden width %d is not supported", v.hid);
+    const int tiles = (M + 127) / 128;
+    const int blocks = tiles < 2 * 148 ? tiles : 2 * 148;   // persistent over 128-token tiles: the weights are staged once
     {
       Launch l(r, PC_GEMM, 2.0 * M * (4.0 * v.E * v.E) + 2.0 * M * v.E * v.E, bytes / 2 + 10.0 * M * v.E, "lvit5_pre M%d E%d", M, v.E);
       l.sym("lvit5_pre_kernel<%d>", C);
-      if (C == 24) lvit5_pre_kernel<24><<<blocks, 256, Lvit5Cfg<24>::SMEM, r.st>>>(a);
-      else lvit5_pre_kernel<48><<<blocks, 256, Lvit5Cfg<48>::SMEM, r.st>>>(a);
+      if (C == 24) lvit5_pre_kernel<24><<<blocks, 256, Lvit5Cfg<24>::pre_smem(), r.st>>>(a);
+      else lvit5_pre_kernel<48><<<blocks, 256, Lvit5Cfg<48>::pre_smem(), r.st>>>(a);
       CU(cudaGetLastError());
     }
     RET(run_attn16(r, L.lws.qkv16, L.lws.o16, r.nb * nwin, v.L, v.E, v.heads));
     {
       Launch l(r, PC_MLP, 2.0 * M * (v.E * v.E + 4.0 * v.E * v.hid) + 2.0 * M * v.E * v.E, bytes / 2 + 6.0 * M * v.E, "lvit5_post M%d E%d hid%d", M, v.E, v.hid);
       l.sym("lvit5_post_kernel<%d>", C);
-      if (C == 24) lvit5_post_kernel<24><<<blocks, 256, Lvit5Cfg<24>::SMEM, r.st>>>(a);
-      else lvit5_post_kernel<48><<<blocks, 256, Lvit5Cfg<48>::SMEM, r.st>>>(a);
+      if (C == 24) lvit5_post_kernel<24><<<blocks, 256, Lvit5Cfg<24>::post_smem(v.hid), r.st>>>(a);
+      else lvit5_post_kernel<48><<<blocks, 256, Lvit5Cfg<48>::post_smem(v.hid), r.st>>>(a);
       CU(cudaGetLastError());
     }
     *tokens_out = L.lws.t1;

@@ -7,18 +7,17 @@
 //
 // E = 24 / 48 / 96 on the three levels with 6-wide heads: no tensor-core tile of the v3 kernels fits (their UMMA / mma
 // K-steps are 16 deep, their LayerNorm spans the padded width), and the whole call is 16x cheaper than the v3 local ViT it
-// replaces.  Levels 1 and 2 run as two CUDA-core kernels around a tensor-core attention: lvit5_pre_kernel<E> (conv_shrink,
-// linear_encoding + pos, LayerNorm1, in-projection) -> attention_hd6_kernel -> lvit5_post_kernel<E> (out-projection,
-// LayerNorm2 + FFN, mlp_head, conv_extend).  A thread owns a token; its residual stream and LayerNorm output sit in shared
-// memory as [feature][token] columns (conflict-free, no synchronisation: nobody else reads them), every weight is a
-// warp-uniform (broadcast) load of the plan's packed fp32 copy; only t (fp32), q|k|v and the attention output (fp16) pass
-// through HBM between the kernels.  (A first version kept K / V in shared memory and did the attention per thread on CUDA
-// cores: 11 ms per call, 85 % of it in the attention loop.)  Level 3 (E = 96) runs the v3 token kernels on a token matrix
-// between lvit5_shrink_tokens_kernel and lvit5_extend_kernel, with the same attention_hd6_kernel.
+// replaces.  Levels 1 and 2 run as three mma.sync kernels: lvit5_pre_kernel<E> (conv_shrink, linear_encoding + pos,
+// LayerNorm1, in-projection) -> attention_hd6_kernel -> lvit5_post_kernel<E> (out-projection, LayerNorm2 + FFN, mlp_head,
+// conv_extend).  In pre / post a warp owns 16 tokens whose residual stream never leaves its registers; only t (fp32),
+// q|k|v and the attention output (fp16) pass through HBM between the kernels.  (History, one B200, 64 images, level 1:
+// one CUDA-core kernel with K / V in shared memory and a thread per token 11 ms per call; split around the tensor-core
+// attention, still a thread per token, 3.3 ms; these kernels: see DESIGN.md.)  Level 3 (E = 96) runs the v3 token
+// kernels on a token matrix between lvit5_shrink_tokens_kernel and lvit5_extend_kernel, with the same attention.
 //
 // Token row m = ((b*ny + wy)*nx + wx)*L + ty*(win/2) + tx and feature (ky, kx, c') inside a row, as everywhere in the plan;
 // the output is the [M, 4C] fp32 token matrix the local / global merge convolution reads (conv16.cuh, LD_LG).
-// fp32 arithmetic throughout (weights are the plan's TF32-rounded packed copies).
+// fp16 operands (the plan's packed fp16 weight copies), fp32 accumulation, LayerNorm and residual stream, as in the v3 kernels.
 #pragma once
 #include "attn16.cuh"   // mma.sync m16n8k16 / ldmatrix helpers
 
@@ -39,6 +38,7 @@ struct Lvit5Args {
   Lvit5Conv shrink, extend;
   // packed fp32 ViT weights, feature order (ky, kx, c') (cfen_plan_pack_weights)
   const float *w_le, *b_le, *pos, *ln1g, *ln1b, *w_in, *w_out, *w1, *b1, *w2, *b2, *ln2g, *ln2b, *wm0, *bm0, *wm3, *bm3;
+  const __half *h_le, *h_in, *h_out, *h_1, *h_2, *h_m0, *h_m3;   // fp16 operand copies of the same matrices, [N][K]
   int hid;
   float* t;                 // [M, E] fp32 residual stream between the two halves
   __half* qkv16;            // [M, 3E] packed in-projection (pre kernel -> attention)
@@ -82,73 +82,134 @@ __device__ __forceinline__ void lvit5_pointwise(const Lvit5Conv& cv, const float
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// levels 1 and 2: the whole call in one kernel
+// levels 1 and 2: two tensor-core kernels around the attention
 // ------------------------------------------------------------------------------------------------------------------
+// A warp owns 16 tokens; every Linear is a chain of mma.sync m16n8k16 (fp16 operands, fp32 accumulate) whose A operand is
+// built in registers from the previous accumulator (the C layout of two adjacent 8-column tiles IS the A layout of one
+// 16-deep step) and whose B operand comes by ldmatrix from the CTA's shared-memory copy of the weights ([N][K] rows,
+// zero-padded to 16-deep steps, +8 halves of row padding: conflict-free).  conv_shrink / conv_extend run as block-diagonal
+// Linears over the token's four pixels.  CTAs are persistent over 128-token tiles so the weights are staged once.
 template <int E>
 struct Lvit5Cfg {
-  static constexpr int T = 256;                 // tokens (= threads) per CTA
-  static constexpr int CQ = E / 4;              // channels of the shrunk map
-  static constexpr size_t SMEM = (size_t)2 * E * T * sizeof(float);   // two [E][T] fp32 token tiles
+  static constexpr int WARPS = 8, TOK = 16 * WARPS, THREADS = 32 * WARPS;
+  static constexpr int CQ = E / 4;                 // channels of the shrunk map
+  static constexpr int NT = E / 8;                 // 8-column tiles of an E-wide row (3 / 6)
+  static constexpr int KS = (E + 15) / 16;         // 16-deep steps of an E-deep contraction (2 / 3)
+  static constexpr int LDE = KS * 16 + 8;          // shared row stride (halves) of a weight with K = E
+  static constexpr int KS4 = 4 * E / 16;           // steps over the token's four pixels (conv_shrink)
+  static constexpr int LD4 = 4 * E + 8;
   static_assert(E % 24 == 0, "6-wide heads on 4 x C/4 features");
+  static size_t pre_smem() { return ((size_t)E * LD4 + (size_t)E * LDE + (size_t)3 * E * LDE) * sizeof(__half); }
+  static size_t post_smem(int hid) {
+    return ((size_t)E * LDE + (size_t)2 * hid * LDE + (size_t)2 * E * (hid + 8) + (size_t)4 * E * LDE) * sizeof(__half);
+  }
 };
 
-// acc[NC] = sum_k W[n0 + u][k] * in[k][tid]  (W row-major [N][K], K % 4 == 0; `in` is a [K][T] shared buffer)
-template <int NC, int K>
-__device__ __forceinline__ void lvit5_dot(const float* __restrict__ W, int n0, const float* in, int tid, float (&acc)[NC]) {
-#pragma unroll 1
-  for (int k = 0; k < K; k += 4) {
-    const float x0 = in[(k + 0) * 256 + tid], x1 = in[(k + 1) * 256 + tid], x2 = in[(k + 2) * 256 + tid],
-                x3 = in[(k + 3) * 256 + tid];
+// c[NT][4] += A(16 x 16 KS) * W^T for NT column tiles; W points at the first of the NT * 8 weight rows
+template <int KS, int NT>
+__device__ __forceinline__ void lvit5_mma(const uint32_t (&a)[KS][4], const __half* W, int ldw, float (&c)[NT][4], int lane) {
+  const int lm_id = lane >> 3, lm_row = lane & 7;
 #pragma unroll
-    for (int u = 0; u < NC; ++u) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + u) * K + k));
-      acc[u] = fmaf(w4.x, x0, fmaf(w4.y, x1, fmaf(w4.z, x2, fmaf(w4.w, x3, acc[u]))));
+  for (int j = 0; j + 1 < NT; j += 2)
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      uint32_t b[4];
+      ldmatrix_x4(b, W + ((j + (lm_id >> 1)) * 8 + lm_row) * ldw + kk * 16 + (lm_id & 1) * 8);
+      mma_f16_16x8x16(c[j], a[kk], b[0], b[1]);
+      mma_f16_16x8x16(c[j + 1], a[kk], b[2], b[3]);
+    }
+  if (NT & 1) {
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      uint32_t b[2];
+      ldmatrix_x2(b, W + ((NT - 1) * 8 + lm_row) * ldw + kk * 16 + (lm_id & 1) * 8);
+      mma_f16_16x8x16(c[NT - 1], a[kk], b[0], b[1]);
     }
   }
 }
-
-// LayerNorm of the thread's column of `src` into `dst`
-template <int E>
-__device__ __forceinline__ void lvit5_layernorm(const float* src, float* dst, int tid, const float* g, const float* b) {
-  float s = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < E; ++k) s += src[k * 256 + tid];
-  const float mean = s / (float)E;
-  float q = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < E; ++k) {
-    const float d = src[k * 256 + tid] - mean;
-    q = fmaf(d, d, q);
-  }
-  const float rstd = rsqrtf(q / (float)E + 1e-5f);
-#pragma unroll 4
-  for (int k = 0; k < E; ++k) dst[k * 256 + tid] = (src[k * 256 + tid] - mean) * rstd * __ldg(g + k) + __ldg(b + k);
-}
-
-// X += b2 + W2 relu(W1 in + b1): hidden units in groups of four, never stored (in == X is allowed: it is only read
-// before the final write)
-template <int E>
-__device__ __forceinline__ void lvit5_mlp(const float* in, float* X, int tid, const float* __restrict__ W1,
-                                          const float* __restrict__ b1, const float* __restrict__ W2,
-                                          const float* __restrict__ b2, int hid) {
-  float acc[E];
+// the accumulator tiles as the (fp16) A operand of the next contraction; columns beyond NT * 8 are zero
+template <int NT, int KS>
+__device__ __forceinline__ void lvit5_c2a(const float (&c)[NT][4], uint32_t (&a)[KS][4]) {
 #pragma unroll
-  for (int n = 0; n < E; ++n) acc[n] = X[n * 256 + tid] + __ldg(b2 + n);
-#pragma unroll 1
-  for (int j = 0; j < hid; j += 4) {
-    float h[4] = {__ldg(b1 + j), __ldg(b1 + j + 1), __ldg(b1 + j + 2), __ldg(b1 + j + 3)};
-    lvit5_dot<4, E>(W1, j, in, tid, h);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) h[u] = fmaxf(h[u], 0.f);
-#pragma unroll
-    for (int n = 0; n < E; ++n) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(W2 + (size_t)n * hid + j));
-      acc[n] = fmaf(w4.x, h[0], fmaf(w4.y, h[1], fmaf(w4.z, h[2], fmaf(w4.w, h[3], acc[n]))));
+  for (int kk = 0; kk < KS; ++kk) {
+    a[kk][0] = pack_half2(c[2 * kk][0], c[2 * kk][1]);
+    a[kk][1] = pack_half2(c[2 * kk][2], c[2 * kk][3]);
+    if (2 * kk + 1 < NT) {
+      a[kk][2] = pack_half2(c[2 * kk + 1][0], c[2 * kk + 1][1]);
+      a[kk][3] = pack_half2(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+    } else {
+      a[kk][2] = 0u; a[kk][3] = 0u;
     }
   }
-  __syncwarp();
+}
+// rows g / g + 8 of the warp's tile: LayerNorm over the E columns the four lanes of a row share, result as A operand
+template <int NT, int KS>
+__device__ __forceinline__ void lvit5_ln_a(const float (&c)[NT][4], const float* __restrict__ gam, const float* __restrict__ bet,
+                                           int t, uint32_t (&a)[KS][4]) {
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int n = 0; n < E; ++n) X[n * 256 + tid] = acc[n];
+  for (int n = 0; n < NT; ++n) { s0 += c[n][0] + c[n][1]; s1 += c[n][2] + c[n][3]; }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float mean0 = s0 / (float)(NT * 8), mean1 = s1 / (float)(NT * 8);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    q0 += (c[n][0] - mean0) * (c[n][0] - mean0) + (c[n][1] - mean0) * (c[n][1] - mean0);
+    q1 += (c[n][2] - mean1) * (c[n][2] - mean1) + (c[n][3] - mean1) * (c[n][3] - mean1);
+  }
+  q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  const float r0 = rsqrtf(q0 / (float)(NT * 8) + 1e-5f), r1 = rsqrtf(q1 / (float)(NT * 8) + 1e-5f);
+  float h[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + n * 8 + 2 * t));
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bet + n * 8 + 2 * t));
+    h[n][0] = (c[n][0] - mean0) * r0 * gg.x + bb.x; h[n][1] = (c[n][1] - mean0) * r0 * gg.y + bb.y;
+    h[n][2] = (c[n][2] - mean1) * r1 * gg.x + bb.x; h[n][3] = (c[n][3] - mean1) * r1 * gg.y + bb.y;
+  }
+  lvit5_c2a<NT, KS>(h, a);
+}
+// stage a [N][K] fp16 weight (K % 8 == 0) into shared rows of `ld` halves, zero beyond K
+__device__ __forceinline__ void lvit5_stage(__half* dst, const __half* __restrict__ src, int N, int K, int ld, int tid, int nthr) {
+  const int c8 = ld / 8;
+  for (int i = tid; i < N * c8; i += nthr) {
+    const int r = i / c8, c = i - r * c8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c * 8 < K) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * K + c * 8));
+    *reinterpret_cast<uint4*>(dst + r * ld + c * 8) = v;
+  }
+}
+// t += b2 + W2 relu(W1 A + b1): the hidden layer in groups of 16 units that never leave registers
+template <int E>
+__device__ __forceinline__ void lvit5_mlp_tc(const uint32_t (&a)[Lvit5Cfg<E>::KS][4], const __half* W1s, const __half* W2s, int hid,
+                                             const float* __restrict__ b1, const float* __restrict__ b2,
+                                             float (&tacc)[Lvit5Cfg<E>::NT][4], int lane) {
+  using Cfg = Lvit5Cfg<E>;
+  const int t = lane & 3;
+#pragma unroll 1
+  for (int j0 = 0; j0 < hid; j0 += 16) {
+    float c1[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(b1 + j0 + n * 8 + 2 * t));
+      c1[n][0] = bb.x; c1[n][1] = bb.y; c1[n][2] = bb.x; c1[n][3] = bb.y;
+    }
+    lvit5_mma<Cfg::KS, 2>(a, W1s + (size_t)j0 * Cfg::LDE, Cfg::LDE, c1, lane);
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c1[n][e] = fmaxf(c1[n][e], 0.f);
+    uint32_t ah[1][4];
+    lvit5_c2a<2, 1>(c1, ah);
+    lvit5_mma<1, Cfg::NT>(ah, W2s + j0, hid + 8, tacc, lane);
+  }
+#pragma unroll
+  for (int n = 0; n < Cfg::NT; ++n) {
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(b2 + n * 8 + 2 * t));
+    tacc[n][0] += bb.x; tacc[n][1] += bb.y; tacc[n][2] += bb.x; tacc[n][3] += bb.y;
+  }
 }
 
 // ---- first half: conv_shrink, linear_encoding + pos, LayerNorm1, in-projection.  Leaves t [M, E] (fp32) and the packed
@@ -157,59 +218,107 @@ template <int E>
 __global__ void __launch_bounds__(256)
 lvit5_pre_kernel(const Lvit5Args a) {
   using Cfg = Lvit5Cfg<E>;
-  constexpr int T = Cfg::T, CQ = Cfg::CQ;
-  extern __shared__ __align__(16) float lv_smem[];
-  float* X = lv_smem;                 // [E][T] token / residual stream t (a thread only touches its own column)
-  float* Hb = X + E * T;              // [E][T] LayerNorm output
-  const int tid = threadIdx.x;
-  const int m = blockIdx.x * T + tid;
-  const bool live = m < a.M;
-  int b = 0, py = 0, px = 0, l = 0;
-  lvit5_token_pixel(live ? m : 0, a.H, a.W, a.win, b, py, px, l);
-
-  // ---- conv_shrink on the token's four pixels -> X (token features (ky, kx, c'))
-#pragma unroll 1
-  for (int pq = 0; pq < 4; ++pq) {
-    float xin[E];   // C = E channels of one pixel
-    const size_t pix = ((size_t)b * a.H + py + (pq >> 1)) * a.W + px + (pq & 1);
-#pragma unroll
-    for (int c4 = 0; c4 < E / 4; ++c4) {
-      const float4 v = live ? ld_map4(a.map, (pix * E + 4 * c4) >> 2, a.h16 != 0) : make_float4(0.f, 0.f, 0.f, 0.f);
-      xin[4 * c4] = v.x; xin[4 * c4 + 1] = v.y; xin[4 * c4 + 2] = v.z; xin[4 * c4 + 3] = v.w;
-    }
-    lvit5_pointwise<E, CQ>(a.shrink, xin, [&](int n, float v) { X[(pq * CQ + n) * T + tid] = v; });
+  constexpr int NT = Cfg::NT, KS = Cfg::KS, LDE = Cfg::LDE, KS4 = Cfg::KS4, LD4 = Cfg::LD4, CQ = Cfg::CQ;
+  extern __shared__ __align__(16) __half lv_smem[];
+  __half* Wsh = lv_smem;               // [E][LD4]   block-diagonal conv_shrink: row pq*CQ + c', column pq*C + c
+  __half* Wle = Wsh + E * LD4;         // [E][LDE]
+  __half* Win = Wle + E * LDE;         // [3E][LDE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < E * LD4 / 2; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(Wsh)[i] = 0u;
+  lvit5_stage(Wle, a.h_le, E, E, LDE, tid, Cfg::THREADS);
+  lvit5_stage(Win, a.h_in, 3 * E, E, LDE, tid, Cfg::THREADS);
+  __syncthreads();
+  for (int i = tid; i < 4 * CQ * E; i += Cfg::THREADS) {   // (pq, c', c)
+    const int c = i % E, r = i / E, cq = r % CQ, pq = r / CQ;
+    Wsh[(pq * CQ + cq) * LD4 + pq * E + c] = __float2half_rn(__ldg(a.shrink.w + cq * E + c));
   }
+  __syncthreads();
 
-  // ---- t = x + (W_le x + b_le) + pos  -> Hb (and HBM), then the buffers swap roles
-  {
-    const float* posrow = a.pos + (size_t)l * E;
-    float* trow = a.t + (size_t)(live ? m : 0) * E;
+  const int ntiles = (a.M + Cfg::TOK - 1) / Cfg::TOK;
+  const int L = (a.win >> 1) * (a.win >> 1);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m0 = tile * Cfg::TOK + warp * 16;
+    const int mr[2] = {m0 + g, m0 + g + 8};
+    const bool live[2] = {mr[0] < a.M, mr[1] < a.M};
+    size_t pbase[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      int b, py, px, l;
+      lvit5_token_pixel(live[r] ? mr[r] : 0, a.H, a.W, a.win, b, py, px, l);
+      pbase[r] = (((size_t)b * a.H + py) * a.W + px) * E;   // element offset of the token's top-left pixel
+    }
+    // ---- A operand: the token's four pixels as a 4E-wide row (pixels (ky, 0), (ky, 1) are contiguous in NHWC)
+    uint32_t am[KS4][4];
+#pragma unroll
+    for (int kk = 0; kk < KS4; ++kk)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col = kk * 16 + hh * 8 + 2 * t;
+        const int ky = col / (2 * E), rem = col - ky * 2 * E;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          uint32_t v = 0u;
+          if (live[r]) {
+            const size_t off = pbase[r] + (size_t)ky * a.W * E + rem;
+            if (a.h16) v = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(a.map) + off));
+            else { const float2 f = __ldg(reinterpret_cast<const float2*>(a.map + off)); v = pack_half2(f.x, f.y); }
+          }
+          am[kk][hh * 2 + r] = v;
+        }
+      }
+    // ---- conv_shrink (+ bias, ActNorm, ReLU) -> token features (ky, kx, c')
+    float tok[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tok[n][e] = 0.f;
+    lvit5_mma<KS4, NT>(am, Wsh, LD4, tok, lane);
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cq = (n * 8 + 2 * t + e) % CQ;
+        const float bb = __ldg(a.shrink.b + cq) + __ldg(a.shrink.an_b + cq), sc = __expf(__ldg(a.shrink.an_w + cq));
+        tok[n][e] = fmaxf((tok[n][e] + bb) * sc, 0.f);
+        tok[n][e + 2] = fmaxf((tok[n][e + 2] + bb) * sc, 0.f);
+      }
+    // ---- t = x + (W_le x + b_le) + pos
+    uint32_t ax[KS][4];
+    lvit5_c2a<NT, KS>(tok, ax);
+    const float* pos0 = a.pos + (size_t)((live[0] ? mr[0] : 0) % L) * E;
+    const float* pos1 = a.pos + (size_t)((live[1] ? mr[1] : 0) % L) * E;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(a.b_le + n * 8 + 2 * t));
+      const float2 p0 = __ldg(reinterpret_cast<const float2*>(pos0 + n * 8 + 2 * t));
+      const float2 p1 = __ldg(reinterpret_cast<const float2*>(pos1 + n * 8 + 2 * t));
+      tok[n][0] += bb.x + p0.x; tok[n][1] += bb.y + p0.y; tok[n][2] += bb.x + p1.x; tok[n][3] += bb.y + p1.y;
+    }
+    lvit5_mma<KS, NT>(ax, Wle, LDE, tok, lane);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      if (live[0]) *reinterpret_cast<float2*>(a.t + (size_t)mr[0] * E + n * 8 + 2 * t) = make_float2(tok[n][0], tok[n][1]);
+      if (live[1]) *reinterpret_cast<float2*>(a.t + (size_t)mr[1] * E + n * 8 + 2 * t) = make_float2(tok[n][2], tok[n][3]);
+    }
+    // ---- q | k | v = W_in LayerNorm1(t)
+    uint32_t ah[KS][4];
+    lvit5_ln_a<NT, KS>(tok, a.ln1g, a.ln1b, t, ah);
 #pragma unroll 1
-    for (int n0 = 0; n0 < E; n0 += 8) {
-      float acc[8];
+    for (int part = 0; part < 3; ++part) {
+      float c[NT][4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = X[(n0 + u) * T + tid] + __ldg(a.b_le + n0 + u) + __ldg(posrow + n0 + u);
-      lvit5_dot<8, E>(a.w_le, n0, X, tid, acc);
+      for (int n = 0; n < NT; ++n)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) Hb[(n0 + u) * T + tid] = acc[u];
-      if (live) {
-        *reinterpret_cast<float4*>(trow + n0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(trow + n0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        for (int e = 0; e < 4; ++e) c[n][e] = 0.f;
+      lvit5_mma<KS, NT>(ah, Win + (size_t)part * E * LDE, LDE, c, lane);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int col = part * E + n * 8 + 2 * t;
+        if (live[0]) *reinterpret_cast<uint32_t*>(a.qkv16 + (size_t)mr[0] * 3 * E + col) = pack_half2(c[n][0], c[n][1]);
+        if (live[1]) *reinterpret_cast<uint32_t*>(a.qkv16 + (size_t)mr[1] * 3 * E + col) = pack_half2(c[n][2], c[n][3]);
       }
     }
-    float* tmp = X; X = Hb; Hb = tmp;
-  }
-
-  // ---- h = LayerNorm1(t); q | k | v = W_in h
-  lvit5_layernorm<E>(X, Hb, tid, a.ln1g, a.ln1b);
-  __half* qrow = a.qkv16 + (size_t)(live ? m : 0) * 3 * E;
-#pragma unroll 1
-  for (int n0 = 0; n0 < 3 * E; n0 += 8) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    lvit5_dot<8, E>(a.w_in, n0, Hb, tid, acc);
-    if (live)
-      *reinterpret_cast<uint4*>(qrow + n0) = make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                                                        pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
   }
 }
 
@@ -218,64 +327,92 @@ template <int E>
 __global__ void __launch_bounds__(256)
 lvit5_post_kernel(const Lvit5Args a) {
   using Cfg = Lvit5Cfg<E>;
-  constexpr int T = Cfg::T, CQ = Cfg::CQ;
-  extern __shared__ __align__(16) float lv_smem[];
-  float* X = lv_smem;                 // [E][T] residual stream t
-  float* Hb = X + E * T;              // [E][T] attention output, then LayerNorm output
-  const int tid = threadIdx.x;
-  const int m = blockIdx.x * T + tid;
-  const bool live = m < a.M;
-  {
-    const float4* trow = reinterpret_cast<const float4*>(a.t + (size_t)(live ? m : 0) * E);
-    const uint4* orow = reinterpret_cast<const uint4*>(a.o16 + (size_t)(live ? m : 0) * E);
+  constexpr int NT = Cfg::NT, KS = Cfg::KS, LDE = Cfg::LDE, CQ = Cfg::CQ;
+  extern __shared__ __align__(16) __half lv_smem[];
+  const int hid = a.hid, ld2 = hid + 8;
+  __half* Wo = lv_smem;                  // [E][LDE]
+  __half* W1 = Wo + E * LDE;             // [hid][LDE]
+  __half* Wm0 = W1 + (size_t)hid * LDE;  // [hid][LDE]
+  __half* W2 = Wm0 + (size_t)hid * LDE;  // [E][hid + 8]
+  __half* Wm3 = W2 + (size_t)E * ld2;    // [E][hid + 8]
+  __half* Wex = Wm3 + (size_t)E * ld2;   // [4E][LDE]  block-diagonal conv_extend: row pq*C + c, column pq*CQ + c'
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  lvit5_stage(Wo, a.h_out, E, E, LDE, tid, Cfg::THREADS);
+  lvit5_stage(W1, a.h_1, hid, E, LDE, tid, Cfg::THREADS);
+  lvit5_stage(Wm0, a.h_m0, hid, E, LDE, tid, Cfg::THREADS);
+  lvit5_stage(W2, a.h_2, E, hid, ld2, tid, Cfg::THREADS);
+  lvit5_stage(Wm3, a.h_m3, E, hid, ld2, tid, Cfg::THREADS);
+  for (int i = tid; i < 4 * E * LDE / 2; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(Wex)[i] = 0u;
+  __syncthreads();
+  for (int i = tid; i < 4 * E * CQ; i += Cfg::THREADS) {   // (pq, c, c')
+    const int cq = i % CQ, r = i / CQ, c = r % E, pq = r / E;
+    Wex[(pq * E + c) * LDE + pq * CQ + cq] = __float2half_rn(__ldg(a.extend.w + c * CQ + cq));
+  }
+  __syncthreads();
+
+  const int ntiles = (a.M + Cfg::TOK - 1) / Cfg::TOK;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m0 = tile * Cfg::TOK + warp * 16;
+    const int mr[2] = {m0 + g, m0 + g + 8};
+    const bool live[2] = {mr[0] < a.M, mr[1] < a.M};
+    // ---- attention output as A operand, residual stream t as accumulator
+    uint32_t ao[KS][4];
 #pragma unroll
-    for (int k4 = 0; k4 < E / 4; ++k4) {
-      const float4 v = live ? trow[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
-      X[(4 * k4) * T + tid] = v.x; X[(4 * k4 + 1) * T + tid] = v.y; X[(4 * k4 + 2) * T + tid] = v.z; X[(4 * k4 + 3) * T + tid] = v.w;
-    }
+    for (int kk = 0; kk < KS; ++kk)
 #pragma unroll
-    for (int k8 = 0; k8 < E / 8; ++k8) {
-      const uint4 u = live ? orow[k8] : make_uint4(0u, 0u, 0u, 0u);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col = kk * 16 + hh * 8 + 2 * t;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-        Hb[(8 * k8 + 2 * i) * T + tid] = f.x; Hb[(8 * k8 + 2 * i + 1) * T + tid] = f.y;
+        for (int r = 0; r < 2; ++r)
+          ao[kk][hh * 2 + r] = (live[r] && col < E) ? __ldg(reinterpret_cast<const uint32_t*>(a.o16 + (size_t)mr[r] * E + col)) : 0u;
       }
+    float tt[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float2 v0 = live[0] ? *reinterpret_cast<const float2*>(a.t + (size_t)mr[0] * E + n * 8 + 2 * t) : make_float2(0.f, 0.f);
+      const float2 v1 = live[1] ? *reinterpret_cast<const float2*>(a.t + (size_t)mr[1] * E + n * 8 + 2 * t) : make_float2(0.f, 0.f);
+      tt[n][0] = v0.x; tt[n][1] = v0.y; tt[n][2] = v1.x; tt[n][3] = v1.y;
     }
-  }
-  // ---- t += W_out o
-#pragma unroll 1
-  for (int n0 = 0; n0 < E; n0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = X[(n0 + u) * T + tid];
-    lvit5_dot<8, E>(a.w_out, n0, Hb, tid, acc);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) X[(n0 + u) * T + tid] = acc[u];
-  }
-  // ---- t += FFN(LayerNorm2(t)); t += mlp_head(t)
-  lvit5_layernorm<E>(X, Hb, tid, a.ln2g, a.ln2b);
-  lvit5_mlp<E>(Hb, X, tid, a.w1, a.b1, a.w2, a.b2, a.hid);
-  lvit5_mlp<E>(X, X, tid, a.wm0, a.bm0, a.wm3, a.bm3, a.hid);
-  // ---- conv_extend on the four pixels of the folded token -> output token row (ky, kx, c)
-  if (live) {
-    float* orow = a.out + (size_t)m * 4 * E;
+    lvit5_mma<KS, NT>(ao, Wo, LDE, tt, lane);                       // t += W_out o
+    uint32_t ah[KS][4];
+    lvit5_ln_a<NT, KS>(tt, a.ln2g, a.ln2b, t, ah);
+    lvit5_mlp_tc<E>(ah, W1, W2, hid, a.b1, a.b2, tt, lane);         // t += FFN(LayerNorm2(t))
+    lvit5_c2a<NT, KS>(tt, ah);
+    lvit5_mlp_tc<E>(ah, Wm0, Wm3, hid, a.bm0, a.bm3, tt, lane);     // t += mlp_head(t)
+    // ---- conv_extend (+ bias, ActNorm, ReLU) on the four pixels of the folded token -> output row (ky, kx, c)
+    lvit5_c2a<NT, KS>(tt, ah);
 #pragma unroll 1
     for (int pq = 0; pq < 4; ++pq) {
-      float z[CQ];
+      float c[NT][4];
 #pragma unroll
-      for (int c = 0; c < CQ; ++c) z[c] = X[(pq * CQ + c) * T + tid];
-      lvit5_pointwise<CQ, E>(a.extend, z, [&](int n, float v) { orow[pq * E + n] = v; });
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[n][e] = 0.f;
+      lvit5_mma<KS, NT>(ah, Wex + (size_t)pq * E * LDE, LDE, c, lane);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int ch = n * 8 + 2 * t;
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(a.extend.b + ch));
+        const float2 ab = __ldg(reinterpret_cast<const float2*>(a.extend.an_b + ch));
+        const float2 aw = __ldg(reinterpret_cast<const float2*>(a.extend.an_w + ch));
+        const float s0 = __expf(aw.x), s1 = __expf(aw.y);
+        if (live[0])
+          *reinterpret_cast<float2*>(a.out + (size_t)mr[0] * 4 * E + pq * E + ch) =
+              make_float2(fmaxf((c[n][0] + bb.x + ab.x) * s0, 0.f), fmaxf((c[n][1] + bb.y + ab.y) * s1, 0.f));
+        if (live[1])
+          *reinterpret_cast<float2*>(a.out + (size_t)mr[1] * 4 * E + pq * E + ch) =
+              make_float2(fmaxf((c[n][2] + bb.x + ab.x) * s0, 0.f), fmaxf((c[n][3] + bb.y + ab.y) * s1, 0.f));
+      }
     }
   }
 }
 
 template <int E>
 inline cudaError_t lvit5_set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(lvit5_pre_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lvit5Cfg<E>::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(lvit5_pre_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lvit5Cfg<E>::pre_smem());
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(lvit5_post_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lvit5Cfg<E>::SMEM);
+  return cudaFuncSetAttribute(lvit5_post_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lvit5Cfg<E>::post_smem(4 * E));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
