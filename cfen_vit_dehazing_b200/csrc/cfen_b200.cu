@@ -389,6 +389,7 @@ struct cfen_plan {
   VitW lvit[12], gvit[12];
   bool v5 = false;                       // iid_hlgvit_crs_gd4_cfs_v5: quarter-width local ViTs (lvit5.cuh)
   float *v5_shrink[12][4] = {}, *v5_extend[12][4] = {};   // arena copies of conv_shrink / conv_extend {w, b, an_w, an_b}
+  float* v5_reg[12][2][2] = {};          // the caller's ActNorm {weight, bias} of shrink / extend (calibration writes them)
   std::map<std::string, ConvLayer> conv;
   float* cfsm_w[2] = {nullptr, nullptr};  // d03d (C=48), d02d (C=24): 8 weights concatenated
   float* ones = nullptr;
@@ -873,8 +874,10 @@ extern "C" int32_t cfen_plan_pack_weights(cfen_plan* p, void* stream) {
           const float* src;
           RET(lookup(p, pre + ".conv_shrink" + kSfx[k], k == 0 ? (int64_t)Cq * Cf : Cq, &src));
           CU(cudaMemcpyAsync(p->v5_shrink[i][k], src, sizeof(float) * (k == 0 ? (size_t)Cq * Cf : Cq), cudaMemcpyDeviceToDevice, st));
+          if (k >= 2) p->v5_reg[i][0][k - 2] = const_cast<float*>(src);
           RET(lookup(p, pre + ".conv_extend" + kSfx[k], k == 0 ? (int64_t)Cq * Cf : Cf, &src));
           CU(cudaMemcpyAsync(p->v5_extend[i][k], src, sizeof(float) * (k == 0 ? (size_t)Cq * Cf : Cf), cudaMemcpyDeviceToDevice, st));
+          if (k >= 2) p->v5_reg[i][1][k - 2] = const_cast<float*>(src);
         }
       }
     }
@@ -1352,6 +1355,19 @@ static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, co
   const int M = r.nb * nwin * v.L;
   const Lvit5Conv sh{p->v5_shrink[si][0], p->v5_shrink[si][1], p->v5_shrink[si][2], p->v5_shrink[si][3]};
   const Lvit5Conv ex{p->v5_extend[si][0], p->v5_extend[si][1], p->v5_extend[si][2], p->v5_extend[si][3]};
+  const bool cal = p->calibrating;
+  const int rows_per_image = nwin * v.L, Cq = C / 4;
+  auto init_actnorm = [&](int which, const float* tokens) -> int {   // 0: conv_shrink from the map, 1: conv_extend from tokens
+    float** cp = which ? p->v5_extend[si] : p->v5_shrink[si];
+    Launch l(r, PC_NORM, 0.0, 0.0, "lvit5_actnorm_init %s", which ? "extend" : "shrink");
+    l.sym("lvit5_actnorm_init_kernel");
+    lvit5_actnorm_init_kernel<<<which ? C : Cq, 256, 0, r.st>>>(x, all_maps16(p) ? 1 : 0, tokens, r.nb, Hl, Hl, p->win, rows_per_image,
+                                                              which ? Cq : C, cp[0], cp[1], cp[2], cp[3],
+                                                              p->v5_reg[si][which][0], p->v5_reg[si][which][1]);
+    CU(cudaGetLastError());
+    return 0;
+  };
+  if (cal) RET(init_actnorm(0, nullptr));
   const double flops = 2.0 * M * ((double)v.E * v.E * 5 + 4.0 * v.E * v.hid + 2.0 * v.L * v.E) + 4.0 * M * v.E * v.E;
   const double bytes = (all_maps16(p) ? 2.0 : 4.0) * M * 4.0 * C + 4.0 * M * 4.0 * C;
   if (C <= 48) {
@@ -1359,7 +1375,7 @@ static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, co
     Lvit5Args a{x, all_maps16(p) ? 1 : 0, r.nb, Hl, Hl, p->win, M, sh, ex, v.w_le, v.b_le, v.pos, v.ln1g, v.ln1b, v.w_in,
                 v.w_out, v.w1, v.b1, v.w2, v.b2, v.ln2g, v.ln2b, v.wm0, v.bm0, v.wm3, v.bm3,
                 v.h_le, v.h_in, v.h_out, v.h_1, v.h_2, v.h_m0, v.h_m3, v.hid,
-                L.lws.t0, L.lws.qkv16, L.lws.o16, L.lws.t1};
+                L.lws.t0, L.lws.qkv16, L.lws.o16, L.lws.t1, cal ? 1 : 0};
     if (v.hid % 16 != 0 || v.hid > 4 * v.E) return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: hidden width %d is not supported", v.hid);
     const int tiles = (M + 127) / 128;
     const int blocks = tiles < 2 * 148 ? tiles : 2 * 148;   // persistent over 128-token tiles: the weights are staged once
@@ -1378,6 +1394,14 @@ static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, co
       else lvit5_post_kernel<48><<<blocks, 256, Lvit5Cfg<48>::post_smem(v.hid), r.st>>>(a);
       CU(cudaGetLastError());
     }
+    if (cal) {   // the post kernel left the final tokens in t: initialise conv_extend's ActNorm from window 0, then expand
+      RET(init_actnorm(1, L.lws.t0));
+      Launch l(r, PC_TOKENIZE, 2.0 * M * C * C, 20.0 * M * C, "lvit5_extend M%d C%d", M, C);
+      l.sym("lvit5_extend_kernel<%d>", C);
+      if (C == 24) lvit5_extend_kernel<24><<<(4 * M + 127) / 128, 128, 0, r.st>>>(L.lws.t0, M, ex, L.lws.t1);
+      else lvit5_extend_kernel<48><<<(4 * M + 127) / 128, 128, 0, r.st>>>(L.lws.t0, M, ex, L.lws.t1);
+      CU(cudaGetLastError());
+    }
     *tokens_out = L.lws.t1;
     return 0;
   }
@@ -1389,6 +1413,7 @@ static int run_lvit5(Run& r, int si, const float* x, int Hl, int C, int nwin, co
     CU(cudaGetLastError());
   }
   RET(run_vit(r, v, L.lws, r.nb * nwin));
+  if (cal) RET(init_actnorm(1, L.lws.t1));
   {
     Launch l(r, PC_TOKENIZE, 2.0 * M * C * C, 4.0 * M * C + 16.0 * M * C, "lvit5_extend M%d C%d", M, C);
     l.sym("lvit5_extend_kernel<96>");
@@ -1627,9 +1652,6 @@ static int forward_impl(cfen_plan* p, int batch, const void* in, void* xr, void*
   if (batch < 0 || !in || !xd || (!only_d && (!xr || !xs))) return fail(1, "cfen_forward: bad argument");
   if (io & ~(CFEN_IO_U8 | CFEN_ONLY_FAKE_A)) return fail(1, "cfen_forward_ex: unknown io flag bits 0x%x", io);
   if (calibrate && io) return fail(1, "cfen_forward_calibrate takes fp32 tensors and produces all three outputs");
-  if (calibrate && p->v5)
-    return fail(3, "iid_hlgvit_crs_gd4_cfs_v5: first-forward ActNorm initialisation is not available on the GPU (conv_shrink / "
-                   "conv_extend initialise on the top-left window only, v5.py:403): load initialised weights");
   if (calibrate && p->from_blob) return fail(8, "cfen_forward_calibrate: this plan was filled from a packed blob (no registered tensors to initialise)");
   if (u8 && !p->conv_path) return fail(3, "the fused uint8 boundary needs the conv16 generation (conv_path 1)");
   if (calibrate && batch > p->nbmax)

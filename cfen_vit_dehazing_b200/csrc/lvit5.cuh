@@ -44,6 +44,7 @@ struct Lvit5Args {
   __half* qkv16;            // [M, 3E] packed in-projection (pre kernel -> attention)
   const __half* o16;        // [M, E] attention output (attention -> post kernel)
   float* out;               // [M, 4C] fp32 tokens of the expanded map
+  int final_only;           // post kernel: write the final t back to `t` and skip conv_extend (ActNorm calibration pass)
 };
 
 // top-left pixel of token m and its index inside the window
@@ -380,6 +381,14 @@ lvit5_post_kernel(const Lvit5Args a) {
     lvit5_mlp_tc<E>(ah, W1, W2, hid, a.b1, a.b2, tt, lane);         // t += FFN(LayerNorm2(t))
     lvit5_c2a<NT, KS>(tt, ah);
     lvit5_mlp_tc<E>(ah, Wm0, Wm3, hid, a.bm0, a.bm3, tt, lane);     // t += mlp_head(t)
+    if (a.final_only) {   // calibration: conv_extend's ActNorm is initialised from these tokens before it can run
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (live[0]) *reinterpret_cast<float2*>(a.t + (size_t)mr[0] * E + n * 8 + 2 * t) = make_float2(tt[n][0], tt[n][1]);
+        if (live[1]) *reinterpret_cast<float2*>(a.t + (size_t)mr[1] * E + n * 8 + 2 * t) = make_float2(tt[n][2], tt[n][3]);
+      }
+      continue;
+    }
     // ---- conv_extend (+ bias, ActNorm, ReLU) on the four pixels of the folded token -> output row (ky, kx, c)
     lvit5_c2a<NT, KS>(tt, ah);
 #pragma unroll 1
@@ -454,6 +463,51 @@ lvit5_extend_kernel(const float* __restrict__ t, int M, const Lvit5Conv cv, floa
   for (int c = 0; c < CQ; ++c) z[c] = t[(size_t)m * C + pq * CQ + c];
   float* orow = out + (size_t)m * 4 * C + pq * C;
   lvit5_pointwise<CQ, C>(cv, z, [&](int n, float v) { orow[n] = v; });
+}
+
+// First-forward initialisation of the ActNorm behind conv_shrink / conv_extend (models/actnorm.py:25-42): the reference
+// calls a local ViT once per window, so the statistics come from the FIRST call - the top-left window of every image in
+// the batch (v5.py:403).  One CTA per output channel; samples = the win x win pixels of window 0 of each image, read from
+// the level map (tokens == nullptr) or from the token matrix [M, Cin*4] (features (ky, kx, c'), window 0 = rows
+// b*rows_per_image + [0, L)).  bias = -mean, weight = -0.5 log(max(var_unbiased, 0.2)), written to the plan's copy and to
+// the caller's registered tensors.
+__global__ void __launch_bounds__(256)
+lvit5_actnorm_init_kernel(const float* __restrict__ map, int h16, const float* __restrict__ tokens, int B, int H, int W,
+                          int win, int rows_per_image, int Cin, const float* __restrict__ w, const float* __restrict__ bias,
+                          float* an_w, float* an_b, float* an_w_reg, float* an_b_reg) {
+  __shared__ double ssum[256], ssq[256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int per = win * win, n = B * per, half = win >> 1;
+  double s = 0.0, q = 0.0;
+  for (int i = tid; i < n; i += 256) {
+    const int b = i / per, r = i - b * per, y = r / win, x = r - y * win;
+    float acc = bias[c];
+    if (tokens) {
+      const float* row = tokens + ((size_t)b * rows_per_image + (y >> 1) * half + (x >> 1)) * (4 * Cin) + ((y & 1) * 2 + (x & 1)) * Cin;
+      for (int k = 0; k < Cin; ++k) acc = fmaf(w[c * Cin + k], row[k], acc);
+    } else {
+      const size_t pix = ((size_t)b * H + y) * W + x;
+      for (int k = 0; k < Cin; k += 4) {
+        const float4 v = ld_map4(map, (pix * Cin + k) >> 2, h16 != 0);
+        acc = fmaf(w[c * Cin + k], v.x, fmaf(w[c * Cin + k + 1], v.y, fmaf(w[c * Cin + k + 2], v.z, fmaf(w[c * Cin + k + 3], v.w, acc))));
+      }
+    }
+    s += (double)acc; q += (double)acc * (double)acc;
+  }
+  ssum[tid] = s; ssq[tid] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { ssum[tid] += ssum[tid + o]; ssq[tid] += ssq[tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const double mean = ssum[0] / (double)n;
+    double var = (ssq[0] - (double)n * mean * mean) / (double)(n - 1);
+    if (var < 0.2) var = 0.2;
+    const float wv = (float)(-0.5 * log(var)), bv = (float)(-mean);
+    an_w[c] = wv; an_b[c] = bv;
+    if (an_w_reg) { an_w_reg[c] = wv; an_b_reg[c] = bv; }
+  }
 }
 
 // softmax(q k^T / sqrt(6)) v for 6-wide heads on the packed fp16 [nseq*L, 3E] in-projection: attention16_kernel's scheme

@@ -9,7 +9,8 @@ It is ``iid_hlgvit_crs_gd4_cfs_v3`` with a different local ViT (v5.py:1062-1192,
 every ``localvit_*`` first shrinks its window map with a 1x1 conv C -> C/4 + ActNorm + ReLU (``conv_shrink``), runs the
 windowed ViT at a quarter of the width (E = 24 / 48 / 96 on the three levels, 6-wide heads, hidden = E * hidden_dim_ratio)
 and expands the folded result with a 1x1 conv C/4 -> C + ActNorm + ReLU (``conv_extend``).  The two ActNorm layers of a
-local ViT initialise on its FIRST call, i.e. on the top-left window of the level map only (v5.py:403).  1078 ``state_dict``
+local ViT initialise on its FIRST call, i.e. on the top-left window of the level map only (v5.py:403); the GPU
+calibration pass (cfen_forward_calibrate -> lvit5_actnorm_init_kernel) takes its statistics from the same pixels.  1078 ``state_dict``
 entries in the reference's order, same RNG stream.
 
 Device side: the v3 plan graph with ``cfen_config.flags = CFEN_VARIANT_V5``; the local branch of every block runs

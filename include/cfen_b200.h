@@ -64,7 +64,8 @@ typedef struct cfen_config {
 /* iid_hlgvit_crs_gd4_cfs_v5 (models/networks_iid_hlgvit_crs_gd4_cfs_v5.py, model_iid_dehazing.py:93-95): the v3 graph and
  * geometry with every local ViT running at a quarter of the width behind 1x1 conv_shrink / conv_extend layers (:1062-1192).
  * State_dict: 1078 entries (v3's plus conv_shrink / conv_extend of the 12 local ViTs, whose Linear layers are 4x narrower).
- * ActNorm layers must be initialised (cfen_forward_calibrate returns 3).  Exclusive with the other variants. */
+ * cfen_forward_calibrate initialises conv_shrink's / conv_extend's ActNorm from the top-left window of every image, as the
+ * reference's first forward does (one local-ViT call per window, v5.py:403).  Exclusive with the other variants. */
 #define CFEN_VARIANT_V5 4
 
 int32_t     cfen_abi_version(void);

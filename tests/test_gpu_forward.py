@@ -338,10 +338,11 @@ def test_v5_sibling_parity_vs_oracle_and_goldens(name):
         assert d <= MAX_ABS_01, (tag, d)
 
 
-def test_v5_sibling_batch8_level3_fused_kernels_and_uninitialised_error():
-    """512x512 batch 8: level 3 has 8192 tokens (64 tiles), so its quarter-width ViT runs the fused tail kernel and the
-    6-wide-head attention kernel next to lvit5_kernel<24 / 48>; an un-initialised v5 model raises (its shrink / extend
-    ActNorm layers initialise on one window only in the reference: not reproduced on the GPU)."""
+def test_v5_sibling_batch8_level3_fused_kernels_and_calibration():
+    """512x512 batch 8: level 3 has 8192 tokens (64 tiles), so its quarter-width ViT runs the fused tail kernel next to
+    lvit5_pre / attention_hd6 / lvit5_post on levels 1 - 2.  Un-initialised model: the first forward on the GPU
+    reproduces the oracle's priming, including conv_shrink / conv_extend, whose ActNorm layers take their statistics
+    from the top-left window only (v5.py:403)."""
     gnet, sd0, sd1, x0 = _gpu_net_v5(2, 512)
     x = orc.make_inputs(512, [1, 8])[1]
     with torch.no_grad():
@@ -351,10 +352,22 @@ def test_v5_sibling_batch8_level3_fused_kernels_and_uninitialised_error():
         for a, b in zip(out, ref):
             mx, ps = U.err01(a[i:i + 1], b)
             assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (i, mx, ps)
-    gnet2, sd0, sd1, x0 = _gpu_net_v5(2, 128, primed=False)
-    with pytest.raises(RuntimeError, match="initialis"):
+    for hr, size in ((2, 128), (2, 512)):
+        gnet2, sd0, sd1, x0 = _gpu_net_v5(hr, size, primed=False)
         with torch.no_grad():
-            gnet2(x0.cuda())
+            first = gnet2(x0.cuda())
+        got = gnet2.state_dict()
+        worst = max((got[k].cpu() - v).abs().max().item() for k, v in sd1.items()
+                    if (k.rsplit(".", 1)[0] + ".initialized") in sd1 and not k.endswith(".initialized"))
+        assert worst <= 2e-2, (size, worst)
+        shr = max((got[k].cpu() - sd1[k]).abs().max().item() for k in sd1 if ".conv_shrink.1." in k or ".conv_extend.1." in k
+                  if not k.endswith(".initialized"))
+        assert shr <= 2e-2, (size, shr)
+        assert all(int(got[k]) == 1 for k in sd1 if k.endswith(".initialized"))
+        ref = orc.forward(sd1, x0)
+        for a, b in zip(first, ref):
+            mx, ps = U.err01(a, b)
+            assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (size, mx, ps)
 
 
 def test_fp16_range_guard_detects_and_falls_back():
