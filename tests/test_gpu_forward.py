@@ -352,6 +352,14 @@ def test_v5_sibling_batch8_level3_fused_kernels_and_calibration():
         for a, b in zip(out, ref):
             mx, ps = U.err01(a[i:i + 1], b)
             assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (i, mx, ps)
+    img = ((x[:2] + 1) * 127.5).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    xn = ((img.permute(0, 3, 1, 2).float() / 255.0) - 0.5) / 0.5
+    with torch.no_grad():
+        u8 = gnet.forward_u8(img.cuda())
+        only = gnet.forward_u8(img.cuda(), outputs=("fake_A",))
+    for o, rr in zip(u8, orc.forward(sd1, xn)):
+        assert (o.cpu().int() - _tensor2im_u8(rr).int()).abs().max().item() <= 3
+    assert torch.equal(only[0], u8[2])
     for hr, size in ((2, 128), (2, 512)):
         gnet2, sd0, sd1, x0 = _gpu_net_v5(hr, size, primed=False)
         with torch.no_grad():
