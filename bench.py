@@ -70,18 +70,23 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  nvidia-smi needs ~0.1 - 0.3 s to
+    print its first line and the timed region of a many-GPU run is shorter than that, so the sampler is started before
+    the warm-up steps (same work, same load); `mark()` opens the timed window, leaving the `with` block closes it.  The
+    summary uses the samples inside the window; when the window was too short to catch one, the samples taken under the
+    same load within 0.5 s around it (warm-up before, nothing idle in between) - `window` says which."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -89,11 +94,17 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def mark(self):
+        self.t0 = time.time()
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        self.t1 = time.time()
+        if self.t0 is None:
+            self.t0 = self.t1
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -103,20 +114,30 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                              ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
+        def collect(lo, hi):
+            sm, mx, reasons = [], [], set()
+            for ts, r in self.rows:
+                if ts < lo or ts > hi:
+                    continue
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if len(r) > col and r[col].lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        t0, t1 = self.t0 or 0.0, self.t1 or 0.0
+        window = "timed region"
+        sm, mx, reasons = collect(t0, t1 + 0.06)    # a sample is at most one 50 ms period old when it is printed
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            window = "under the same load within 0.5 s of the timed region (region shorter than the sampling period)"
+            sm, mx, reasons = collect(t0 - 0.5, t1 + 0.2)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": window}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # BASELINE.json configs: (size, hidden_dim_ratio) -> (global batch, label)
@@ -393,11 +414,12 @@ def run_ours(args):
         stream = torch.cuda.current_stream(dev)
 
         # ---------------- device-resident throughput: K steps bracketed by events, nothing else on the stream
-        for _ in range(max(3, args.warmup)):
-            out = net(x_dev)
-        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clocks:
+            for _ in range(max(3, args.warmup)):
+                out = net(x_dev)
+            barrier()
+            clocks.mark()
             e0.record(stream)
             for _ in range(args.steps):
                 out = net(x_dev)

@@ -124,3 +124,20 @@ def test_frac_by_shape_measures_each_shape_against_its_own_bound():
     tot = {"us": 3000.0, "gflop": 1010.0, "mbytes": 4010.0}
     assert b.roofline_of(tot, peaks)["bound"] == "tensor" and abs(b.roofline_of(tot, peaks)["frac"] - 0.33666) < 1e-3
     assert b.frac_by_shape("absent", shapes, peaks) == 0.0
+
+
+def test_clock_sampler_window_selection():
+    """Samples inside the timed window are used; a window shorter than the sampling period falls back to the samples
+    taken under the same load right around it and says so."""
+    import bench as b
+    row = lambda mhz, cap="Not Active": ["0", str(mhz), "1965", "700", "0x0", "Not Active", "Not Active", "Not Active", cap]
+    c = b.ClockSampler(0)
+    c.rows = [(99.0, row(300)), (100.02, row(1950)), (100.07, row(1965, "Active")), (101.5, row(400))]
+    c.t0, c.t1 = 100.0, 100.1
+    s = c.summary()
+    assert s["samples"] == 2 and s["sm_mhz"] == 1957.5 and s["reasons"] == ["sw_power_cap"] and s["window"] == "timed region"
+    c.rows = [(99.7, row(1965)), (100.4, row(1960)), (103.0, row(300))]
+    s = c.summary()
+    assert s["samples"] == 1 and s["sm_mhz"] == 1965.0 and s["window"].startswith("under the same load")
+    c.rows = []
+    assert c.summary()["samples"] == 0
