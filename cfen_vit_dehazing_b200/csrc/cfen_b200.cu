@@ -645,6 +645,10 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
     delete p;
     return fail(3, "iid_hlgvit_crs_gd4_cfs needs the conv16 generation (conv_path 1)");
   }
+  if (p->v5 && p->gemm_path != 2) {
+    delete p;
+    return fail(3, "iid_hlgvit_crs_gd4_cfs_v5 needs the fp16 token kernels (gemm_path 2): its 6-wide heads have no TF32 attention kernel");
+  }
   plan_declare_convs(p);
   plan_layout(p, true, true);  // dry run: sizes
   const size_t wbytes = p->wa.off, sbytes = p->ws.off;
