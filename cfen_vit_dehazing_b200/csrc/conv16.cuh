@@ -139,6 +139,21 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
   };
   load_w(0, 0, 0);
   cp_async_commit();
+  // the residual rows of this tile are only read in the copy-out at the very end, by a load whose result is needed at
+  // once (23 % of the merge kernels' warp samples sat on its conversion, profiles/r2_v7_lg1_full.md): pull them into L2
+  // now, one 128-byte line per thread
+  if ((a.flags & CF_RES) && !S::TRANSPOSED) {
+    const int esz = (a.flags & CF_RES16) ? 2 : 4;
+    const int row_bytes = C::TW * S::COUT * esz, lines = (row_bytes + 127) / 128;
+    if (tid < C::TH * lines) {
+      const int y = tid / lines, ln = tid - y * lines;
+      if (ty0 + y < Hout) {
+        const char* rp = reinterpret_cast<const char*>(a.res) +
+                         ((((size_t)b * Hout + ty0 + y) * Wout + tx0) * S::COUT) * esz + ln * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+      }
+    }
+  }
 
   // smem offset (halves) of tap `tap` of phase `ph`, relative to a pixel's a_base
   auto tap_offset = [&](int ph, int tap) -> int {
