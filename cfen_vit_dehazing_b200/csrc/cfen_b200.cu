@@ -1904,9 +1904,14 @@ extern "C" int32_t cfen_layernorm_f16(const float* x, void* y16, const float* ga
 extern "C" int32_t cfen_attention_f16(const void* qkv16, void* out16, int32_t nseq, int32_t L, int32_t E,
                                       int32_t heads, void* stream) {
   if (!qkv16 || !out16) return fail(1, "cfen_attention_f16: null argument");
-  if (heads <= 0 || E % heads != 0 || (E / heads != 24 && E / heads != 96))
-    return fail(1, "cfen_attention_f16: head dim must be 24 or 96");
+  if (heads <= 0 || E % heads != 0 || (E / heads != 24 && E / heads != 96 && E / heads != 6))
+    return fail(1, "cfen_attention_f16: head dim must be 6, 24 or 96");
   CU(set_kernel_attributes());
+  if (E / heads == 6) {   // local ViTs of iid_hlgvit_crs_gd4_cfs_v5
+    CU(launch_attention_hd6(static_cast<const __half*>(qkv16), static_cast<__half*>(out16), nseq, L, E,
+                            static_cast<cudaStream_t>(stream)));
+    return 0;
+  }
   const char* at = getenv("CFEN_ATTN_TC");   // same selection as the plan (option "attn_tc")
   if ((!at || atoi(at) != 0) && attention_tc_supported(L, E, heads)) {
     CU(launch_attention_tc(static_cast<const __half*>(qkv16), static_cast<__half*>(out16), nseq, L, E, heads,

@@ -192,7 +192,8 @@ int32_t cfen_vit_front_f16(const float* src, int32_t src_is_map, int32_t B, int3
 /* LayerNorm with fp16 output (the A operand of the next Linear). */
 int32_t cfen_layernorm_f16(const float* x, void* y16, const float* gamma, const float* beta, int32_t rows,
                            int32_t E, float eps, void* stream);
-/* Attention core on fp16 qkv[nseq*L,3E] -> fp16 out[nseq*L,E] (mma.sync m16n8k16, fp32 softmax). */
+/* Attention core on fp16 qkv[nseq*L,3E] -> fp16 out[nseq*L,E]; head width E/heads = 24 or 96 (tcgen05 for 256-token
+ * sequences of 24-wide heads, else mma.sync m16n8k16) or 6 (the local ViTs of iid_hlgvit_crs_gd4_cfs_v5); fp32 softmax. */
 int32_t cfen_attention_f16(const void* qkv16, void* out16, int32_t nseq, int32_t L, int32_t E,
                            int32_t heads, void* stream);
 

@@ -270,7 +270,10 @@ def test_layernorm_f16(rows, E):
 
 
 @pytest.mark.parametrize("nseq,Lq,E,heads", [(3, 256, 96, 4), (2, 256, 384, 16), (2, 256, 384, 4), (2, 64, 768, 8),
-                                             (5, 16, 1536, 16), (1, 1024, 96, 4), (2, 80, 192, 8), (1, 1024, 384, 4)])
+                                             (5, 16, 1536, 16), (1, 1024, 96, 4), (2, 80, 192, 8), (1, 1024, 384, 4),
+                                             # 6-wide heads (attention_hd6_kernel, local ViTs of iid_hlgvit_crs_gd4_cfs_v5)
+                                             (70, 256, 24, 4), (9, 256, 48, 8), (3, 256, 96, 16), (5, 16, 24, 4),
+                                             (2, 1024, 48, 8), (3, 80, 24, 4)])
 def test_attention_f16(nseq, Lq, E, heads):
     L = _native.lib()
     hd = E // heads
