@@ -349,7 +349,12 @@ struct VitW {
   __half *h_le, *h_in, *h_out, *h_1, *h_2, *h_m0, *h_m3;  // fp16 operand copies (gemm_path 2)
 };
 
-struct TokWs { float *t0, *t1, *h, *qkv, *o, *f, *part; __half *x16, *h16, *qkv16, *o16, *f16; };
+struct TokWs {
+  float *t0, *t1, *h, *qkv, *o, *f, *part;
+  __half *x16, *h16, *qkv16, *o16, *f16;
+  const float* out_tokens = nullptr;   // where the last run_vit left its output tokens (t1, or h16 as fp16)
+  bool out16 = false;
+};
 // split-K partial tiles of one Linear: slices x padded rows x N <= ~148 CTAs x 128 x 192 floats (gemm16_pick_split)
 static const size_t kSplitPartFloats = (size_t)4 << 20;
 
@@ -387,6 +392,7 @@ struct cfen_plan {
   Arena wa, ws;  // packed weights, workspace
   bool allocated = false, packed = false, from_blob = false;
   VitW lvit[12], gvit[12];
+  bool tok16 = true;                     // fused local ViT tail hands its tokens to the merge convolution as fp16
   bool v5 = false;                       // iid_hlgvit_crs_gd4_cfs_v5: quarter-width local ViTs (lvit5.cuh)
   float *v5_shrink[12][4] = {}, *v5_extend[12][4] = {};   // arena copies of conv_shrink / conv_extend {w, b, an_w, an_b}
   float* v5_reg[12][2][2] = {};          // the caller's ActNorm {weight, bias} of shrink / extend (calibration writes them)
@@ -636,6 +642,7 @@ extern "C" int32_t cfen_plan_create(const cfen_config* cfg, cfen_plan** out) {
   if (const char* at = getenv("CFEN_ATTN_TC")) p->attn_tc = atoi(at) != 0;
   if (const char* ct = getenv("CFEN_CONV_TC")) p->conv_tc = atoi(ct);
   if (const char* gs = getenv("CFEN_GEMM_SMALL")) p->gemm_small = atoi(gs) != 0;
+  if (const char* tk = getenv("CFEN_TOK16")) p->tok16 = atoi(tk) != 0;
   if (const char* mm = getenv("CFEN_MAPS16")) p->maps16 = atoi(mm);
   if (const char* mt = getenv("CFEN_FUSE_MIN_TILES")) p->fuse_min_tiles = atoi(mt);
   if (const char* sk = getenv("CFEN_SPLIT_K")) p->split_k = atoi(sk) != 0;
@@ -738,6 +745,7 @@ extern "C" int32_t cfen_plan_get_option(const cfen_plan* p, const char* name, in
   if (strcmp(name, "attn_tc") == 0) { *value = p->attn_tc; return 0; }
   if (strcmp(name, "conv_tc") == 0) { *value = p->conv_tc; return 0; }
   if (strcmp(name, "gemm_small") == 0) { *value = p->gemm_small; return 0; }
+  if (strcmp(name, "tok16") == 0) { *value = p->tok16; return 0; }
   if (strcmp(name, "fuse_tail") == 0) { *value = p->fuse_tail; return 0; }
   if (strcmp(name, "split_k") == 0) { *value = p->split_k; return 0; }
   return fail(5, "unknown option '%s'", name);
@@ -762,6 +770,7 @@ extern "C" int32_t cfen_plan_set_option(cfen_plan* p, const char* name, int64_t 
   if (strcmp(name, "attn_tc") == 0) { p->attn_tc = value != 0; return 0; }
   if (strcmp(name, "conv_tc") == 0) { p->conv_tc = (int)value; return 0; }
   if (strcmp(name, "gemm_small") == 0) { p->gemm_small = value != 0; return 0; }
+  if (strcmp(name, "tok16") == 0) { p->tok16 = value != 0; return 0; }
   if (strcmp(name, "maps16") == 0) { p->maps16 = (int)value; return 0; }
   if (strcmp(name, "fuse_min_tiles") == 0) { p->fuse_min_tiles = (int)value; return 0; }
   if (strcmp(name, "split_k") == 0) { p->split_k = value != 0; return 0; }
@@ -1082,11 +1091,13 @@ static int run_mlp16(Run& r, const __half* X, const __half* W1, const float* b1,
   return 0;
 }
 // t <- out-proj + LN + FFN + MLP head of one ViT call, in place on the fp32 token matrix t (vit_tail16.cuh)
-static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
+// Y16 != nullptr (tail kernel with the residual in TMEM only): the output tokens leave as fp16 into Y16 instead of fp32 into T
+static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M, __half* Y16 = nullptr) {
   const int E = v.E, hid = v.hid;
   const CUtensorMap *to, *tt, *two, *t1, *t2, *m0, *m3;
   RET(get_tmap2(r.p, O, 2, M, E, 64, 128, &to));
-  RET(get_tmap2(r.p, T, 4, M, E, 32, 128, &tt));
+  if (Y16) RET(get_tmap2(r.p, Y16, 2, M, E, 32, 128, &tt));
+  else RET(get_tmap2(r.p, T, 4, M, E, 32, 128, &tt));
   RET(get_tmap2(r.p, v.h_out, 2, E, E, 64, E, &two));
   RET(get_tmap2(r.p, v.h_1, 2, hid, E, 64, 64, &t1));
   RET(get_tmap2(r.p, v.h_2, 2, E, hid, 64, E, &t2));
@@ -1096,7 +1107,7 @@ static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M) {
            "tail16 M%d E%d hid%d", M, E, hid);
   l.sym(tail_in_tmem(r.p->tail_variant, E) ? "vit_tail16r_kernel<%d>" : "vit_tail16_kernel<%d>", E);
   if (tail_in_tmem(r.p->tail_variant, E)) {
-    Tail16RArgs ra{T, v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, hid};
+    Tail16RArgs ra{T, v.ln2g, v.ln2b, v.b1, v.b2, v.bm0, v.bm3, M, hid, Y16 ? 1 : 0};
     CU(launch_tail16r(E, *to, *two, *t1, *t2, *m0, *m3, *tt, ra, r.st));
     return 0;
   }
@@ -1197,8 +1208,10 @@ static bool front_fusable(const cfen_plan* p, int E, int M) {
   return p->gemm_path == 2 && p->fuse_front && front16_supported(E) && (M + 127) / 128 >= p->fuse_min_tiles;
 }
 // `src` != nullptr: the tokens of this (local) call have NOT been materialised; the fused front kernel gathers them.
-static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* src = nullptr) {
+static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* src = nullptr, bool tok16_ok = false) {
   const int M = nseq * v.L, E = v.E, hid = v.hid;
+  w.out_tokens = w.t1;
+  w.out16 = false;
   if (src && !front_fusable(r.p, E, M)) return fail(20, "run_vit: map source without the fused front kernel");
   if (r.p->gemm_path == 2) {  // fp16 operands, fp32 residual stream
     if (src) {
@@ -1209,7 +1222,16 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
       RET(run_gemm16(r, w.h16, v.h_in, nullptr, w.qkv16, M, 3 * E, E, nullptr, nullptr, nullptr, 0, 0, w.part));
     }
     RET(run_attn16(r, w.qkv16, w.o16, nseq, v.L, E, v.heads));
-    if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= r.p->fuse_min_tiles) return run_tail16(r, v, w.o16, w.t1, M);
+    if (r.p->fuse_tail && tail16_supported(E, hid) && (M + 127) / 128 >= r.p->fuse_min_tiles) {
+      // local ViT feeding a merge convolution that reads fp16 operands anyway: hand the tokens over as fp16 (same rounding,
+      // done here instead of in the conv loader; half the bytes on both sides)
+      if (tok16_ok && r.p->tok16 && all_maps16(r.p) && tail_in_tmem(r.p->tail_variant, E)) {
+        w.out_tokens = reinterpret_cast<const float*>(w.h16);
+        w.out16 = true;
+        return run_tail16(r, v, w.o16, w.t1, M, w.h16);
+      }
+      return run_tail16(r, v, w.o16, w.t1, M);
+    }
     RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0, w.part));
     RET(run_ln16(r, w.t1, w.h16, v.ln2g, v.ln2b, M, E));
     const int bm = 128 * mlp16_shape(E).MH;
@@ -1275,7 +1297,7 @@ static int run_conv(Run& r, const std::string& name, const float* in0, const flo
     // pass 1: conv + bias only, per-CTA statistics (models/actnorm.py:25-37)
     const int cout = conv_cout(c.kind);
     const int parts = p->conv_path ? conv16_parts(c.kind, H, W) : conv_parts(c.kind, H, W);
-    a.scale = p->ones; a.shift = c.bias_src; a.flags = flags & CF_FMT_MASK; a.stats = r.ln->partials;
+    a.scale = p->ones; a.shift = c.bias_src; a.flags = flags & (CF_FMT_MASK | CF_TOK16); a.stats = r.ln->partials;   // operand formats stay
     {
       Launch l(r, pcls, cflops, cbytes, "%s cal", name.c_str());
       l.sym("%s<%s>", p->conv_path ? "conv16_kernel" : "conv_igemm_kernel", conv_kind_name(c.kind));
@@ -1458,7 +1480,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
   }
   if (front_fusable(p, p->lvit[si].E, r.nb * nwin * p->lvit[si].L)) {
     const FrontSrc src{x, Hl, Hl, C, p->win, all_maps16(p)};
-    RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin, &src));
+    RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin, &src, true));
   } else {
     const long long n4 = (long long)r.nb * Hl * Hl * C / 4;
     {
@@ -1471,7 +1493,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
   }
   RET(stream_edge(p, L.gst, main_st));
   const std::string name = "lgcat_conv_" + stage_tag(kStages[si]);
-  return run_conv(r, name, L.lws.t1, L.gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES);
+  return run_conv(r, name, L.lws.out_tokens, L.gws.t1, x, out, Hl, Hl, CF_RELU | CF_RES | (L.lws.out16 ? CF_TOK16 : 0));
 }
 
 // io: CFEN_IO_U8 = uint8 HWC images at the boundary (fused into the head loader / tail epilogue),

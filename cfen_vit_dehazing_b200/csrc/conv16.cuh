@@ -205,6 +205,30 @@ __global__ void __launch_bounds__(256, Conv16<S, BIG>::MINB) conv16_kernel(const
       __syncthreads();
       const float* lbase = a.in0 + (size_t)b * Hin * Win * CC;   // tokens of image b: Hin * Win / 4 rows of 4 CC
       constexpr int U = 8, TOTAL = C::TH * C::TW * CC4;
+      if (a.flags & CF_TOK16) {   // fp16 tokens: the halves are the operand as they are
+        const __half* lb16 = reinterpret_cast<const __half*>(a.in0) + (size_t)b * Hin * Win * CC;
+        for (int i0 = tid; i0 < TOTAL; i0 += S::THREADS * U) {
+          uint2 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * S::THREADS;
+            v[u] = make_uint2(0u, 0u);
+            if (i < TOTAL) {
+              const int c4 = i % CC4, pix = i / CC4;
+              const uint32_t off = (uint32_t)(lgtab[pix / C::TW] + lgtab[C::TH + pix % C::TW] + c4 * 4);
+              v[u] = *reinterpret_cast<const uint2*>(lb16 + off);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * S::THREADS;
+            if (i < TOTAL) {
+              const int c4 = i % CC4, pix = i / CC4;
+              *reinterpret_cast<uint2*>(tile + pix * C::CPITCH + c4 * 4) = v[u];
+            }
+          }
+        }
+      } else
       for (int i0 = tid; i0 < TOTAL; i0 += S::THREADS * U) {
         float4 v[U];
 #pragma unroll

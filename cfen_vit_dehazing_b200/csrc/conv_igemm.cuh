@@ -29,6 +29,8 @@ enum ConvFlags {
   //   CF_OUT_U8 (with CF_OUT_NCHW staging): out is a uint8 HWC image [B,H,W,3] = tensor2im (util/util.py:12-24):
   //             (y + 1) / 2 * 255 truncated to uint8, one-channel maps tiled to three channels
   CF_IN_U8 = 128, CF_OUT_U8 = 256,
+  // LD_LG loader (conv16 generation): in0 holds the local ViT tokens as fp16 (vit_tail16r's y16 output)
+  CF_TOK16 = 512,
   CF_KEEP_FMT = 1 << 20   // host-side only (run_conv): do not apply the plan-wide fp16-map format bits
 };
 

@@ -40,6 +40,8 @@ struct Tail16RArgs {
   const float *lng, *lnb;            // norm2 weight / bias [E]
   const float *b1, *b2, *bm0, *bm3;  // [hid], [E], [hid], [E]
   int M, hid;
+  int y16;                           // 1: the output tokens leave as fp16 (tmY maps an fp16 [M, E] matrix, box 32 x 128):
+                                     // their only reader, the merge convolution, rounds them to fp16 anyway
 };
 
 template <int E>
@@ -400,6 +402,8 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
             tc::tmem_ld32(lane_addr + COL_A + 32 * i, v);
             tc::tmem_ld_wait();
             uint8_t* line = stage + i * 16384 + roff;
+            uint8_t* line16 = stage + i * 8192 + (roff >> 10) * 512 + ((roff >> 7) & 7) * 64;   // dense 64-byte fp16 rows
+            uint32_t hx[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 p = *reinterpret_cast<const float4*>(a.b2 + 32 * i + 4 * j);
@@ -407,13 +411,19 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
               float4 t;
               t.x = __uint_as_float(v[4 * j + 0]) + (p.x + r.x); t.y = __uint_as_float(v[4 * j + 1]) + (p.y + r.y);
               t.z = __uint_as_float(v[4 * j + 2]) + (p.z + r.z); t.w = __uint_as_float(v[4 * j + 3]) + (p.w + r.w);
-              *reinterpret_cast<float4*>(line + ((j ^ sw) << 4)) = t;
+              if (a.y16) { hx[2 * j] = pack_half2(t.x, t.y); hx[2 * j + 1] = pack_half2(t.z, t.w); }
+              else *reinterpret_cast<float4*>(line + ((j ^ sw) << 4)) = t;
+            }
+            if (a.y16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(line16 + 16 * j) = make_uint4(hx[4 * j], hx[4 * j + 1], hx[4 * j + 2], hx[4 * j + 3]);
             }
           }
           tc::fence_async_smem();
           tc::named_bar_sync(1, 128);
           if (warp == 2 && tc::elect_one()) {
-            for (int i = 0; i < NP; ++i) tc::tma_store_2d(&tmY, stage + i * 16384, i * 32, m0);
+            for (int i = 0; i < NP; ++i) tc::tma_store_2d(&tmY, stage + i * (a.y16 ? 8192 : 16384), i * 32, m0);
             tc::tma_store_commit();
             tc::tma_store_wait_read();
           }

@@ -160,6 +160,7 @@ OPTION_SETS = [
     {"CFEN_FUSE_MIN_TILES": "1", "CFEN_ATTN_TC": "0"},
     {"CFEN_CONV_TC": "0"},
     {"CFEN_GEMM_SMALL": "0"},
+    {"CFEN_TOK16": "0"},
     {"CFEN_CONV_TC": "2"},
     {"CFEN_SPLIT_K": "0"},
     {"CFEN_STREAMS": "0"},
@@ -376,6 +377,33 @@ def test_v5_sibling_batch8_level3_fused_kernels_and_calibration():
         for a, b in zip(first, ref):
             mx, ps = U.err01(a, b)
             assert mx <= MAX_ABS_01 and ps >= MIN_PSNR, (size, mx, ps)
+
+
+def test_fp16_token_handover_is_bit_exact(monkeypatch):
+    """The fused tail kernel hands the local ViT's tokens to the merge convolution as fp16 (CFEN_TOK16, default on); the
+    merge loader rounded the fp32 tokens to fp16 with the same instruction before, so the outputs must not change by a bit."""
+    x = orc.make_inputs(512, [1, 2])[1].cuda()
+    outs = []
+    for v in ("1", "0"):
+        monkeypatch.setenv("CFEN_TOK16", v)
+        gnet, sd0, sd1, x0 = _gpu_net(4, 512)
+        with torch.no_grad():
+            outs.append([o.clone() for o in gnet(x)])
+        torch.cuda.synchronize()
+        del gnet
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # ... and neither may the first-forward ActNorm initialisation (its statistics pass must read the tokens in the
+    # format they were written in)
+    sds = []
+    for v in ("1", "0"):
+        monkeypatch.setenv("CFEN_TOK16", v)
+        gnet, sd0, sd1, x0 = _gpu_net(4, 512, primed=False)
+        with torch.no_grad():
+            gnet(x0.cuda())
+        sds.append({k: t.clone() for k, t in gnet.state_dict().items() if ".1." in k or ".2." in k})
+        del gnet
+    assert all(torch.equal(sds[0][k], sds[1][k]) for k in sds[0])
 
 
 def test_siblings_at_large_inputs_vs_oracle():
