@@ -1096,7 +1096,7 @@ static int run_tail16(Run& r, const VitW& v, const __half* O, float* T, int M, _
   const int E = v.E, hid = v.hid;
   const CUtensorMap *to, *tt, *two, *t1, *t2, *m0, *m3;
   RET(get_tmap2(r.p, O, 2, M, E, 64, 128, &to));
-  if (Y16) RET(get_tmap2(r.p, Y16, 2, M, E, 32, 128, &tt));
+  if (Y16) RET(get_tmap2(r.p, Y16, 2, M, E, 64, 128, &tt));
   else RET(get_tmap2(r.p, T, 4, M, E, 32, 128, &tt));
   RET(get_tmap2(r.p, v.h_out, 2, E, E, 64, E, &two));
   RET(get_tmap2(r.p, v.h_1, 2, hid, E, 64, 64, &t1));

@@ -40,7 +40,7 @@ struct Tail16RArgs {
   const float *lng, *lnb;            // norm2 weight / bias [E]
   const float *b1, *b2, *bm0, *bm3;  // [hid], [E], [hid], [E]
   int M, hid;
-  int y16;                           // 1: the output tokens leave as fp16 (tmY maps an fp16 [M, E] matrix, box 32 x 128):
+  int y16;                           // 1: the output tokens leave as fp16 (tmY maps an fp16 [M, E] matrix, box 64 x 128, SWIZZLE_128B):
                                      // their only reader, the merge convolution, rounds them to fp16 anyway
 };
 
@@ -402,28 +402,38 @@ vit_tail16r_kernel(const __grid_constant__ CUtensorMap tmO, const __grid_constan
             tc::tmem_ld32(lane_addr + COL_A + 32 * i, v);
             tc::tmem_ld_wait();
             uint8_t* line = stage + i * 16384 + roff;
-            uint8_t* line16 = stage + i * 8192 + (roff >> 10) * 512 + ((roff >> 7) & 7) * 64;   // dense 64-byte fp16 rows
-            uint32_t hx[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 p = *reinterpret_cast<const float4*>(a.b2 + 32 * i + 4 * j);
-              const float4 r = *reinterpret_cast<const float4*>(a.bm3 + 32 * i + 4 * j);
-              float4 t;
-              t.x = __uint_as_float(v[4 * j + 0]) + (p.x + r.x); t.y = __uint_as_float(v[4 * j + 1]) + (p.y + r.y);
-              t.z = __uint_as_float(v[4 * j + 2]) + (p.z + r.z); t.w = __uint_as_float(v[4 * j + 3]) + (p.w + r.w);
-              if (a.y16) { hx[2 * j] = pack_half2(t.x, t.y); hx[2 * j + 1] = pack_half2(t.z, t.w); }
-              else *reinterpret_cast<float4*>(line + ((j ^ sw) << 4)) = t;
-            }
+            uint8_t* line16 = stage + (i >> 1) * 16384 + roff;   // fp16: 64-column SWIZZLE_128B boxes, as the operand tile Xa
             if (a.y16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(line16 + 16 * j) = make_uint4(hx[4 * j], hx[4 * j + 1], hx[4 * j + 2], hx[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) {     // 8 columns -> one 16-byte chunk
+                const float4 p0 = *reinterpret_cast<const float4*>(a.b2 + 32 * i + 8 * j), p1 = *reinterpret_cast<const float4*>(a.b2 + 32 * i + 8 * j + 4);
+                const float4 r0 = *reinterpret_cast<const float4*>(a.bm3 + 32 * i + 8 * j), r1 = *reinterpret_cast<const float4*>(a.bm3 + 32 * i + 8 * j + 4);
+                *reinterpret_cast<uint4*>(line16 + ((((i & 1) * 4 + j) ^ sw) << 4)) = make_uint4(
+                    pack_half2(__uint_as_float(v[8 * j + 0]) + (p0.x + r0.x), __uint_as_float(v[8 * j + 1]) + (p0.y + r0.y)),
+                    pack_half2(__uint_as_float(v[8 * j + 2]) + (p0.z + r0.z), __uint_as_float(v[8 * j + 3]) + (p0.w + r0.w)),
+                    pack_half2(__uint_as_float(v[8 * j + 4]) + (p1.x + r1.x), __uint_as_float(v[8 * j + 5]) + (p1.y + r1.y)),
+                    pack_half2(__uint_as_float(v[8 * j + 6]) + (p1.z + r1.z), __uint_as_float(v[8 * j + 7]) + (p1.w + r1.w)));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 p = *reinterpret_cast<const float4*>(a.b2 + 32 * i + 4 * j);
+                const float4 r = *reinterpret_cast<const float4*>(a.bm3 + 32 * i + 4 * j);
+                float4 t;
+                t.x = __uint_as_float(v[4 * j + 0]) + (p.x + r.x); t.y = __uint_as_float(v[4 * j + 1]) + (p.y + r.y);
+                t.z = __uint_as_float(v[4 * j + 2]) + (p.z + r.z); t.w = __uint_as_float(v[4 * j + 3]) + (p.w + r.w);
+                *reinterpret_cast<float4*>(line + ((j ^ sw) << 4)) = t;
+              }
             }
           }
           tc::fence_async_smem();
           tc::named_bar_sync(1, 128);
           if (warp == 2 && tc::elect_one()) {
-            for (int i = 0; i < NP; ++i) tc::tma_store_2d(&tmY, stage + i * (a.y16 ? 8192 : 16384), i * 32, m0);
+            if (a.y16) {
+              for (int i = 0; i < (E + 63) / 64; ++i) tc::tma_store_2d(&tmY, stage + i * 16384, i * 64, m0);   // columns >= E are clipped
+            } else {
+              for (int i = 0; i < NP; ++i) tc::tma_store_2d(&tmY, stage + i * 16384, i * 32, m0);
+            }
             tc::tma_store_commit();
             tc::tma_store_wait_read();
           }
