@@ -1234,16 +1234,19 @@ static int run_vit(Run& r, const VitW& v, TokWs& w, int nseq, const FrontSrc* sr
     }
     RET(run_gemm16(r, w.o16, v.h_out, w.t1, nullptr, M, E, E, nullptr, w.t1, nullptr, 0, 0, w.part));
     RET(run_ln16(r, w.t1, w.h16, v.ln2g, v.ln2b, M, E));
+    // (local ViT feeding the merge convolution: the last Linear emits the tokens as fp16 only, see run_tail16)
+    const bool y16 = tok16_ok && r.p->tok16 && all_maps16(r.p);
+    if (y16) { w.out_tokens = reinterpret_cast<const float*>(w.h16); w.out16 = true; }
     const int bm = 128 * mlp16_shape(E).MH;
     if (r.p->fuse_mlp && mlp16_supported(E, hid) && (M + bm - 1) / bm >= r.p->fuse_min_tiles * 2 / 3) {
       RET(run_mlp16(r, w.h16, v.h_1, v.b1, v.h_2, v.b2, w.t1, w.t1, w.x16, M, E, hid));
-      RET(run_mlp16(r, w.x16, v.h_m0, v.bm0, v.h_m3, v.bm3, w.t1, w.t1, nullptr, M, E, hid));
+      RET(run_mlp16(r, w.x16, v.h_m0, v.bm0, v.h_m3, v.bm3, w.t1, y16 ? nullptr : w.t1, y16 ? w.h16 : nullptr, M, E, hid));
       return 0;
     }
     RET(run_gemm16(r, w.h16, v.h_1, nullptr, w.f16, M, hid, E, v.b1, nullptr, nullptr, 0, 1, w.part));
     RET(run_gemm16(r, w.f16, v.h_2, w.t1, w.x16, M, E, hid, v.b2, w.t1, nullptr, 0, 0, w.part));
     RET(run_gemm16(r, w.x16, v.h_m0, nullptr, w.f16, M, hid, E, v.bm0, nullptr, nullptr, 0, 1, w.part));
-    RET(run_gemm16(r, w.f16, v.h_m3, w.t1, nullptr, M, E, hid, v.bm3, w.t1, nullptr, 0, 0, w.part));
+    RET(run_gemm16(r, w.f16, v.h_m3, y16 ? nullptr : w.t1, y16 ? w.h16 : nullptr, M, E, hid, v.bm3, w.t1, nullptr, 0, 0, w.part));
     return 0;
   }
   RET(run_gemm(r, w.t0, v.w_le, w.t1, M, E, E, v.b_le, w.t0, v.pos, v.L, 0));
@@ -1489,7 +1492,7 @@ static int run_block(Run& r, int si, const float* x, float* out) {
       tokenize_local_kernel<<<ew_blocks(n4), 256, 0, r.st>>>(x, L.lws.t0, L.lws.x16, r.nb, Hl, Hl, C, p->win, all_maps16(p));
       CU(cudaGetLastError());
     }
-    RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin));
+    RET(run_vit(r, p->lvit[si], L.lws, r.nb * nwin, nullptr, true));
   }
   RET(stream_edge(p, L.gst, main_st));
   const std::string name = "lgcat_conv_" + stage_tag(kStages[si]);
